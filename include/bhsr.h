@@ -1,0 +1,131 @@
+/* bhsr.h — C ABI of libbhsr.so: the B200 (sm_100a) kernels behind the RRDBNet x4 feature
+ * extractor and the feature-aggregation height head.
+ *
+ * The reference (lauraset/Super-resolution-building-height-estimation) has no FFI of its own:
+ * its hot path is a chain of stock torch.nn calls.  Each entry point below replaces one such
+ * call site (cited as reference file:line); the Python nn.Module mirrors in
+ * super-resolution-building-height-estimation_b200/ bind these with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (the library never allocates, frees or keeps device memory past a call);
+ *   - every function enqueues on the CUDA stream passed as `stream` (a cudaStream_t cast to
+ *     void*), never synchronises, and is CUDA-graph capturable;
+ *   - return 0 on success, a negative BHSR_E* code otherwise; bhsr_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread;
+ *   - activations between kernels live in "planes": NHWC fp16 arrays [NB][H][W][C] holding the
+ *     high half of an fp32 value (`hi`) and, optionally, the residual (value-hi)*2^11 (`lo`).
+ *     hi + lo*2^-11 reproduces the fp32 value to ~22 bits; the `exact` numerics mode feeds both
+ *     planes to the tensor cores (3 fp16 products), the `fast` mode feeds only `hi`.
+ */
+#ifndef BHSR_H_
+#define BHSR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BHSR_VERSION 100
+
+enum {
+  BHSR_OK = 0,
+  BHSR_EINVAL = -1,   /* bad argument / unsupported shape */
+  BHSR_ECUDA = -2,    /* CUDA runtime or driver error (message has the CUDA string) */
+  BHSR_ENOGPU = -3    /* no sm_100 device */
+};
+
+/* numerics mode of the tensor-core convolutions */
+enum { BHSR_NUMERICS_EXACT_F16X3 = 0, BHSR_NUMERICS_FAST_F16 = 1 };
+
+/* epilogue flags of bhsr_conv_tc (OR-ed) */
+enum {
+  BHSR_EPI_LRELU = 1,      /* v = v > 0 ? v : 0.2 v            (rrdbnet_arch.py:137-140, 219-220) */
+  BHSR_EPI_RES1 = 2,       /* v = v * alpha1 + res1            (rrdbnet_arch.py:143, 217)         */
+  BHSR_EPI_RES2 = 4,       /* v = v * alpha2 + res2  (after 1) (rrdbnet_arch.py:167)              */
+  BHSR_EPI_OUT_NCHW_F32 = 8 /* write fp32 NCHW instead of fp16 planes (rrdbnet_arch.py:238)      */
+};
+
+int bhsr_version(void);
+const char* bhsr_last_error(void);
+/* number of SMs / compute capability of the current device; <0 on error */
+int bhsr_device_sm_count(void);
+int bhsr_device_cc(void);
+
+/* ------------------------------------------------------------------------------------------
+ * One 3x3 (or tap-table) convolution as an im2col-free implicit GEMM on tcgen05 tensor cores.
+ * Replaces nn.Conv2d(+LeakyReLU / residual / torch.cat / F.interpolate(nearest x2)) call sites:
+ *   ResidualDenseBlock.forward  SR/rrdbnet_arch.py:136-143
+ *   RRDB.forward                SR/rrdbnet_arch.py:162-167
+ *   RRDBNet.forward_feature     SR/rrdbnet_arch.py:225-240 (conv_body, conv_up1/2, conv_hr)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct BhsrConvTcDesc {
+  /* input planes: NHWC fp16 [nb][h][w][in_ctot]; channels [in_choff, in_choff+cin) are read */
+  const void* in_hi;
+  const void* in_lo;        /* used only by BHSR_NUMERICS_EXACT_F16X3 */
+  int32_t nb, h, w;         /* w must be a multiple of 64 */
+  int32_t in_ctot, in_choff, cin; /* cin multiple of 16; in_ctot multiple of 64 */
+  /* packed weights from bhsr_pack_conv_weights (same numerics mode, same tap table) */
+  const void* w_packed;
+  int32_t cout;             /* 32 or 64 */
+  const float* bias;        /* [cout] or NULL */
+  /* tap table: output(y,x) = sum_t W_t . in(y+dy[t], x+dx[t]); zero outside the image */
+  int32_t ntaps;            /* 1..9 */
+  int8_t dy[9], dx[9];
+  /* output: pixel (y,x) of the conv grid lands at (y*out_scale+out_oy, x*out_scale+out_ox)
+   * of an [nb][oh][ow] image; out_scale is 1, or 2 for the sub-pixel phases of nearest-x2 */
+  int32_t oh, ow, out_scale, out_oy, out_ox;
+  void* out_hi;             /* NHWC fp16 [nb][oh][ow][out_ctot], channels [out_choff, +cout) */
+  void* out_lo;             /* may be NULL */
+  int32_t out_ctot, out_choff;
+  float* out_f32;           /* with BHSR_EPI_OUT_NCHW_F32: [nb][out_ctot][oh][ow] fp32 */
+  int32_t epilogue;         /* BHSR_EPI_* flags */
+  float alpha1, alpha2;
+  const void* res1_hi; const void* res1_lo; int32_t res1_ctot, res1_choff;
+  const void* res2_hi; const void* res2_lo; int32_t res2_ctot, res2_choff;
+  int32_t numerics;         /* BHSR_NUMERICS_* */
+  int32_t mblocks;          /* 128-pixel accumulator blocks per tile: 1 or 2 (0 = auto) */
+  int32_t max_ctas;         /* 0 = one CTA per SM */
+  int32_t desc_mode;        /* 0 = default shared-memory descriptor mode (see conv_tc.cu) */
+} BhsrConvTcDesc;
+
+int bhsr_conv_tc(const BhsrConvTcDesc* desc, void* stream);
+
+/* bytes of the packed weight blob for one conv */
+size_t bhsr_packed_conv_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps, int32_t numerics);
+/* Pack an OIHW fp32 conv weight [cout][cin][3][3] (device) for bhsr_conv_tc.
+ * fold_phase < 0: plain 3x3, 9 taps in (ky,kx) row-major order, dy=ky-1, dx=kx-1.
+ * fold_phase = 2*a+b (a,b in {0,1}): the 2x2-tap phase (a,b) of conv3x3(nearest_x2(x)):
+ *   rows  a=0: dy=-1 <- w[ky=0], dy=0 <- w[1]+w[2];  a=1: dy=0 <- w[0]+w[1], dy=+1 <- w[2]
+ *   (same for columns with b); taps ordered (dy,dx) row-major.  SR/rrdbnet_arch.py:236-237. */
+int bhsr_pack_conv_weights(const float* w_oihw, int32_t cout, int32_t cin, int32_t fold_phase,
+                           int32_t numerics, void* w_packed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / precision plumbing around the tensor-core convs
+ * ------------------------------------------------------------------------------------------ */
+/* fp32 NCHW [nb][c][h][w] -> hi/lo planes NHWC [nb][h][w][ctot] at channel offset choff */
+int bhsr_nchw_f32_to_planes(const float* x, int32_t nb, int32_t c, int32_t h, int32_t w,
+                            void* out_hi, void* out_lo, int32_t ctot, int32_t choff, void* stream);
+/* planes -> fp32 NCHW (hi + lo*2^-11; lo may be NULL) */
+int bhsr_planes_to_nchw_f32(const void* in_hi, const void* in_lo, int32_t nb, int32_t c, int32_t h,
+                            int32_t w, int32_t ctot, int32_t choff, float* y, void* stream);
+
+/* Direct fp32 3x3 convolution on CUDA cores for the thin ends of the net (K=27 or N=3):
+ * conv_first (SR/rrdbnet_arch.py:232) reads fp32 NCHW with an arbitrary batch/channel stride
+ * (so x[:, :3] views need no copy) and writes planes; conv_last (:222) reads planes and
+ * writes fp32 NCHW.  lrelu_in applies LeakyReLU(0.2) to the input (forward(): :221). */
+int bhsr_conv3x3_first(const float* x, int64_t x_stride_n, int64_t x_stride_c, int64_t x_stride_h,
+                       int64_t x_stride_w, int32_t nb, int32_t cin, int32_t h, int32_t w,
+                       const float* weight, const float* bias, int32_t cout, void* out_hi,
+                       void* out_lo, int32_t out_ctot, int32_t out_choff, void* stream);
+int bhsr_conv3x3_last(const void* in_hi, const void* in_lo, int32_t in_ctot, int32_t in_choff,
+                      int32_t nb, int32_t cin, int32_t h, int32_t w, int32_t lrelu_in,
+                      const float* weight, const float* bias, int32_t cout, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHSR_H_ */

@@ -1,0 +1,124 @@
+"""ctypes binding of libbhsr.so (C ABI declared in include/bhsr.h).
+
+The library is the product: if it is missing, or a call fails, this module raises — there is no
+PyTorch/CPU fallback anywhere in the package.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbhsr.so")
+
+NUMERICS_EXACT = 0  # BHSR_NUMERICS_EXACT_F16X3
+NUMERICS_FAST = 1   # BHSR_NUMERICS_FAST_F16
+NUMERICS = {"exact": NUMERICS_EXACT, "fast": NUMERICS_FAST}
+
+EPI_LRELU = 1
+EPI_RES1 = 2
+EPI_RES2 = 4
+EPI_OUT_NCHW_F32 = 8
+
+
+class BhsrError(RuntimeError):
+    pass
+
+
+class ConvTcDesc(C.Structure):
+    """Mirror of `BhsrConvTcDesc` (include/bhsr.h)."""
+
+    _fields_ = [
+        ("in_hi", C.c_void_p), ("in_lo", C.c_void_p),
+        ("nb", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("in_ctot", C.c_int32), ("in_choff", C.c_int32), ("cin", C.c_int32),
+        ("w_packed", C.c_void_p),
+        ("cout", C.c_int32),
+        ("bias", C.c_void_p),
+        ("ntaps", C.c_int32),
+        ("dy", C.c_int8 * 9), ("dx", C.c_int8 * 9),
+        ("oh", C.c_int32), ("ow", C.c_int32), ("out_scale", C.c_int32),
+        ("out_oy", C.c_int32), ("out_ox", C.c_int32),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("out_ctot", C.c_int32), ("out_choff", C.c_int32),
+        ("out_f32", C.c_void_p),
+        ("epilogue", C.c_int32),
+        ("alpha1", C.c_float), ("alpha2", C.c_float),
+        ("res1_hi", C.c_void_p), ("res1_lo", C.c_void_p),
+        ("res1_ctot", C.c_int32), ("res1_choff", C.c_int32),
+        ("res2_hi", C.c_void_p), ("res2_lo", C.c_void_p),
+        ("res2_ctot", C.c_int32), ("res2_choff", C.c_int32),
+        ("numerics", C.c_int32), ("mblocks", C.c_int32), ("max_ctas", C.c_int32),
+        ("desc_mode", C.c_int32),
+    ]
+
+
+# symbol -> (restype, argtypes); tests check every symbol of include/bhsr.h is listed here
+# and exported by the shared object.
+_SIGNATURES = {
+    "bhsr_version": (C.c_int, []),
+    "bhsr_last_error": (C.c_char_p, []),
+    "bhsr_device_sm_count": (C.c_int, []),
+    "bhsr_device_cc": (C.c_int, []),
+    "bhsr_conv_tc": (C.c_int, [C.POINTER(ConvTcDesc), C.c_void_p]),
+    "bhsr_packed_conv_weight_bytes": (C.c_size_t, [C.c_int32] * 4),
+    "bhsr_pack_conv_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p]),
+    "bhsr_nchw_f32_to_planes": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p,
+                                          C.c_int32, C.c_int32, C.c_void_p]),
+    "bhsr_planes_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 +
+                                [C.c_void_p, C.c_void_p]),
+    "bhsr_conv3x3_first": (C.c_int, [C.c_void_p] + [C.c_int64] * 4 + [C.c_int32] * 4 +
+                           [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                            C.c_int32, C.c_void_p]),
+    "bhsr_conv3x3_last": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 +
+                          [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load libbhsr.so (built by `__graft_entry__.build()` / `build.py`).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BhsrError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` — this package has no fallback path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc < 0:
+        msg = load().bhsr_last_error().decode("utf-8", "replace")
+        raise BhsrError(f"{what or 'bhsr call'} failed ({rc}): {msg}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise BhsrError(
+            f"{name} must be a CUDA tensor (got device {t.device}); the B200 kernels have no CPU "
+            "fallback — run the reference modules for a CPU oracle")

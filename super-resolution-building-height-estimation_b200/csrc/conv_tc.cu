@@ -1,0 +1,525 @@
+// conv_tc.cu — tap-table convolution as an im2col-free implicit GEMM on tcgen05 tensor cores.
+//
+// Replaces the nn.Conv2d (+LeakyReLU, +0.2-scaled residuals, +torch.cat, +F.interpolate) call
+// sites of the reference RRDBNet (SR/rrdbnet_arch.py:136-143, 162-167, 225-240).
+//
+// Formulation ("flat shifted GEMM").  An image strip 64 pixels wide is laid out in shared
+// memory as R rows x 66 columns (one halo column each side) x 64 channels, 128 bytes per pixel,
+// written by ONE TMA box load per 64-channel chunk (out-of-bounds rows/columns are zero-filled
+// by TMA, which is exactly the conv's zero padding).  In that pitch-66 "flat" pixel index f,
+// every filter tap (dy,dx) is a pure shift by dy*66+dx, so the A operand of tap t for 128
+// consecutive flat output positions is the SAME shared-memory tile read from a start address
+// shifted by (dy*66+dx)*128 bytes: the halo tile is loaded once and reused by all 9 taps
+// instead of nine separate im2col loads.  Two of every 66 flat positions are halo columns;
+// their accumulator rows are computed and discarded (3% of the MMA rows).
+//
+//   D[128 x N] (TMEM, fp32) += A_tap[128 x 16] (smem, fp16, K-major SW128) * W_tap[N x 16]^T
+//
+// Numerics.  fast: one fp16 product.  exact: activations and weights are split hi + lo*2^-11
+// and three products are accumulated: hi*hi into the main accumulator, hi*lo' and lo'*hi into
+// a second accumulator that the epilogue scales by 2^-11.  hi*hi and hi*lo' share the A
+// operand, so they are one MMA with the two weight tiles stacked along N (N -> 2N).
+//
+// Warp roles (224 threads, 1 CTA per SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer for activation halo tiles   (ring of 2 stages)
+//   warp 1 lane 0 : tcgen05.mma issuer; warp 1 also owns the TMEM allocation
+//   warps 2..5    : epilogue (TMEM -> registers -> bias/LeakyReLU/residual -> global)
+//   warp 6 lane 0 : TMA producer for weight tiles (ring of `wslots` per-tap slabs; when the
+//                   whole layer fits the ring the weights are loaded once and stay resident)
+// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace bhsr {
+
+constexpr int kPitch = 66;          // strip width 64 + 2 halo columns
+constexpr int kStrip = 64;
+constexpr int kThreads = 224;
+constexpr int kMaxWSlots = 32;
+constexpr int kSmemLimit = 232448;  // 227 KB
+
+struct ConvTcKernelParams {
+  int nb, h, w;
+  int n_strips, tiles_per_strip, total_tiles;
+  int in_choff, cin, n_chunks;
+  int ntaps;
+  int tap_shift[9];  // dy*66 + dx
+  int oh, ow, out_scale, out_oy, out_ox;
+  __half* out_hi;
+  __half* out_lo;
+  int out_ctot, out_choff;
+  float* out_f32;
+  const float* bias;
+  int epilogue;
+  float alpha1, alpha2;
+  const __half* res1_hi;
+  const __half* res1_lo;
+  int res1_ctot, res1_choff;
+  const __half* res2_hi;
+  const __half* res2_lo;
+  int res2_ctot, res2_choff;
+  int wslots, w_resident;
+  int desc_mode;
+};
+
+template <int MB>
+struct TileGeom {
+  static constexpr int kRows = (MB == 1) ? 5 : 7;  // halo tile rows covering 128*MB + 2*67 px
+  static constexpr int kTileBytesRaw = kRows * kPitch * 128;
+  static constexpr int kTileBytes = (kTileBytesRaw + 1023) / 1024 * 1024;
+};
+
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
+__device__ __forceinline__ void split_hi_lo(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
+}
+
+// Read 32 consecutive channels of a residual pixel (hi [+ lo]) and fold them into v[].
+__device__ __forceinline__ void add_residual32(float (&v)[32], float alpha, const __half* hi,
+                                               const __half* lo, size_t off) {
+  const uint4* ph = reinterpret_cast<const uint4*>(hi + off);
+  const uint4* pl = lo ? reinterpret_cast<const uint4*>(lo + off) : nullptr;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 a = __ldg(ph + q);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(ah[j]);
+      r[2 * j] = f.x;
+      r[2 * j + 1] = f.y;
+    }
+    if (pl) {
+      uint4 b = __ldg(pl + q);
+      const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(bh[j]);
+        r[2 * j] = fmaf(f.x, 1.f / 2048.f, r[2 * j]);
+        r[2 * j + 1] = fmaf(f.y, 1.f / 2048.f, r[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[q * 8 + j] = fmaf(v[q * 8 + j], alpha, r[j]);
+  }
+}
+
+template <int N, bool EXACT, int MB>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+               const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_w, const ConvTcKernelParams p) {
+  using G = TileGeom<MB>;
+  constexpr int ROWS_B = EXACT ? 2 * N : N;        // weight rows per tap slab (= TMEM columns)
+  constexpr int W_SLAB = ROWS_B * 128;             // bytes
+  constexpr int A_STAGE = G::kTileBytes * (EXACT ? 2 : 1);
+  constexpr int A_TX = G::kTileBytesRaw * (EXACT ? 2 : 1);
+  constexpr int ACC_COLS = MB * ROWS_B;            // TMEM columns per accumulator stage
+  constexpr int MT = 128 * MB;
+  static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+  constexpr uint32_t IDESC_WIDE = make_idesc_f16(ROWS_B);
+  constexpr uint32_t IDESC_N = make_idesc_f16(N);
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; the launcher reserves the slack.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_base = smem_base;
+  const uint32_t w_base = a_base + 2 * A_STAGE;
+  uint8_t* tail = smem + 2 * A_STAGE + p.wslots * W_SLAB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  // barrier indices
+  auto bar = [&](int i) { return smem_u32(bars + i); };
+  constexpr int B_AFULL = 0, B_AEMPTY = 2, B_TFULL = 4, B_TEMPTY = 6, B_WFULL = 8;
+  const int B_WEMPTY = B_WFULL + kMaxWSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_WFULL + 2 * kMaxWSlots);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(B_AFULL + i), 1);
+      mbar_init(bar(B_AEMPTY + i), 1);
+      mbar_init(bar(B_TFULL + i), 1);
+      mbar_init(bar(B_TEMPTY + i), 128);
+    }
+    for (int i = 0; i < p.wslots; ++i) {
+      mbar_init(bar(B_WFULL + i), 1);
+      mbar_init(bar(B_WEMPTY + i), 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_a_hi);
+    if (EXACT) tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (threadIdx.x < N) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int first_tile = blockIdx.x;
+  const int tile_step = gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------ activation producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const int t = tile % p.tiles_per_strip;
+        const int sn = tile / p.tiles_per_strip;
+        const int s = sn % p.n_strips;
+        const int n = sn / p.n_strips;
+        const int r0 = (t * MT) / kPitch - 1;
+        for (int c = 0; c < p.n_chunks; ++c, ++it) {
+          const int st = it & 1;
+          mbar_wait(bar(B_AEMPTY + st), ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(bar(B_AFULL + st), A_TX);
+          const uint32_t dst = a_base + st * A_STAGE;
+          tma_load_4d(dst, &tm_a_hi, bar(B_AFULL + st), p.in_choff + c * 64, s * kStrip - 1, r0, n);
+          if (EXACT)
+            tma_load_4d(dst + G::kTileBytes, &tm_a_lo, bar(B_AFULL + st), p.in_choff + c * 64,
+                        s * kStrip - 1, r0, n);
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------ weight producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      const int slabs = p.n_chunks * p.ntaps;
+      bool first = true;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        if (p.w_resident && !first) break;
+        for (int sl = 0; sl < slabs; ++sl, ++it) {
+          const int ws = it % p.wslots;
+          mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
+          mbar_expect_tx(bar(B_WFULL + ws), W_SLAB);
+          tma_load_2d(w_base + ws * W_SLAB, &tm_w, bar(B_WFULL + ws), 0, sl * ROWS_B);
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t a_it = 0, w_it = 0, tile_it = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+        const int t = tile % p.tiles_per_strip;
+        const int flat_mod = (t * MT) % kPitch;
+        const int as = tile_it & 1;
+        mbar_wait(bar(B_TEMPTY + as), ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * ACC_COLS;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < p.n_chunks; ++c, ++a_it) {
+          const int st = a_it & 1;
+          mbar_wait(bar(B_AFULL + st), (a_it >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = a_base + st * A_STAGE;
+          const int rem = p.cin - c * 64;
+          const int ksteps = rem >= 64 ? 4 : (rem >> 4);
+          for (int tap = 0; tap < p.ntaps; ++tap, ++w_it) {
+            int ws;
+            if (p.w_resident) {
+              ws = c * p.ntaps + tap;
+              if (tile_it == 0) {
+                mbar_wait(bar(B_WFULL + ws), 0);
+                tc_fence_after();
+              }
+            } else {
+              ws = w_it % p.wslots;
+              mbar_wait(bar(B_WFULL + ws), (w_it / p.wslots) & 1);
+              tc_fence_after();
+            }
+            const uint32_t w_addr = w_base + ws * W_SLAB;
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              // first flat row of this tap inside the halo tile (see file header)
+              const int row0 = flat_mod + kPitch + 1 + mb * 128 + p.tap_shift[tap];
+              const uint32_t a_row = a_hi + row0 * 128;
+              const uint32_t bo = p.desc_mode == 1 ? (row0 & 7) : 0;
+              const uint32_t d_acc = acc + mb * ROWS_B;
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t da = make_sw128_desc(a_row + k * 32, bo);
+                const uint64_t db = make_sw128_desc(w_addr + k * 32, 0);
+                const uint32_t acc_flag = accumulate | (uint32_t)(k > 0);
+                umma_f16_ss(d_acc, da, db, IDESC_WIDE, acc_flag);
+                if (EXACT) {
+                  const uint64_t dl = make_sw128_desc(a_row + G::kTileBytes + k * 32, bo);
+                  umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
+                }
+              }
+            }
+            accumulate = 1;
+            if (!p.w_resident) umma_commit(bar(B_WEMPTY + ws));
+          }
+          umma_commit(bar(B_AEMPTY + st));
+        }
+        umma_commit(bar(B_TFULL + as));
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    uint32_t tile_it = 0;
+    const bool nchw = (p.epilogue & BHSR_EPI_OUT_NCHW_F32) != 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+      const int t = tile % p.tiles_per_strip;
+      const int sn = tile / p.tiles_per_strip;
+      const int s = sn % p.n_strips;
+      const int n = sn / p.n_strips;
+      const int as = tile_it & 1;
+      mbar_wait(bar(B_TFULL + as), (tile_it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int f = t * MT + mb * 128 + row;
+        const int py = f / kPitch;
+        const int pc = f - py * kPitch;
+        const int px = s * kStrip + pc;
+        const bool valid = (pc < kStrip) && (py < p.h);
+        const size_t in_pix = (static_cast<size_t>(n) * p.h + py) * p.w + px;
+        const int oy = py * p.out_scale + p.out_oy;
+        const int ox = px * p.out_scale + p.out_ox;
+        const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS +
+                               mb * ROWS_B;
+#pragma unroll
+        for (int cc = 0; cc < N / 32; ++cc) {
+          uint32_t raw[32];
+          float v[32];
+          tmem_ld_32x32(t_row + cc * 32, raw);
+          if (EXACT) {
+            uint32_t rawl[32];
+            tmem_ld_32x32(t_row + N + cc * 32, rawl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = fmaf(__uint_as_float(rawl[j]), 1.f / 2048.f, __uint_as_float(raw[j]));
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += s_bias[cc * 32 + j];
+            if (p.epilogue & BHSR_EPI_LRELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
+            }
+            if (p.epilogue & BHSR_EPI_RES1)
+              add_residual32(v, p.alpha1, p.res1_hi, p.res1_lo,
+                             in_pix * p.res1_ctot + p.res1_choff + cc * 32);
+            if (p.epilogue & BHSR_EPI_RES2)
+              add_residual32(v, p.alpha2, p.res2_hi, p.res2_lo,
+                             in_pix * p.res2_ctot + p.res2_choff + cc * 32);
+            if (nchw) {
+              const size_t plane = static_cast<size_t>(p.oh) * p.ow;
+              float* o = p.out_f32 + (static_cast<size_t>(n) * p.out_ctot + p.out_choff + cc * 32) *
+                                         plane + static_cast<size_t>(oy) * p.ow + ox;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j * plane] = v[j];
+            } else {
+              const size_t off = out_pix * p.out_ctot + p.out_choff + cc * 32;
+              uint4* oh4 = reinterpret_cast<uint4*>(p.out_hi + off);
+              uint4* ol4 = p.out_lo ? reinterpret_cast<uint4*>(p.out_lo + off) : nullptr;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                __align__(16) __half hh[8];
+                __align__(16) __half ll[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) split_hi_lo(v[g * 8 + j], hh[j], ll[j]);
+                oh4[g] = *reinterpret_cast<const uint4*>(hh);
+                if (ol4) ol4[g] = *reinterpret_cast<const uint4*>(ll);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar(B_TEMPTY + as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+template <int MB>
+static constexpr int a_stage_bytes(bool exact) {
+  return TileGeom<MB>::kTileBytes * (exact ? 2 : 1);
+}
+
+static constexpr int kTailBytes = (8 + 2 * kMaxWSlots) * 8 + 16 + 64 * 4 + 64;
+
+static int make_act_map(CUtensorMap* tm, const void* base, int nb, int h, int w, int ctot,
+                        int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return BHSR_ECUDA;
+  cuuint64_t dims[4] = {(cuuint64_t)ctot, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)nb};
+  cuuint64_t strides[3] = {(cuuint64_t)ctot * 2, (cuuint64_t)w * ctot * 2,
+                           (cuuint64_t)h * w * ctot * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kPitch, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(act) -> %d", (int)r);
+  return 0;
+}
+
+static int make_weight_map(CUtensorMap* tm, const void* base, int total_rows, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return BHSR_ECUDA;
+  cuuint64_t dims[2] = {64, (cuuint64_t)total_rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(w) -> %d", (int)r);
+  return 0;
+}
+
+template <int N, bool EXACT, int MB>
+static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream) {
+  using G = TileGeom<MB>;
+  constexpr int ROWS_B = EXACT ? 2 * N : N;
+  constexpr int W_SLAB = ROWS_B * 128;
+  constexpr int A_STAGE = G::kTileBytes * (EXACT ? 2 : 1);
+  const int slabs = p.n_chunks * p.ntaps;
+  int avail = kSmemLimit - 1024 /*alignment slack*/ - 2 * A_STAGE - kTailBytes;
+  int wslots = avail / W_SLAB;
+  if (wslots > kMaxWSlots) wslots = kMaxWSlots;
+  if (wslots < 2) return set_error(BHSR_EINVAL, "conv_tc: no room for weight ring");
+  p.w_resident = slabs <= wslots ? 1 : 0;
+  if (p.w_resident) wslots = slabs;
+  p.wslots = wslots;
+  const int smem_bytes = 1024 + 2 * A_STAGE + wslots * W_SLAB + kTailBytes;
+
+  CUtensorMap tm_hi, tm_lo, tm_w;
+  int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows);
+  if (rc) return rc;
+  rc = make_act_map(&tm_lo, EXACT ? d.in_lo : d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows);
+  if (rc) return rc;
+  rc = make_weight_map(&tm_w, d.w_packed, slabs * ROWS_B, ROWS_B);
+  if (rc) return rc;
+
+  auto kern = conv_tc_kernel<N, EXACT, MB>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    BHSR_CUDA_CHECK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  int sms = device_sm_count();
+  if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
+  int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
+  kern<<<grid, kThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_w, p);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bhsr
+
+using namespace bhsr;
+
+extern "C" size_t bhsr_packed_conv_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps,
+                                                int32_t numerics) {
+  const int chunks = (cin + 63) / 64;
+  const int rows = numerics == BHSR_NUMERICS_EXACT_F16X3 ? 2 * cout : cout;
+  return static_cast<size_t>(chunks) * ntaps * rows * 64 * sizeof(__half);
+}
+
+extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
+  if (!dp) return set_error(BHSR_EINVAL, "conv_tc: null descriptor");
+  const BhsrConvTcDesc& d = *dp;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BHSR_REQUIRE(d.cout == 32 || d.cout == 64, "conv_tc: cout must be 32 or 64 (got %d)", d.cout);
+  BHSR_REQUIRE(d.w > 0 && d.w % kStrip == 0, "conv_tc: width must be a multiple of 64 (got %d)", d.w);
+  BHSR_REQUIRE(d.h > 0 && d.nb > 0, "conv_tc: empty input");
+  BHSR_REQUIRE(d.cin > 0 && d.cin % 16 == 0, "conv_tc: cin must be a multiple of 16 (got %d)", d.cin);
+  BHSR_REQUIRE(d.in_ctot % 64 == 0 && d.in_choff % 64 == 0 &&
+                   d.in_choff + (d.cin + 63) / 64 * 64 <= d.in_ctot,
+               "conv_tc: input channel window [%d,+%d) must sit on 64-channel chunks of %d",
+               d.in_choff, d.cin, d.in_ctot);
+  BHSR_REQUIRE(d.ntaps >= 1 && d.ntaps <= 9, "conv_tc: ntaps out of range");
+  BHSR_REQUIRE(d.out_scale == 1 || d.out_scale == 2, "conv_tc: out_scale must be 1 or 2");
+  BHSR_REQUIRE(d.oh >= d.h * d.out_scale && d.ow >= d.w * d.out_scale, "conv_tc: output too small");
+  BHSR_REQUIRE(d.in_hi && d.w_packed, "conv_tc: null input");
+  const bool exact = d.numerics == BHSR_NUMERICS_EXACT_F16X3;
+  BHSR_REQUIRE(!exact || d.in_lo, "conv_tc: exact numerics needs the lo plane");
+  const bool nchw = (d.epilogue & BHSR_EPI_OUT_NCHW_F32) != 0;
+  BHSR_REQUIRE(nchw ? d.out_f32 != nullptr : d.out_hi != nullptr, "conv_tc: null output");
+  BHSR_REQUIRE(nchw || (d.out_ctot % 8 == 0 && d.out_choff % 8 == 0),
+               "conv_tc: output channel offset/stride must be multiples of 8");
+  if (d.epilogue & BHSR_EPI_RES1)
+    BHSR_REQUIRE(d.res1_hi && d.out_scale == 1 && d.res1_ctot % 8 == 0 && d.res1_choff % 8 == 0,
+                 "conv_tc: bad res1");
+  if (d.epilogue & BHSR_EPI_RES2)
+    BHSR_REQUIRE(d.res2_hi && d.out_scale == 1 && d.res2_ctot % 8 == 0 && d.res2_choff % 8 == 0,
+                 "conv_tc: bad res2");
+  for (int t = 0; t < d.ntaps; ++t)
+    BHSR_REQUIRE(d.dy[t] >= -1 && d.dy[t] <= 1 && d.dx[t] >= -1 && d.dx[t] <= 1,
+                 "conv_tc: tap offsets must be in [-1,1]");
+
+  int mb = d.mblocks;
+  if (mb == 0) mb = exact ? 1 : 2;
+  BHSR_REQUIRE(mb == 1 || (mb == 2 && !exact), "conv_tc: mblocks must be 1, or 2 in fast mode");
+
+  ConvTcKernelParams p{};
+  p.nb = d.nb; p.h = d.h; p.w = d.w;
+  p.n_strips = d.w / kStrip;
+  const int mt = 128 * mb;
+  p.tiles_per_strip = (d.h * kPitch + mt - 1) / mt;
+  p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;
+  p.in_choff = d.in_choff; p.cin = d.cin; p.n_chunks = (d.cin + 63) / 64;
+  p.ntaps = d.ntaps;
+  for (int t = 0; t < d.ntaps; ++t) p.tap_shift[t] = d.dy[t] * kPitch + d.dx[t];
+  p.oh = d.oh; p.ow = d.ow; p.out_scale = d.out_scale; p.out_oy = d.out_oy; p.out_ox = d.out_ox;
+  p.out_hi = static_cast<__half*>(d.out_hi);
+  p.out_lo = static_cast<__half*>(d.out_lo);
+  p.out_ctot = d.out_ctot; p.out_choff = d.out_choff;
+  p.out_f32 = d.out_f32;
+  p.bias = d.bias;
+  p.epilogue = d.epilogue;
+  p.alpha1 = d.alpha1; p.alpha2 = d.alpha2;
+  p.res1_hi = static_cast<const __half*>(d.res1_hi);
+  p.res1_lo = static_cast<const __half*>(d.res1_lo);
+  p.res1_ctot = d.res1_ctot; p.res1_choff = d.res1_choff;
+  p.res2_hi = static_cast<const __half*>(d.res2_hi);
+  p.res2_lo = static_cast<const __half*>(d.res2_lo);
+  p.res2_ctot = d.res2_ctot; p.res2_choff = d.res2_choff;
+  p.desc_mode = d.desc_mode;
+
+  if (d.cout == 32) {
+    if (exact) return launch<32, true, 1>(d, p, stream);
+    return mb == 2 ? launch<32, false, 2>(d, p, stream) : launch<32, false, 1>(d, p, stream);
+  } else {
+    if (exact) return launch<64, true, 1>(d, p, stream);
+    return mb == 2 ? launch<64, false, 2>(d, p, stream) : launch<64, false, 1>(d, p, stream);
+  }
+}

@@ -1,0 +1,172 @@
+"""Development probe for the tcgen05 conv kernel (run on a B200 through gpurun).
+
+Usage: python tools/probe_conv_tc.py <case> [desc_mode]
+Each case runs in its own process (a device trap poisons the CUDA context), prints one JSON
+line with the max error against a float64 torch conv of the same (decoded) operands.
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+
+import bhsr  # noqa: F401
+from bhsr import ops
+from bhsr._lib import NUMERICS_EXACT, NUMERICS_FAST
+
+
+def split(v):
+    hi = v.to(torch.float16)
+    lo = ((v - hi.float()) * 2048.0).to(torch.float16)
+    return hi, lo
+
+
+def to_planes(x, ctot, choff=0):
+    """fp32 NCHW -> (hi, lo) NHWC planes with ctot channels (others random finite)."""
+    nb, c, h, w = x.shape
+    full = torch.randn(nb, h, w, ctot, device=x.device) * 0.5
+    full[..., choff:choff + c] = x.permute(0, 2, 3, 1)
+    return split(full)
+
+
+def decode(hi, lo, exact):
+    v = hi.double()
+    if exact and lo is not None:
+        v = v + lo.double() / 2048.0
+    return v.permute(0, 3, 1, 2).contiguous()
+
+
+def run_case(name, desc_mode):
+    torch.manual_seed(1234)
+    dev = "cuda"
+    cfg = dict(nb=2, h=64, w=64, cin=64, ctot=192, cout=32, exact=False, mb=1, lrelu=True,
+               res=0, up=False, nchw=False, time=False)
+    cases = {
+        "fast32": {},
+        "fast32_mb2": dict(mb=2),
+        "exact32": dict(exact=True),
+        "fast64_c192": dict(cout=64, cin=192, lrelu=False, res=2),
+        "exact64_c192": dict(cout=64, cin=192, exact=True, lrelu=False, res=2),
+        "exact32_c96": dict(cin=96, exact=True),
+        "fast32_c160_mb2": dict(cin=160, mb=2),
+        "up_exact": dict(cout=64, cin=64, ctot=64, exact=True, up=True),
+        "up_fast_mb2": dict(cout=64, cin=64, ctot=64, mb=2, up=True),
+        "hr_exact_nchw": dict(nb=1, h=256, w=256, cout=64, cin=64, ctot=64, exact=True, lrelu=False, nchw=True),
+        "hr_fast_nchw_mb2": dict(nb=1, h=256, w=256, cout=64, cin=64, ctot=64, mb=2, lrelu=False, nchw=True),
+        "odd_h": dict(nb=3, h=40, w=128, cin=128, exact=True),
+        "time_fast32": dict(nb=64, mb=2, time=True),
+        "time_exact32": dict(nb=64, exact=True, time=True),
+        "time_fast64_c192": dict(nb=64, cout=64, cin=192, mb=2, lrelu=False, res=1, time=True),
+        "time_exact64_c192": dict(nb=64, cout=64, cin=192, exact=True, lrelu=False, res=1, time=True),
+        "time_fast32_mb1": dict(nb=64, mb=1, time=True),
+    }
+    cfg.update(cases[name])
+    nb, h, w, cin, ctot, cout = (cfg[k] for k in ("nb", "h", "w", "cin", "ctot", "cout"))
+    exact = cfg["exact"]
+    numerics = NUMERICS_EXACT if exact else NUMERICS_FAST
+    x = torch.rand(nb, cin, h, w, device=dev) * 2 - 0.5
+    wt = torch.randn(cout, cin, 3, 3, device=dev) * (0.3 / (cin ** 0.5))
+    bias = torch.randn(cout, device=dev) * 0.1
+    in_hi, in_lo = to_planes(x, ctot)
+    xd = decode(in_hi, in_lo, exact)[:, :cin]
+    wd = wt.double() if exact else wt.to(torch.float16).double()
+    res = []
+    for i in range(cfg["res"]):
+        r = torch.randn(nb, 64, h, w, device=dev)
+        res.append(to_planes(r, 64))
+
+    if cfg["up"]:
+        oh, ow = 2 * h, 2 * w
+        ref = F.conv2d(F.interpolate(xd, scale_factor=2, mode="nearest"), wt.double() if exact else None,
+                       bias.double(), padding=1) if exact else None
+        out_hi = torch.zeros(nb, oh, ow, cout, dtype=torch.float16, device=dev)
+        out_lo = torch.zeros_like(out_hi)
+        refs = torch.zeros(nb, cout, oh, ow, dtype=torch.float64, device=dev)
+        for a in range(2):
+            for b in range(2):
+                wp = ops.pack_conv_weights(wt, numerics, fold_phase=2 * a + b)
+                ops.conv_tc(in_hi, in_lo, 0, cin, wp, cout, bias, ops.phase_taps(a, b), out_hi, out_lo,
+                            out_scale=2, out_oy=a, out_ox=b, lrelu=cfg["lrelu"], numerics=numerics,
+                            mblocks=cfg["mb"], desc_mode=desc_mode)
+        if not exact:
+            # fast mode folds fp32 weight sums then rounds to fp16: rebuild that reference per phase
+            for a in range(2):
+                for b in range(2):
+                    taps = ops.phase_taps(a, b)
+                    acc = torch.zeros(nb, cout, h, w, dtype=torch.float64, device=dev)
+                    xp = F.pad(xd, (1, 1, 1, 1))
+                    for iy in range(2):
+                        for ix in range(2):
+                            kys = ([0], [1, 2]) if a == 0 else ([0, 1], [2])
+                            kxs = ([0], [1, 2]) if b == 0 else ([0, 1], [2])
+                            wf = sum(wt[:, :, ky, kx] for ky in kys[iy] for kx in kxs[ix])
+                            wf = wf.to(torch.float16).double()
+                            dy, dx = taps[iy * 2 + ix]
+                            patch = xp[:, :, 1 + dy:1 + dy + h, 1 + dx:1 + dx + w]
+                            acc += torch.einsum("oc,nchw->nohw", wf, patch)
+                    refs[:, :, a::2, b::2] = acc + bias.double().view(1, -1, 1, 1)
+            ref = refs
+        if cfg["lrelu"]:
+            ref = F.leaky_relu(ref, 0.2)
+        got = decode(out_hi, out_lo, True)
+    else:
+        ref = F.conv2d(xd, wd, bias.double(), padding=1)
+        if cfg["lrelu"]:
+            ref = F.leaky_relu(ref, 0.2)
+        kw = {}
+        if cfg["res"] >= 1:
+            ref = ref * 0.2 + decode(*res[0], True)
+            kw.update(res1=(res[0][0], res[0][1], 0), alpha1=0.2)
+        if cfg["res"] >= 2:
+            ref = ref * 0.2 + decode(*res[1], True)
+            kw.update(res2=(res[1][0], res[1][1], 0), alpha2=0.2)
+        wp = ops.pack_conv_weights(wt, numerics)
+        if cfg["nchw"]:
+            out = torch.zeros(nb, cout, h, w, device=dev)
+            call = lambda: ops.conv_tc(in_hi, in_lo, 0, cin, wp, cout, bias, ops.PLAIN_TAPS, None, None,
+                                       out_f32=out, lrelu=cfg["lrelu"], numerics=numerics,
+                                       mblocks=cfg["mb"], desc_mode=desc_mode, **kw)
+        else:
+            octot = 192
+            out_hi = torch.zeros(nb, h, w, octot, dtype=torch.float16, device=dev)
+            out_lo = torch.zeros_like(out_hi)
+            call = lambda: ops.conv_tc(in_hi, in_lo, 0, cin, wp, cout, bias, ops.PLAIN_TAPS, out_hi, out_lo,
+                                       out_choff=64, lrelu=cfg["lrelu"], numerics=numerics,
+                                       mblocks=cfg["mb"], desc_mode=desc_mode, **kw)
+        call()
+        torch.cuda.synchronize()
+        if cfg["nchw"]:
+            got = out.double()
+        else:
+            got = decode(out_hi, out_lo, True)[:, 64:64 + cout]
+            untouched = float(out_hi[..., :64].abs().max()) + float(out_hi[..., 64 + cout:].abs().max())
+        if cfg["time"]:
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            iters = 20
+            for _ in range(iters):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            flops = 2.0 * nb * h * w * cout * cin * 9
+            print(json.dumps({"case": name, "ms": ms, "tflops": flops / ms / 1e9}))
+    torch.cuda.synchronize()
+    err = (got - ref).abs()
+    tol = 1e-5 + 1e-4 * ref.abs()  # loose here: fp16 hi/lo output quantisation is ~2^-22 relative
+    out = {"case": name, "desc_mode": desc_mode, "max_abs_err": float(err.max()),
+           "max_ref": float(ref.abs().max()), "frac_bad": float((err > tol).double().mean()),
+           "rel_l2": float((got - ref).norm() / ref.norm())}
+    if not cfg["up"] and not cfg["nchw"]:
+        out["untouched_abs"] = untouched
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    run_case(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
