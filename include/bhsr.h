@@ -65,7 +65,7 @@ typedef struct BhsrConvTcDesc {
   /* input planes: NHWC fp16 [nb][h][w][in_ctot]; channels [in_choff, in_choff+cin) are read */
   const void* in_hi;
   const void* in_lo;        /* used only by BHSR_NUMERICS_EXACT_F16X3 */
-  int32_t nb, h, w;         /* w must be a multiple of 64 */
+  int32_t nb, h, w;         /* any size; the kernel walks 64-pixel-wide strips */
   int32_t in_ctot, in_choff, cin; /* cin multiple of 16; in_ctot multiple of 64 */
   /* packed weights from bhsr_pack_conv_weights (same numerics mode, same tap table) */
   const void* w_packed;
@@ -124,6 +124,40 @@ int bhsr_conv3x3_first(const float* x, int64_t x_stride_n, int64_t x_stride_c, i
 int bhsr_conv3x3_last(const void* in_hi, const void* in_lo, int32_t in_ctot, int32_t in_choff,
                       int32_t nb, int32_t cin, int32_t h, int32_t w, int32_t lrelu_in,
                       const float* weight, const float* bias, int32_t cout, float* y, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-network entry: RRDBNet (SR/rrdbnet_arch.py:170-240; same arithmetic as SR/RRDBNet.py:53-78)
+ * num_feat = 64, num_grow_ch = 32 (the only widths the reference instantiates).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct BhsrRrdbNetDesc {
+  int32_t num_in_ch;        /* channels seen by conv_first (after pixel_unshuffle, if any) */
+  int32_t num_out_ch;       /* conv_last outputs (<= 8); only used by bhsr_rrdbnet_forward(feature=0) */
+  int32_t num_block;
+  int32_t numerics;         /* BHSR_NUMERICS_* */
+  int32_t nb, h, w;         /* LR batch and tile size seen by conv_first */
+  const float* conv_first_w; const float* conv_first_b;   /* raw fp32 OIHW / [64] */
+  const float* conv_last_w;  const float* conv_last_b;    /* raw fp32 OIHW / [num_out_ch] */
+  const void* packed;       /* blob from bhsr_rrdbnet_pack (same num_block, numerics) */
+  const float* biases;      /* blob from bhsr_rrdbnet_pack */
+  void* workspace;          /* >= bhsr_rrdbnet_workspace_bytes(nb,h,w, feature) bytes, 1024-aligned */
+  size_t workspace_bytes;
+  int32_t mblocks;          /* forwarded to bhsr_conv_tc (0 = auto) */
+} BhsrRrdbNetDesc;
+
+size_t bhsr_rrdbnet_packed_bytes(int32_t num_block, int32_t numerics);
+size_t bhsr_rrdbnet_bias_floats(int32_t num_block);
+size_t bhsr_rrdbnet_workspace_bytes(int32_t nb, int32_t h, int32_t w, int32_t feature_only);
+/* params: device pointers to the fp32 tensors of the tensor-core convs in state_dict order —
+ * for each block b, rdb r, conv c: weight, bias; then conv_body, conv_up1, conv_up2, conv_hr
+ * (weight, bias each): 2 * (15*num_block + 4) pointers. */
+int bhsr_rrdbnet_pack(const float* const* params, int32_t num_block, int32_t numerics,
+                      void* packed, float* biases, void* stream);
+/* x: fp32 [nb][num_in_ch][h][w] with element strides (sn, sc, sh, sw) — views such as x[:, :3]
+ * need no copy.  feature != 0: y = forward_feature(x), fp32 NCHW [nb][64][4h][4w]
+ * (rrdbnet_arch.py:225-240); feature == 0: y = forward(x), [nb][num_out_ch][4h][4w] (:208-223). */
+int bhsr_rrdbnet_forward(const BhsrRrdbNetDesc* desc, const float* x, int64_t sn, int64_t sc,
+                         int64_t sh, int64_t sw, float* y, int32_t feature, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,21 @@ class ConvTcDesc(C.Structure):
     ]
 
 
+class RrdbNetDesc(C.Structure):
+    """Mirror of `BhsrRrdbNetDesc` (include/bhsr.h)."""
+
+    _fields_ = [
+        ("num_in_ch", C.c_int32), ("num_out_ch", C.c_int32), ("num_block", C.c_int32),
+        ("numerics", C.c_int32),
+        ("nb", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("conv_first_w", C.c_void_p), ("conv_first_b", C.c_void_p),
+        ("conv_last_w", C.c_void_p), ("conv_last_b", C.c_void_p),
+        ("packed", C.c_void_p), ("biases", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("mblocks", C.c_int32),
+    ]
+
+
 # symbol -> (restype, argtypes); tests check every symbol of include/bhsr.h is listed here
 # and exported by the shared object.
 _SIGNATURES = {
@@ -76,6 +91,13 @@ _SIGNATURES = {
                             C.c_int32, C.c_void_p]),
     "bhsr_conv3x3_last": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 +
                           [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bhsr_rrdbnet_packed_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "bhsr_rrdbnet_bias_floats": (C.c_size_t, [C.c_int32]),
+    "bhsr_rrdbnet_workspace_bytes": (C.c_size_t, [C.c_int32] * 4),
+    "bhsr_rrdbnet_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "bhsr_rrdbnet_forward": (C.c_int, [C.POINTER(RrdbNetDesc), C.c_void_p] + [C.c_int64] * 4 +
+                             [C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -30,6 +30,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -251,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
               // first flat row of this tap inside the halo tile (see file header)
               const int row0 = flat_mod + kPitch + 1 + mb * 128 + p.tap_shift[tap];
               const uint32_t a_row = a_hi + row0 * 128;
-              const uint32_t bo = p.desc_mode == 1 ? (row0 & 7) : 0;
+              const uint32_t bo = 0;  // swizzle is a function of absolute smem address bits (measured)
               const uint32_t d_acc = acc + mb * ROWS_B;
               for (int k = 0; k < ksteps; ++k) {
                 const uint64_t da = make_sw128_desc(a_row + k * 32, bo);
@@ -292,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int py = f / kPitch;
         const int pc = f - py * kPitch;
         const int px = s * kStrip + pc;
-        const bool valid = (pc < kStrip) && (py < p.h);
+        const bool valid = (pc < kStrip) && (py < p.h) && (px < p.w);
         const size_t in_pix = (static_cast<size_t>(n) * p.h + py) * p.w + px;
         const int oy = py * p.out_scale + p.out_oy;
         const int ox = px * p.out_scale + p.out_ox;
@@ -415,6 +416,10 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
   if (wslots > kMaxWSlots) wslots = kMaxWSlots;
   if (wslots < 2) return set_error(BHSR_EINVAL, "conv_tc: no room for weight ring");
   p.w_resident = slabs <= wslots ? 1 : 0;
+  {
+    static const char* force = getenv("BHSR_DEBUG_FORCE_STREAM");  // debug knob: never resident
+    if (force && force[0] == '1' && wslots >= 2) { p.w_resident = 0; if (wslots > 4) wslots = 4; }
+  }
   if (p.w_resident) wslots = slabs;
   p.wslots = wslots;
   const int smem_bytes = 1024 + 2 * A_STAGE + wslots * W_SLAB + kTailBytes;
@@ -459,8 +464,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   const BhsrConvTcDesc& d = *dp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BHSR_REQUIRE(d.cout == 32 || d.cout == 64, "conv_tc: cout must be 32 or 64 (got %d)", d.cout);
-  BHSR_REQUIRE(d.w > 0 && d.w % kStrip == 0, "conv_tc: width must be a multiple of 64 (got %d)", d.w);
-  BHSR_REQUIRE(d.h > 0 && d.nb > 0, "conv_tc: empty input");
+  BHSR_REQUIRE(d.w > 0 && d.h > 0 && d.nb > 0, "conv_tc: empty input");
   BHSR_REQUIRE(d.cin > 0 && d.cin % 16 == 0, "conv_tc: cin must be a multiple of 16 (got %d)", d.cin);
   BHSR_REQUIRE(d.in_ctot % 64 == 0 && d.in_choff % 64 == 0 &&
                    d.in_choff + (d.cin + 63) / 64 * 64 <= d.in_ctot,
@@ -492,7 +496,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
 
   ConvTcKernelParams p{};
   p.nb = d.nb; p.h = d.h; p.w = d.w;
-  p.n_strips = d.w / kStrip;
+  p.n_strips = (d.w + kStrip - 1) / kStrip;
   const int mt = 128 * mb;
   p.tiles_per_strip = (d.h * kPitch + mt - 1) / mt;
   p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;

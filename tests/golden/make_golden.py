@@ -1,0 +1,194 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE modules on CPU.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+The reference is imported from where it lies (nothing is copied): SR/rrdbnet_arch.py,
+SR/RRDBNet.py, SR/HRfuse.py and aggregate_utils.py import after stubbing their unused
+matplotlib / rasterio imports; mymodels.py does not parse (IndentationError at line 467), so
+its hot class is exec'd from the source slice lines 7-14 + 231-337 with the smp names bound to
+this repo's stand-in encoder/decoder (smp is a third-party dependency absent from the reference
+tree).  Inputs and parameters come from tests/golden/synth.py.
+
+Also stages the one real checkpoint the reference ships (SR/pretrained/RealESRGAN_x4plus.pth)
+into oracle/_ref/ (git-ignored; travels to the GPU box) for the realistic-weights parity test.
+"""
+import os
+import shutil
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("BHSR_REFERENCE", "/root/reference")
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+import synth  # noqa: E402
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "rasterio"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    sys.path.insert(0, REF)
+    # make sure `SR` resolves to the reference package, not to this repo's drop-in of the same name
+    for k in [k for k in sys.modules if k == "SR" or k.startswith("SR.") or k in ("aggregate_utils", "mymodels")]:
+        del sys.modules[k]
+    import importlib.util
+
+    def load(modname, relpath, package_dir=None):
+        spec = importlib.util.spec_from_file_location(
+            modname, os.path.join(REF, relpath),
+            submodule_search_locations=[package_dir] if package_dir else None)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = m
+        spec.loader.exec_module(m)
+        return m
+
+    sr = types.ModuleType("SR")
+    sr.__path__ = [os.path.join(REF, "SR")]
+    sys.modules["SR"] = sr
+    load("SR.srloss", "SR/srloss.py")
+    arch = load("SR.rrdbnet_arch", "SR/rrdbnet_arch.py")
+    old = load("SR.RRDBNet", "SR/RRDBNet.py")
+    hrf = load("SR.HRfuse", "SR/HRfuse.py")
+    agg = load("aggregate_utils", "aggregate_utils.py")
+    return arch, old, hrf, agg
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def load_sd(module, sd):
+    module.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+    return module
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    arch, old, hrf, agg = import_reference()
+    out = {}
+
+    # ---------------------------------------------------------------- RRDBNet, 2 blocks
+    with torch.no_grad():
+        sd = synth.rrdbnet_state(num_block=2, seed=11)
+        net = load_sd(arch.RRDBNet(3, 3, scale=4, num_feat=64, num_block=2, num_grow_ch=32), sd).eval()
+        x = synth.tiles(2, 3, seed=1337)
+        fea = net.forward_feature(t(x)).numpy()
+        img = net.forward(t(x)).numpy()
+        out["rrdb2_feature_sub"] = synth.subsample(fea)
+        out["rrdb2_feature_stats"] = synth.stats(fea)
+        out["rrdb2_forward_sub"] = synth.subsample(img, 1, 4)
+        out["rrdb2_forward_stats"] = synth.stats(img)
+        # one full-resolution tile corner so index-path errors cannot hide in the subsampling
+        out["rrdb2_feature_corner"] = np.ascontiguousarray(fea[0, :8, :20, :20])
+        out["rrdb2_feature_edge"] = np.ascontiguousarray(fea[1, 56:, 236:, 236:])
+        print("rrdb2 feature range", fea.min(), fea.max())
+
+        # ------------------------------------------------------------ RRDBNet, 23 blocks
+        sd = synth.rrdbnet_state(num_block=23, seed=23)
+        net = load_sd(arch.RRDBNet(3, 3, scale=4, num_feat=64, num_block=23, num_grow_ch=32), sd).eval()
+        nparams = sum(p.numel() for p in net.parameters())
+        assert nparams == 16697987, nparams  # rrdbnet_arch.py:658 "generator 16.70M"
+        x = synth.tiles(1, 3, seed=4242)
+        fea = net.forward_feature(t(x)).numpy()
+        out["rrdb23_feature_sub"] = synth.subsample(fea)
+        out["rrdb23_feature_stats"] = synth.stats(fea)
+        print("rrdb23 feature range", fea.min(), fea.max())
+
+        # ------------------------------------------------------------ real checkpoint
+        ckpt = os.path.join(REF, "SR", "pretrained", "RealESRGAN_x4plus.pth")
+        if os.path.exists(ckpt):
+            dst = os.path.join(ROOT, "oracle", "_ref")
+            os.makedirs(dst, exist_ok=True)
+            if not os.path.exists(os.path.join(dst, "RealESRGAN_x4plus.pth")):
+                shutil.copy(ckpt, os.path.join(dst, "RealESRGAN_x4plus.pth"))
+            w = torch.load(ckpt, map_location="cpu")["params_ema"]
+            net.load_state_dict(w, strict=True)
+            import cv2
+            imgs = []
+            tdir = os.path.join(REF, "SR", "testimg")
+            for f in sorted(os.listdir(tdir))[:2]:
+                im = cv2.cvtColor(cv2.imread(os.path.join(tdir, f)), cv2.COLOR_BGR2RGB)
+                imgs.append(im)
+            u8 = np.stack(imgs)  # [2,64,64,3] uint8, rrdbnet_arch.py:660-663
+            xin = torch.from_numpy(u8).float().permute(0, 3, 1, 2) / 255.0
+            fea = net.forward_feature(xin).numpy()
+            out["x4plus_input_u8"] = u8
+            out["x4plus_feature_sub"] = synth.subsample(fea)
+            out["x4plus_feature_stats"] = synth.stats(fea)
+            print("x4plus feature range", fea.min(), fea.max())
+
+        # ------------------------------------------------------------ old-style class, scale variants
+        sd = synth.rrdbnet_state(num_in_ch=4, num_block=1, seed=5)
+        net = load_sd(old.RRDBNet(in_nc=4, out_nc=3, nf=64, nb=1, gc=32), synth.to_old_rrdbnet_keys(sd)).eval()
+        x = synth.tiles(2, 4, seed=99)  # SR/RRDBNet.py:82 smoke shape
+        out["old_rrdb1_forward_sub"] = synth.subsample(net(t(x)).numpy(), 1, 4)
+        for sc, hw in ((2, 128), (1, 256)):
+            sd = synth.rrdbnet_state(num_in_ch=3, scale=sc, num_block=1, seed=50 + sc)
+            net = load_sd(arch.RRDBNet(3, 3, scale=sc, num_feat=64, num_block=1, num_grow_ch=32), sd).eval()
+            x = synth.tiles(1, 3, hw, hw, seed=60 + sc)
+            out[f"rrdb1_scale{sc}_forward_sub"] = synth.subsample(net(t(x)).numpy(), 1, 4)
+        xs = synth.features(2, 3, 8, 12, seed=3)
+        out["pixel_unshuffle_in"] = xs
+        out["pixel_unshuffle_s2"] = arch.pixel_unshuffle(t(xs), 2).numpy()
+        out["pixel_unshuffle_s4"] = arch.pixel_unshuffle(t(xs), 4).numpy()
+
+    # ---------------------------------------------------------------- HR fusion head pieces
+    hr = synth.features(2, 64, 64, 64, seed=21)
+    lr = synth.features(2, 16, 16, 16, seed=22)
+    hr16 = synth.features(2, 16, 64, 64, seed=23)
+    for training in (False, True):
+        tag = "train" if training else "eval"
+        with torch.no_grad():
+            m = load_sd(hrf.HRfeature(64, 16, 16), synth.hrfeature_state(seed=31))
+            m.train(training)
+            out[f"hrfeature_{tag}"] = m(t(hr)).numpy()
+            if training:
+                for k, v in m.state_dict().items():
+                    if "running" in k or "num_batches" in k:
+                        out[f"hrfeature_train_buf.{k}"] = v.numpy()
+            for oc in (1, 7):
+                m = load_sd(hrf.HRfuse_residual(16, 16, 16, oc, 4), synth.hrfuse_residual_state(out=oc, seed=40 + oc))
+                m.train(training)
+                out[f"hrfuse_out{oc}_{tag}"] = m(t(lr), t(hr16)).numpy()
+    with torch.no_grad():
+        m = hrf.Upsampler(scale=4, n_feats=16)
+        sd = {}
+        synth.upsampler_state(np.random.RandomState(77), sd, "u", 16, 4)
+        load_sd(m, {k[2:]: v for k, v in sd.items()})
+        out["upsampler"] = m(t(lr)).numpy()
+        ps_in = synth.features(1, 8, 3, 5, seed=9)
+        out["pixel_shuffle_in"] = ps_in
+        out["pixel_shuffle_r2"] = torch.nn.PixelShuffle(2)(t(ps_in)).numpy()
+        up_in = synth.features(1, 2, 3, 4, seed=10)
+        out["nearest_in"] = up_in
+        out["nearest_x2"] = torch.nn.functional.interpolate(t(up_in), scale_factor=2, mode="nearest").numpy()
+
+    # ---------------------------------------------------------------- aggregation
+    h256 = (np.random.RandomState(8).rand(1, 1, 256, 256) * 60).astype(np.float32)
+    h256[h256 < 45] = 0  # mostly-zero height label, like the dataset
+    out["aggregate_in"] = h256
+    out["aggregate_torch"] = agg.aggregate_torch(t(h256), 0.25).numpy()
+    out["aggregate_torch_gpu"] = agg.aggregate_torch_gpu(t(h256), 0.25, device="cpu").detach().numpy()
+    out["aggregate_loop"] = agg.aggregate(h256[0, 0], 0.25)
+
+    # ---------------------------------------------------------------- loss-weight KAT (BH_loader.py:1116-1124)
+    stats = np.loadtxt(os.path.join(REF, "datasetglobe", "bh_stats_globe.txt"))
+    out["bh_stats_globe"] = stats
+    out["hierweight_kat"] = np.array([0.08743518, 0.26821995, 0.32067124, 0.73515255, 0.98135007,
+                                      1.60267172, 3.0044993])
+
+    np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
+    sz = os.path.getsize(os.path.join(HERE, "reference_vectors.npz"))
+    print("wrote reference_vectors.npz", sz / 1e6, "MB;", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

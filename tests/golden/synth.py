@@ -56,8 +56,14 @@ def to_old_rrdbnet_keys(sd):
     """Rename to the SR/RRDBNet.py:53-67 attribute names."""
     out = OrderedDict()
     for k, v in sd.items():
-        for a, b in _NEW_TO_OLD:
-            k = k.replace(a, b)
+        if k.startswith("body."):
+            k = "RRDB_trunk." + k[len("body."):]
+            for a, b in _NEW_TO_OLD[1:4]:
+                k = k.replace(a, b)
+        else:
+            for a, b in _NEW_TO_OLD[4:]:
+                if k.startswith(a):
+                    k = b + k[len(a):]
         out[k] = v
     return out
 

@@ -1,0 +1,299 @@
+"""GPU parity tests of the RRDBNet path (run on the B200 box: pytest -m gpu).
+
+Every comparison is CUDA path (through the C ABI) vs the numpy oracle on the same seeded inputs,
+or vs the committed golden vectors the reference modules produced.  Tolerance is the north-star
+one: |got - ref| <= 1e-4 + 1e-3 |ref| elementwise in `exact` numerics; index paths bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from conftest import ROOT, assert_close
+from oracle import ref_numpy as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def load_np_state(module, sd, dev):
+    module.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    return module.to(dev).eval()
+
+
+def cuda(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ------------------------------------------------------------------ single conv through bhsr_conv_tc
+def _planes(x, ctot, dev, seed=0):
+    """fp32 NCHW numpy -> (hi, lo) NHWC planes with ctot channels; extra channels hold noise."""
+    from bhsr import ops
+    nb, c, h, w = x.shape
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    hi = (torch.randn((nb, h, w, ctot), generator=g) * 0.5).to(torch.float16).to(dev)
+    lo = torch.zeros_like(hi)
+    ops.nchw_to_planes(cuda(x, dev), hi, lo, 0)
+    return hi, lo
+
+
+@pytest.mark.parametrize("numerics,rtol,atol", [("exact", 1e-3, 1e-4), ("fast", 2e-2, 2e-2)])
+@pytest.mark.parametrize("cin,cout,h,w,nb", [(64, 32, 64, 64, 2), (96, 32, 64, 64, 1), (160, 32, 40, 64, 2),
+                                             (192, 64, 64, 64, 2), (64, 64, 48, 80, 1), (128, 32, 7, 200, 1)])
+def test_conv_tc_vs_oracle(dev, numerics, rtol, atol, cin, cout, h, w, nb):
+    from bhsr import ops
+    from bhsr._lib import NUMERICS
+    rng = np.random.RandomState(cin + cout + h)
+    x = (rng.rand(nb, cin, h, w) * 2 - 0.5).astype(np.float32)
+    wt = (rng.standard_normal((cout, cin, 3, 3)) * (0.5 / np.sqrt(cin * 9))).astype(np.float32)
+    b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    ref = R.leaky_relu(R.conv2d(x, wt, b, padding=1, acc_dtype=np.float64))
+    hi, lo = _planes(x, 192, dev)
+    out_hi = torch.zeros((nb, h, w, 192), dtype=torch.float16, device=dev)
+    out_lo = torch.zeros_like(out_hi)
+    num = NUMERICS[numerics]
+    wp = ops.pack_conv_weights(cuda(wt, dev), num)
+    ops.conv_tc(hi, lo, 0, cin, wp, cout, cuda(b, dev), ops.PLAIN_TAPS, out_hi, out_lo, out_choff=64,
+                lrelu=True, numerics=num)
+    got = ops.planes_to_nchw(out_hi, out_lo, cout, 64).cpu().numpy()
+    assert_close(got, ref, rtol, atol, f"conv {cin}->{cout} {numerics}")
+    # channels outside the written slice are untouched
+    assert float(out_hi[..., :64].abs().max()) == 0.0 and float(out_hi[..., 64 + cout:].abs().max()) == 0.0
+
+
+def test_conv_tc_residual_epilogues(dev):
+    """conv5 of rdb3: (conv*0.2 + x)*0.2 + rrdb_in  (rrdbnet_arch.py:143,167)."""
+    from bhsr import ops
+    from bhsr._lib import NUMERICS_EXACT
+    rng = np.random.RandomState(5)
+    nb, h, w = 2, 64, 64
+    x = rng.standard_normal((nb, 192, h, w)).astype(np.float32)
+    r2 = rng.standard_normal((nb, 64, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((64, 192, 3, 3)) * 0.02).astype(np.float32)
+    b = (rng.standard_normal(64) * 0.1).astype(np.float32)
+    ref = (R.conv2d(x, wt, b, padding=1, acc_dtype=np.float64) * 0.2 + x[:, :64]) * 0.2 + r2
+    hi, lo = _planes(x, 192, dev)
+    rhi, rlo = _planes(r2, 192, dev)
+    wp = ops.pack_conv_weights(cuda(wt, dev), NUMERICS_EXACT)
+    # in place over the second residual, as the RRDB tail does
+    ops.conv_tc(hi, lo, 0, 192, wp, 64, cuda(b, dev), ops.PLAIN_TAPS, rhi, rlo, out_choff=0,
+                res1=(hi, lo, 0), alpha1=0.2, res2=(rhi, rlo, 0), alpha2=0.2, numerics=NUMERICS_EXACT)
+    got = ops.planes_to_nchw(rhi, rlo, 64, 0).cpu().numpy()
+    assert_close(got, ref, what="rdb3 conv5 epilogue")
+
+
+def test_upsample_phases_index_path_bit_exact(dev):
+    """nearest-x2 folded into the conv: with a centre-tap identity kernel the four sub-pixel
+    phases must reproduce F.interpolate(nearest) bit for bit (src = dst // 2)."""
+    from bhsr import ops
+    from bhsr._lib import NUMERICS_EXACT
+    nb, h, w = 2, 24, 70
+    x = np.random.RandomState(3).standard_normal((nb, 64, h, w)).astype(np.float16).astype(np.float32)
+    wt = np.zeros((64, 64, 3, 3), np.float32)
+    wt[np.arange(64), np.arange(64), 1, 1] = 1.0
+    hi, lo = _planes(x, 64, dev)
+    out_hi = torch.zeros((nb, 2 * h, 2 * w, 64), dtype=torch.float16, device=dev)
+    out_lo = torch.zeros_like(out_hi)
+    for a in range(2):
+        for b in range(2):
+            wp = ops.pack_conv_weights(cuda(wt, dev), NUMERICS_EXACT, fold_phase=2 * a + b)
+            ops.conv_tc(hi, lo, 0, 64, wp, 64, None, ops.phase_taps(a, b), out_hi, out_lo,
+                        out_scale=2, out_oy=a, out_ox=b, numerics=NUMERICS_EXACT)
+    got = ops.planes_to_nchw(out_hi, out_lo, 64, 0).cpu().numpy()
+    assert np.array_equal(got, R.nearest_up2(x))
+
+
+def test_upsample_conv_vs_oracle(dev):
+    from bhsr import ops
+    from bhsr._lib import NUMERICS_EXACT
+    rng = np.random.RandomState(8)
+    nb, h, w = 1, 32, 64
+    x = rng.standard_normal((nb, 64, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((64, 64, 3, 3)) * 0.05).astype(np.float32)
+    b = (rng.standard_normal(64) * 0.1).astype(np.float32)
+    ref = R.leaky_relu(R.conv2d(R.nearest_up2(x), wt, b, padding=1, acc_dtype=np.float64))
+    hi, lo = _planes(x, 64, dev)
+    out_hi = torch.zeros((nb, 2 * h, 2 * w, 64), dtype=torch.float16, device=dev)
+    out_lo = torch.zeros_like(out_hi)
+    for a in range(2):
+        for bb in range(2):
+            wp = ops.pack_conv_weights(cuda(wt, dev), NUMERICS_EXACT, fold_phase=2 * a + bb)
+            ops.conv_tc(hi, lo, 0, 64, wp, 64, cuda(b, dev), ops.phase_taps(a, bb), out_hi, out_lo,
+                        out_scale=2, out_oy=a, out_ox=bb, lrelu=True, numerics=NUMERICS_EXACT)
+    got = ops.planes_to_nchw(out_hi, out_lo, 64, 0).cpu().numpy()
+    assert_close(got, ref, what="conv3x3(nearest_x2)")
+
+
+def test_planes_roundtrip_and_thin_convs(dev):
+    from bhsr import ops
+    rng = np.random.RandomState(2)
+    x = rng.standard_normal((2, 5, 20, 37)).astype(np.float32)
+    hi = torch.zeros((2, 20, 37, 8), dtype=torch.float16, device=dev)
+    lo = torch.zeros_like(hi)
+    ops.nchw_to_planes(cuda(x, dev), hi, lo, 3)
+    back = ops.planes_to_nchw(hi, lo, 5, 3).cpu().numpy()
+    np.testing.assert_allclose(back, x, rtol=2e-6, atol=1e-7)
+    # conv_first on a non-contiguous channel view (predict script passes x[:, :3])
+    x8 = rng.rand(2, 8, 30, 45).astype(np.float32)
+    wt = (rng.standard_normal((64, 3, 3, 3)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(64).astype(np.float32)
+    xv = cuda(x8, dev)[:, :3]
+    assert not xv.is_contiguous()
+    ohi = torch.zeros((2, 30, 45, 64), dtype=torch.float16, device=dev)
+    olo = torch.zeros_like(ohi)
+    ops.conv3x3_first(xv, cuda(wt, dev), cuda(b, dev), ohi, olo)
+    got = ops.planes_to_nchw(ohi, olo, 64, 0).cpu().numpy()
+    assert_close(got, R.conv2d(x8[:, :3], wt, b, padding=1, acc_dtype=np.float64), what="conv_first")
+    wl = (rng.standard_normal((3, 64, 3, 3)) * 0.05).astype(np.float32)
+    bl = rng.standard_normal(3).astype(np.float32)
+    got = ops.conv3x3_last(ohi, olo, 0, 64, cuda(wl, dev), cuda(bl, dev), True).cpu().numpy()
+    ref = R.conv2d(R.leaky_relu(R.conv2d(x8[:, :3], wt, b, padding=1, acc_dtype=np.float64)), wl, bl,
+                   padding=1, acc_dtype=np.float64)
+    assert_close(got, ref, what="conv_last")
+
+
+# ------------------------------------------------------------------ blocks and the network
+def test_rdb_and_rrdb_blocks_vs_oracle(dev):
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_block=1, seed=3)
+    x = synth.features(2, 64, 64, 64, seed=4)
+    blk = rrdbnet.RRDB(64, 32)
+    load_np_state(blk, {k[len("body.0."):]: v for k, v in sd.items() if k.startswith("body.0.")}, dev)
+    with torch.no_grad():
+        got = blk(cuda(x, dev)).cpu().numpy()
+        got_rdb = blk.rdb2(cuda(x, dev)).cpu().numpy()
+    assert_close(got, R.rrdb(x, sd, "body.0", acc_dtype=np.float64), what="RRDB")
+    assert_close(got_rdb, R.residual_dense_block(x, sd, "body.0.rdb2", acc_dtype=np.float64), what="RDB")
+
+
+def test_rrdbnet_2block_vs_oracle_and_golden(dev, golden):
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_block=2, seed=11)
+    net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=2, num_grow_ch=32), sd, dev)
+    x = synth.tiles(2, 3, seed=1337)
+    with torch.no_grad():
+        fea = net.forward_feature(cuda(x, dev))
+        img = net(cuda(x, dev))
+    assert fea.shape == (2, 64, 256, 256) and fea.dtype == torch.float32 and fea.is_contiguous()
+    fea, img = fea.cpu().numpy(), img.cpu().numpy()
+    # full elementwise vs the live oracle
+    assert_close(fea, R.rrdbnet_forward_feature(x, sd, acc_dtype=np.float64), what="forward_feature vs oracle")
+    assert_close(img, R.rrdbnet_forward(x, sd, acc_dtype=np.float64), what="forward vs oracle")
+    # and vs what the reference itself produced
+    assert_close(synth.subsample(fea), golden["rrdb2_feature_sub"], what="forward_feature vs golden")
+    assert_close(fea[0, :8, :20, :20], golden["rrdb2_feature_corner"], what="golden corner")
+    assert_close(fea[1, 56:, 236:, 236:], golden["rrdb2_feature_edge"], what="golden edge")
+    assert_close(synth.subsample(img, 1, 4), golden["rrdb2_forward_sub"], what="forward vs golden")
+    np.testing.assert_allclose(synth.stats(fea)[:3], golden["rrdb2_feature_stats"][:3], rtol=1e-4)
+
+
+def test_rrdbnet_23block_vs_golden(dev, golden):
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_block=23, seed=23)
+    net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=23, num_grow_ch=32), sd, dev)
+    x = synth.tiles(1, 3, seed=4242)
+    with torch.no_grad():
+        fea = net.forward_feature(cuda(x, dev)).cpu().numpy()
+    assert_close(synth.subsample(fea), golden["rrdb23_feature_sub"], what="23-block forward_feature vs golden")
+    np.testing.assert_allclose(synth.stats(fea)[:3], golden["rrdb23_feature_stats"][:3], rtol=1e-4)
+    # fast numerics: TF32-class error, checked in relative L2 (SURVEY §7 hard part 1)
+    net.numerics = "fast"
+    with torch.no_grad():
+        fast = net.forward_feature(cuda(x, dev)).cpu().numpy()
+    ref = golden["rrdb23_feature_sub"].astype(np.float64)
+    rel = np.linalg.norm(synth.subsample(fast) - ref) / np.linalg.norm(ref)
+    assert rel < 5e-3, rel
+
+
+def test_rrdbnet_x4plus_checkpoint_vs_golden(dev, golden):
+    """The one real checkpoint the reference ships (SR/pretrained/RealESRGAN_x4plus.pth,
+    'params_ema', strict load) on two of its test tiles (rrdbnet_arch.py:648-667)."""
+    from bhsr import rrdbnet
+    ckpt = os.path.join(ROOT, "oracle", "_ref", "RealESRGAN_x4plus.pth")
+    if not os.path.exists(ckpt) or "x4plus_feature_sub" not in golden:
+        pytest.skip("RealESRGAN_x4plus.pth not staged under oracle/_ref (run tests/golden/make_golden.py)")
+    net = rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=23, num_grow_ch=32)
+    net.load_state_dict(torch.load(ckpt, map_location="cpu")["params_ema"], strict=True)
+    net = net.to(dev).eval()
+    x = torch.from_numpy(golden["x4plus_input_u8"]).float().permute(0, 3, 1, 2) / 255.0
+    with torch.no_grad():
+        fea = net.forward_feature(x.to(dev)).cpu().numpy()
+    assert_close(synth.subsample(fea), golden["x4plus_feature_sub"], what="x4plus forward_feature vs golden")
+    np.testing.assert_allclose(synth.stats(fea)[1:3], golden["x4plus_feature_stats"][1:3], rtol=1e-4)
+
+
+def test_old_rrdbnet_and_scale_variants_vs_golden(dev, golden):
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_in_ch=4, num_block=1, seed=5)
+    net = load_np_state(rrdbnet.OldRRDBNet(in_nc=4, out_nc=3, nf=64, nb=1, gc=32), synth.to_old_rrdbnet_keys(sd), dev)
+    x = synth.tiles(2, 4, seed=99)
+    with torch.no_grad():
+        y = net(cuda(x, dev)).cpu().numpy()
+    assert y.shape == (2, 3, 256, 256)  # SR/RRDBNet.py:82-85 smoke shape
+    assert_close(synth.subsample(y, 1, 4), golden["old_rrdb1_forward_sub"], what="old RRDBNet")
+    for sc, hw in ((2, 128), (1, 256)):
+        sd = synth.rrdbnet_state(num_in_ch=3, scale=sc, num_block=1, seed=50 + sc)
+        net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=sc, num_feat=64, num_block=1, num_grow_ch=32), sd, dev)
+        x = synth.tiles(1, 3, hw, hw, seed=60 + sc)
+        with torch.no_grad():
+            y = net(cuda(x, dev)).cpu().numpy()
+        assert_close(synth.subsample(y, 1, 4), golden[f"rrdb1_scale{sc}_forward_sub"], what=f"scale {sc}")
+
+
+def test_rrdbnet_views_ragged_sizes_and_batch_independence(dev):
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_block=1, seed=77)
+    net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=1, num_grow_ch=32), sd, dev)
+    # non-contiguous channel slice of an 8-band tile, ragged (non multiple of 64) size
+    x8 = synth.tiles(3, 8, 40, 72, seed=5)
+    xv = cuda(x8, dev)[:, :3]
+    with torch.no_grad():
+        fea = net.forward_feature(xv)
+        assert fea.shape == (3, 64, 160, 288)
+        assert_close(fea.cpu().numpy(), R.rrdbnet_forward_feature(x8[:, :3], sd, acc_dtype=np.float64), what="ragged view")
+        # a tile's result does not depend on its batch position or on the batch size, bit for bit
+        alone = net.forward_feature(xv[1:2].contiguous())
+        again = net.forward_feature(xv)
+    assert torch.equal(alone[0], fea[1]) and torch.equal(again, fea)
+
+
+def test_rrdbnet_full_batch_properties(dev):
+    """BASELINE config 2 size (B=64, 23 blocks): run-to-run determinism and batch independence."""
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_block=23, seed=23)
+    net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=23, num_grow_ch=32), sd, dev)
+    x = cuda(synth.tiles(64, 3, seed=1), dev)
+    with torch.no_grad():
+        a = net.forward_feature(x)
+        b = net.forward_feature(x)
+        one = net.forward_feature(x[37:38])
+    assert torch.equal(a, b)
+    assert torch.equal(one[0], a[37])
+    assert torch.isfinite(a).all()
+
+
+def test_error_behaviour(dev):
+    from bhsr import rrdbnet
+    from bhsr._lib import BhsrError
+    net = rrdbnet.RRDBNet(3, 3, num_block=1).to(dev)
+    with pytest.raises(BhsrError):
+        net.forward_feature(torch.zeros(1, 3, 64, 64))  # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        net.forward_feature(torch.zeros(1, 3, 64, 64, device=dev, requires_grad=True))
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            net.forward_feature(torch.zeros(1, 5, 64, 64, device=dev))
+    # weights updated in place are re-packed (cache keyed on parameter versions)
+    x = torch.rand(1, 3, 64, 64, device=dev)
+    with torch.no_grad():
+        y0 = net.forward_feature(x)
+        net.conv_hr.bias.add_(1.0)
+        y1 = net.forward_feature(x)
+    torch.testing.assert_close(y1, y0 + 1.0, rtol=1e-5, atol=1e-5)

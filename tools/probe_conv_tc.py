@@ -63,7 +63,14 @@ def run_case(name, desc_mode):
         "time_exact64_c192": dict(nb=64, cout=64, cin=192, exact=True, lrelu=False, res=1, time=True),
         "time_fast32_mb1": dict(nb=64, mb=1, time=True),
     }
+    cases["small_multi"] = dict(nb=8, max_ctas=4)
+    cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
+    cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
+    cfg["max_ctas"] = 0
     cfg.update(cases[name])
+    def note(msg):
+        print("#", msg, file=sys.stderr, flush=True)
+    note("start " + name)
     nb, h, w, cin, ctot, cout = (cfg[k] for k in ("nb", "h", "w", "cin", "ctot", "cout"))
     exact = cfg["exact"]
     numerics = NUMERICS_EXACT if exact else NUMERICS_FAST
@@ -135,9 +142,12 @@ def run_case(name, desc_mode):
             out_lo = torch.zeros_like(out_hi)
             call = lambda: ops.conv_tc(in_hi, in_lo, 0, cin, wp, cout, bias, ops.PLAIN_TAPS, out_hi, out_lo,
                                        out_choff=64, lrelu=cfg["lrelu"], numerics=numerics,
-                                       mblocks=cfg["mb"], desc_mode=desc_mode, **kw)
+                                       mblocks=cfg["mb"], desc_mode=desc_mode, max_ctas=cfg["max_ctas"], **kw)
+        torch.cuda.synchronize()
+        note("inputs ready")
         call()
         torch.cuda.synchronize()
+        note("first call done")
         if cfg["nchw"]:
             got = out.double()
         else:
