@@ -216,62 +216,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      uint32_t a_it = 0, w_it = 0, tile_it = 0;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
-        const int t = tile % p.tiles_per_strip;
-        const int flat_mod = (t * MT) % kPitch;
-        const int as = tile_it & 1;
-        mbar_wait(bar(B_TEMPTY + as), ((tile_it >> 1) & 1) ^ 1);
+    // The whole warp walks the loop (warp-uniform control flow keeps the descriptor arithmetic
+    // on the uniform datapath); one elected lane issues the tcgen05 instructions.  Descriptors
+    // are advanced by adding to their low word: +2 per 16-channel k-step (32 B), +8 per flat row.
+    const uint64_t desc_hi_lo0 = make_sw128_desc(0, 0);
+    const uint32_t desc_hi = static_cast<uint32_t>(desc_hi_lo0 >> 32);
+    const uint32_t desc_lo0 = static_cast<uint32_t>(desc_hi_lo0);  // LBO field, start = 0
+    auto mk = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
+    uint32_t a_it = 0, w_it = 0, tile_it = 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+      const int t = tile % p.tiles_per_strip;
+      const int flat_mod = (t * MT) % kPitch;
+      const int as = tile_it & 1;
+      mbar_wait(bar(B_TEMPTY + as), ((tile_it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + as * ACC_COLS;
+      uint32_t accumulate = 0;
+      for (int c = 0; c < p.n_chunks; ++c, ++a_it) {
+        const int st = a_it & 1;
+        mbar_wait(bar(B_AFULL + st), (a_it >> 1) & 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + as * ACC_COLS;
-        uint32_t accumulate = 0;
-        for (int c = 0; c < p.n_chunks; ++c, ++a_it) {
-          const int st = a_it & 1;
-          mbar_wait(bar(B_AFULL + st), (a_it >> 1) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = a_base + st * A_STAGE;
-          const int rem = p.cin - c * 64;
-          const int ksteps = rem >= 64 ? 4 : (rem >> 4);
-          for (int tap = 0; tap < p.ntaps; ++tap, ++w_it) {
-            int ws;
-            if (p.w_resident) {
-              ws = c * p.ntaps + tap;
-              if (tile_it == 0) {
-                mbar_wait(bar(B_WFULL + ws), 0);
-                tc_fence_after();
-              }
-            } else {
-              ws = w_it % p.wslots;
-              mbar_wait(bar(B_WFULL + ws), (w_it / p.wslots) & 1);
+        // descriptor low word of flat row 0 (tap shift 0, m-block 0) of this stage
+        const uint32_t a_lo0 =
+            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1) * 8;
+        const int rem = p.cin - c * 64;
+        const int ksteps = rem >= 64 ? 4 : (rem >> 4);
+        for (int tap = 0; tap < p.ntaps; ++tap, ++w_it) {
+          int ws;
+          if (p.w_resident) {
+            ws = c * p.ntaps + tap;
+            if (tile_it == 0) {
+              mbar_wait(bar(B_WFULL + ws), 0);
               tc_fence_after();
             }
-            const uint32_t w_addr = w_base + ws * W_SLAB;
+          } else {
+            ws = w_it % p.wslots;
+            mbar_wait(bar(B_WFULL + ws), (w_it / p.wslots) & 1);
+            tc_fence_after();
+          }
+          const uint32_t b_lo = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
+          const uint32_t a_lo = a_lo0 + p.tap_shift[tap] * 8;
+          if (elect_one()) {
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
-              // first flat row of this tap inside the halo tile (see file header)
-              const int row0 = flat_mod + kPitch + 1 + mb * 128 + p.tap_shift[tap];
-              const uint32_t a_row = a_hi + row0 * 128;
-              const uint32_t bo = 0;  // swizzle is a function of absolute smem address bits (measured)
               const uint32_t d_acc = acc + mb * ROWS_B;
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t da = make_sw128_desc(a_row + k * 32, bo);
-                const uint64_t db = make_sw128_desc(w_addr + k * 32, 0);
-                const uint32_t acc_flag = accumulate | (uint32_t)(k > 0);
-                umma_f16_ss(d_acc, da, db, IDESC_WIDE, acc_flag);
-                if (EXACT) {
-                  const uint64_t dl = make_sw128_desc(a_row + G::kTileBytes + k * 32, bo);
-                  umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
+                  const uint64_t db = mk(b_lo + k * 2);
+                  umma_f16_ss(d_acc, da, db, IDESC_WIDE, k > 0 ? 1u : accumulate);
+                  if (EXACT) {
+                    const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
+                    umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
+                  }
                 }
               }
             }
-            accumulate = 1;
             if (!p.w_resident) umma_commit(bar(B_WEMPTY + ws));
           }
-          umma_commit(bar(B_AEMPTY + st));
+          __syncwarp();
+          accumulate = 1;
         }
-        umma_commit(bar(B_TFULL + as));
+        if (elect_one()) umma_commit(bar(B_AEMPTY + st));
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(bar(B_TFULL + as));
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------ epilogue (warps 2..5)
