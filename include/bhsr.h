@@ -159,6 +159,68 @@ int bhsr_rrdbnet_pack(const float* const* params, int32_t num_block, int32_t num
 int bhsr_rrdbnet_forward(const BhsrRrdbNetDesc* desc, const float* x, int64_t sn, int64_t sc,
                          int64_t sh, int64_t sw, float* y, int32_t feature, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Feature-aggregation head (SR/HRfuse.py:17-190, mymodels.py:259-293, aggregate_utils.py:29-59).
+ * fp32 NCHW tensors addressed as (base, channels of the underlying buffer, channel offset) so a
+ * producer can write its slice of a concat buffer.  N = 1..64 output channels on 256x256 maps:
+ * HBM-bound CUDA-core kernels.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct BhsrHeadConvDesc {
+  const float* x; int32_t x_ctot, x_choff;
+  int32_t nb, cin, h, w;       /* conv grid (stride 1, zero "same" padding) */
+  int32_t x_unshuffle;         /* read x through the inverse of PixelShuffle(2) (backward of K7) */
+  const float* in_scale;       /* optional fused BatchNorm(+ReLU) on the input read:            */
+  const float* in_shift;       /*   x' = relu?(x * in_scale[c] + in_shift[c])  (HRfuse.py:146-148) */
+  int32_t in_relu;
+  const float* weight;         /* [cout][cin][k][k] fp32 */
+  const float* bias;           /* [cout] or NULL */
+  int32_t cout, ksize;         /* ksize 1 or 3 */
+  float* y; int32_t y_ctot, y_choff;
+  int32_t y_shuffle;           /* scatter through nn.PixelShuffle(2) (HRfuse.py:24): bit-exact index path */
+  double* stats;               /* [2*cout]: += sum, sum of squares of the outputs (BatchNorm batch stats) */
+  int32_t accumulate;          /* y += conv (sums gradient contributions) */
+} BhsrHeadConvDesc;
+
+int bhsr_head_conv(const BhsrHeadConvDesc* desc, void* stream);
+/* dw[cout][cin][k][k] = sum dy * x' (and db = sum dy); desc gives the x side of the forward conv */
+int bhsr_head_conv_wgrad(const BhsrHeadConvDesc* desc, const float* dy, int32_t dy_ctot,
+                         int32_t dy_choff, int32_t dy_unshuffle, float* dw, float* db, void* stream);
+/* training-mode BatchNorm2d from epilogue statistics: scale/shift for the fused apply, saved
+ * mean/invstd, running-stat update (momentum, unbiased variance) — HRfuse.py:129-138 */
+int bhsr_bn_finalize(const double* stats, int32_t c, double count, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean,
+                     float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                     void* stream);
+int bhsr_bn_eval_affine(int32_t c, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* scale, float* shift,
+                        float* invstd, void* stream);
+/* out = relu(a*sa+ta + (b*sb+tb | b))   BasicBlock tail, HRfuse.py:152-157 */
+int bhsr_affine_add_relu(const float* a, const float* sa, const float* ta, const float* b,
+                         int32_t b_ctot, int32_t b_choff, const float* sb, const float* tb,
+                         int32_t nb, int32_t c, int32_t hw, float* out, int32_t o_ctot,
+                         int32_t o_choff, void* stream);
+/* backward of the fused BN(+add)+ReLU: per-channel sums {g', g'*a, g'*b}, g' = g_out*[out>0]
+ * (out == NULL: mask recomputed as a*sa+ta > 0) */
+int bhsr_bn_bwd_reduce(const float* g_out, int32_t g_ctot, int32_t g_choff, const float* out,
+                       int32_t o_ctot, int32_t o_choff, const float* a, const float* sa,
+                       const float* ta, const float* b, int32_t b_ctot, int32_t b_choff, int32_t nb,
+                       int32_t c, int32_t hw, double* sums, void* stream);
+int bhsr_bn_bwd_coeffs(const double* sums, int32_t which, int32_t c, double count,
+                       const float* gamma, const float* mean, const float* invstd,
+                       const float* scale_eval, int32_t training, float* k1, float* k2, float* k3,
+                       float* dgamma, float* dbeta, void* stream);
+int bhsr_bn_bwd_apply(const float* g_out, int32_t g_ctot, int32_t g_choff, const float* out,
+                      int32_t o_ctot, int32_t o_choff, const float* a, const float* sa,
+                      const float* ta, const float* k1, const float* k2, const float* k3, float* g_a,
+                      const float* b, int32_t b_ctot, int32_t b_choff, const float* kb1,
+                      const float* kb2, const float* kb3, float* g_b, int32_t gb_ctot,
+                      int32_t gb_choff, int32_t gb_accumulate, int32_t nb, int32_t c, int32_t hw,
+                      void* stream);
+/* step x step block aggregation: out = sum(x) / (count(x >= thr | x > thr) + 1e-10)
+ * (aggregate_utils.py:29-41 uses >= 0; :44-59 uses > 1.0) on [nimg][h][w] -> [nimg][h/step][w/step] */
+int bhsr_aggregate(const float* x, int32_t nimg, int32_t h, int32_t w, int32_t step,
+                   float threshold, int32_t strict, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,23 @@ class RrdbNetDesc(C.Structure):
     ]
 
 
+class HeadConvDesc(C.Structure):
+    """Mirror of `BhsrHeadConvDesc` (include/bhsr.h)."""
+
+    _fields_ = [
+        ("x", C.c_void_p), ("x_ctot", C.c_int32), ("x_choff", C.c_int32),
+        ("nb", C.c_int32), ("cin", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("x_unshuffle", C.c_int32),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
+        ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("cout", C.c_int32), ("ksize", C.c_int32),
+        ("y", C.c_void_p), ("y_ctot", C.c_int32), ("y_choff", C.c_int32),
+        ("y_shuffle", C.c_int32),
+        ("stats", C.c_void_p),
+        ("accumulate", C.c_int32),
+    ]
+
+
 # symbol -> (restype, argtypes); tests check every symbol of include/bhsr.h is listed here
 # and exported by the shared object.
 _SIGNATURES = {
@@ -96,6 +113,25 @@ _SIGNATURES = {
     "bhsr_rrdbnet_workspace_bytes": (C.c_size_t, [C.c_int32] * 4),
     "bhsr_rrdbnet_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    "bhsr_head_conv": (C.c_int, [C.POINTER(HeadConvDesc), C.c_void_p]),
+    "bhsr_head_conv_wgrad": (C.c_int, [C.POINTER(HeadConvDesc), C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bhsr_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
+                                   C.c_float, C.c_float] + [C.c_void_p] * 7),
+    "bhsr_bn_eval_affine": (C.c_int, [C.c_int32] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 4),
+    "bhsr_affine_add_relu": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_void_p]),
+    "bhsr_bn_bwd_reduce": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bhsr_bn_bwd_coeffs": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 4 +
+                           [C.c_int32] + [C.c_void_p] * 6),
+    "bhsr_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32] +
+                          [C.c_void_p] * 8 + [C.c_int32, C.c_int32] + [C.c_void_p] * 4 +
+                          [C.c_int32] * 6 + [C.c_void_p]),
+    "bhsr_aggregate": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p,
+                                 C.c_void_p]),
     "bhsr_rrdbnet_forward": (C.c_int, [C.POINTER(RrdbNetDesc), C.c_void_p] + [C.c_int64] * 4 +
                              [C.c_void_p, C.c_int32, C.c_void_p]),
 }

@@ -257,18 +257,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
           const uint32_t b_lo = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
           const uint32_t a_lo = a_lo0 + p.tap_shift[tap] * 8;
           if (elect_one()) {
+            if (p.desc_mode == 0) {
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-              const uint32_t d_acc = acc + mb * ROWS_B;
+              for (int mb = 0; mb < MB; ++mb) {
+                const uint32_t d_acc = acc + mb * ROWS_B;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps) {
+                    const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
+                    const uint64_t db = mk(b_lo + k * 2);
+                    umma_f16_ss(d_acc, da, db, IDESC_WIDE, k > 0 ? 1u : accumulate);
+                    if (EXACT) {
+                      const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
+                      umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
+                    }
+                  }
+                }
+              }
+            } else {
+              // TIMING EXPERIMENTS ONLY (results are wrong for desc_mode >= 3):
+              //  2: k-outer / m-block-inner issue order (independent accumulators interleaved)
+              //  3: as 2, and every k-step accumulates into its own TMEM columns
+              //  4: as 0 but every MMA targets its own TMEM columns (no dependent chains at all)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (k < ksteps) {
-                  const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
-                  const uint64_t db = mk(b_lo + k * 2);
-                  umma_f16_ss(d_acc, da, db, IDESC_WIDE, k > 0 ? 1u : accumulate);
-                  if (EXACT) {
-                    const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
-                    umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                  if (k < ksteps) {
+                    uint32_t d_acc = acc + mb * ROWS_B;
+                    if (p.desc_mode >= 3) d_acc = tmem_base + ((k * MB + mb) * ROWS_B) % (512 - ROWS_B);
+                    const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
+                    const uint64_t db = mk(b_lo + k * 2);
+                    umma_f16_ss(d_acc, da, db, IDESC_WIDE, k > 0 ? 1u : accumulate);
+                    if (EXACT) {
+                      const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
+                      umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
+                    }
                   }
                 }
               }

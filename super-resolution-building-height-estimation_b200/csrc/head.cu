@@ -1,0 +1,618 @@
+// head.cu — fp32 NCHW kernels of the feature-aggregation height head (SR/HRfuse.py:17-190,
+// mymodels.py:259-293): small-channel 3x3 / 1x1 convolutions with fused BatchNorm+ReLU on the
+// input read, BatchNorm statistics in the epilogue, pixel-shuffle scatter, channel-slice
+// (concat) writes; weight-gradient reduction; BatchNorm finalize / apply / backward; 4x4 block
+// aggregation.  These layers have N = 1..64 output channels on 256x256 maps: ~36 FLOP per HBM
+// byte unfused, so they are written as coalesced CUDA-core kernels (HBM-bound), not as MMAs.
+//
+// Tensors are fp32 NCHW "views": base pointer + channel count of the underlying buffer + channel
+// offset, so producers write straight into their slice of a concat buffer (torch.cat disappears).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+
+namespace bhsr {
+
+constexpr int kTW = 32;  // pixel tile width  (threadIdx.x)
+constexpr int kTH = 8;   // pixel tile height (threadIdx.y)
+constexpr int kCI = 8;   // input channels per shared-memory chunk
+
+struct View {            // fp32 NCHW [nb][ctot][h][w], channels [choff, choff+c) addressed
+  const float* p;
+  int ctot, choff;
+};
+
+struct ConvArgs {
+  const float* x; int x_ctot, x_choff;
+  int nb, cin, h, w;               // conv grid = input spatial size (stride 1, "same" padding)
+  int x_unshuffle;                 // read x through PixelShuffle(2)^-1: x[n, c/4, 2h+(c%4)/2, 2w+c%2]
+  const float* in_scale; const float* in_shift; int in_relu;   // x' = relu(x*s[c]+t[c]) (optional)
+  const float* wgt;                // [cout][cin][K][K]
+  const float* bias;               // [cout] or null
+  int cout;
+  float* y; int y_ctot, y_choff;
+  int y_shuffle;                   // write through PixelShuffle(2): y[n, co/4, 2h+(co%4)/2, 2w+co%2]
+  double* stats;                   // [2*cout] sum / sum of squares of the (biased) outputs, or null
+  int accumulate;                  // y += result (used to sum gradient contributions)
+};
+
+__device__ __forceinline__ float load_in(const ConvArgs& a, int n, int c, int yy, int xx) {
+  if (yy < 0 || yy >= a.h || xx < 0 || xx >= a.w) return 0.f;
+  float v;
+  if (a.x_unshuffle) {
+    const int cs = c >> 2, i = (c >> 1) & 1, j = c & 1;
+    v = a.x[((static_cast<size_t>(n) * a.x_ctot + a.x_choff + cs) * (2 * a.h) + 2 * yy + i) *
+                (2 * a.w) + 2 * xx + j];
+  } else {
+    v = a.x[((static_cast<size_t>(n) * a.x_ctot + a.x_choff + c) * a.h + yy) * a.w + xx];
+  }
+  if (a.in_scale) v = fmaf(v, a.in_scale[c], a.in_shift[c]);
+  if (a.in_relu) v = fmaxf(v, 0.f);
+  return v;
+}
+
+// ------------------------------------------------------------------ forward conv (also dgrad)
+template <int K, int CT>
+__global__ void __launch_bounds__(kTW * kTH)
+conv_fwd_kernel(const ConvArgs a) {
+  constexpr int P = K / 2;
+  constexpr int IW = kTW + 2 * P, IH = kTH + 2 * P;
+  __shared__ float s_in[kCI][IH][IW + 1];
+  __shared__ float s_w[kCI][K * K][CT];
+  const int tiles_x = (a.w + kTW - 1) / kTW;
+  const int tx0 = (blockIdx.x % tiles_x) * kTW, ty0 = (blockIdx.x / tiles_x) * kTH;
+  const int co0 = blockIdx.y * CT;
+  const int n = blockIdx.z;
+  const int tid = threadIdx.y * kTW + threadIdx.x;
+  float acc[CT];
+#pragma unroll
+  for (int j = 0; j < CT; ++j) acc[j] = 0.f;
+
+  for (int c0 = 0; c0 < a.cin; c0 += kCI) {
+    for (int i = tid; i < kCI * IH * IW; i += kTW * kTH) {
+      const int ci = i / (IH * IW), r = i % (IH * IW);
+      const int yy = r / IW, xx = r % IW;
+      float v = 0.f;
+      if (c0 + ci < a.cin) v = load_in(a, n, c0 + ci, ty0 + yy - P, tx0 + xx - P);
+      s_in[ci][yy][xx] = v;
+    }
+    for (int i = tid; i < kCI * K * K * CT; i += kTW * kTH) {
+      const int j = i % CT, t = (i / CT) % (K * K), ci = i / (CT * K * K);
+      float v = 0.f;
+      if (c0 + ci < a.cin && co0 + j < a.cout)
+        v = a.wgt[(static_cast<size_t>(co0 + j) * a.cin + c0 + ci) * (K * K) + t];
+      s_w[ci][t][j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ci = 0; ci < kCI; ++ci) {
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const float v = s_in[ci][threadIdx.y + ky][threadIdx.x + kx];
+          const float* wr = s_w[ci][ky * K + kx];
+#pragma unroll
+          for (int j = 0; j < CT; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int px = tx0 + threadIdx.x, py = ty0 + threadIdx.y;
+  const bool valid = px < a.w && py < a.h;
+#pragma unroll
+  for (int j = 0; j < CT; ++j) {
+    const int co = co0 + j;
+    if (co >= a.cout) break;
+    float v = acc[j] + (a.bias ? a.bias[co] : 0.f);
+    if (a.stats) {
+      float s1 = valid ? v : 0.f, s2 = valid ? v * v : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (threadIdx.x == 0) {
+        atomicAdd(a.stats + co, static_cast<double>(s1));
+        atomicAdd(a.stats + a.cout + co, static_cast<double>(s2));
+      }
+    }
+    if (valid) {
+      size_t o;
+      if (a.y_shuffle) {
+        const int cs = co >> 2, i = (co >> 1) & 1, jj = co & 1;
+        o = ((static_cast<size_t>(n) * a.y_ctot + a.y_choff + cs) * (2 * a.h) + 2 * py + i) *
+                (2 * a.w) + 2 * px + jj;
+      } else {
+        o = ((static_cast<size_t>(n) * a.y_ctot + a.y_choff + co) * a.h + py) * a.w + px;
+      }
+      if (a.accumulate) a.y[o] += v; else a.y[o] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weight gradient
+// dw[co][ci][ky][kx] = sum_{n,y,x} dy[n,co,y,x] * x'[n,ci,y+ky-P,x+kx-P]   (x' = transformed input)
+// One block walks pixel tiles (grid-stride), keeps a [CT x (kCI*K*K)] register-tiled partial
+// product (2 co x 3 (ci,tap) per thread) and adds it to global dw once at the end.
+struct WgradArgs {
+  ConvArgs in;                     // x side (x, transform, geometry); wgt/y unused
+  const float* dy; int dy_ctot, dy_choff; int dy_unshuffle;
+  int cout;
+  float* dw;                       // [cout][cin][K][K], accumulated with atomics (pre-zeroed)
+  float* db;                       // [cout] or null
+};
+
+__device__ __forceinline__ float load_dy(const WgradArgs& a, int n, int c, int yy, int xx) {
+  if (yy >= a.in.h || xx >= a.in.w) return 0.f;
+  if (a.dy_unshuffle) {
+    const int cs = c >> 2, i = (c >> 1) & 1, j = c & 1;
+    return a.dy[((static_cast<size_t>(n) * a.dy_ctot + a.dy_choff + cs) * (2 * a.in.h) + 2 * yy + i) *
+                    (2 * a.in.w) + 2 * xx + j];
+  }
+  return a.dy[((static_cast<size_t>(n) * a.dy_ctot + a.dy_choff + c) * a.in.h + yy) * a.in.w + xx];
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const WgradArgs a, int co0, int c0) {
+  constexpr int P = K / 2;
+  constexpr int KK = K * K;
+  constexpr int CT = 16;
+  constexpr int IW = kTW + 2 * P, IH = kTH + 2 * P;
+  constexpr int NB = kCI * KK;                 // B columns (ci,tap)
+  constexpr int NBT = (NB + 2) / 3;            // column triples
+  __shared__ float s_in[kCI][IH][IW + 1];
+  __shared__ float s_dy[CT][kTH][kTW + 1];
+  const int tid = threadIdx.x;
+  const int rp = tid / NBT;                    // row pair 0..7 -> co = 2*rp, 2*rp+1
+  const int ct = tid % NBT;
+  const bool active = rp < CT / 2;
+  int col_ci[3], col_ky[3], col_kx[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    int col = ct * 3 + j;
+    if (col >= NB) col = NB - 1;
+    col_ci[j] = col / KK;
+    col_ky[j] = (col % KK) / K;
+    col_kx[j] = (col % KK) % K;
+  }
+  float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float dbacc = 0.f;
+  const int tiles_x = (a.in.w + kTW - 1) / kTW, tiles_y = (a.in.h + kTH - 1) / kTH;
+  const int tiles = tiles_x * tiles_y * a.in.nb;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int tr = tile % (tiles_x * tiles_y);
+    const int tx0 = (tr % tiles_x) * kTW, ty0 = (tr / tiles_x) * kTH;
+    for (int i = tid; i < kCI * IH * IW; i += 256) {
+      const int ci = i / (IH * IW), r = i % (IH * IW);
+      const int yy = r / IW, xx = r % IW;
+      float v = 0.f;
+      if (c0 + ci < a.in.cin) v = load_in(a.in, n, c0 + ci, ty0 + yy - P, tx0 + xx - P);
+      s_in[ci][yy][xx] = v;
+    }
+    for (int i = tid; i < CT * kTH * kTW; i += 256) {
+      const int co = i / (kTH * kTW), r = i % (kTH * kTW);
+      const int yy = r / kTW, xx = r % kTW;
+      float v = 0.f;
+      if (co0 + co < a.cout) v = load_dy(a, n, co0 + co, ty0 + yy, tx0 + xx);
+      s_dy[co][yy][xx] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int yy = 0; yy < kTH; ++yy) {
+#pragma unroll 8
+        for (int xx = 0; xx < kTW; ++xx) {
+          const float d0 = s_dy[2 * rp][yy][xx], d1 = s_dy[2 * rp + 1][yy][xx];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float v = s_in[col_ci[j]][yy + col_ky[j]][xx + col_kx[j]];
+            acc[0][j] = fmaf(d0, v, acc[0][j]);
+            acc[1][j] = fmaf(d1, v, acc[1][j]);
+          }
+        }
+      }
+    }
+    if (a.db && c0 == 0 && tid < CT) {  // bias gradient: one thread per output channel
+      float s = 0.f;
+      for (int yy = 0; yy < kTH; ++yy)
+        for (int xx = 0; xx < kTW; ++xx) s += s_dy[tid][yy][xx];
+      dbacc += s;
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int co = co0 + 2 * rp + r;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int col = ct * 3 + j;
+        const int ci = c0 + col_ci[j];
+        if (col < NB && co < a.cout && ci < a.in.cin)
+          atomicAdd(a.dw + (static_cast<size_t>(co) * a.in.cin + ci) * KK + col_ky[j] * K + col_kx[j],
+                    acc[r][j]);
+      }
+    }
+  }
+  if (a.db && c0 == 0 && tid < CT && co0 + tid < a.cout) atomicAdd(a.db + co0 + tid, dbacc);
+}
+
+// ------------------------------------------------------------------ BatchNorm pieces
+// stats (double sum, sumsq over count elements) -> scale/shift for the fused apply, saved
+// mean / invstd for backward, running-stat update (momentum, unbiased variance) like
+// nn.BatchNorm2d in training mode (SR/HRfuse.py:129-138).
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int c, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* running_mean,
+                                   float* running_var, float* scale, float* shift, float* mean_out,
+                                   float* invstd_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const double mean = stats[i] / count;
+  double var = stats[c + i] / count - mean * mean;
+  if (var < 0) var = 0;
+  const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
+  const float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+  scale[i] = static_cast<float>(g * invstd);
+  shift[i] = static_cast<float>(b - mean * g * invstd);
+  if (mean_out) mean_out[i] = static_cast<float>(mean);
+  if (invstd_out) invstd_out[i] = static_cast<float>(invstd);
+  if (running_mean) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[i] = static_cast<float>((1.0 - momentum) * running_mean[i] + momentum * mean);
+    running_var[i] = static_cast<float>((1.0 - momentum) * running_var[i] + momentum * unbiased);
+  }
+}
+
+// eval mode: scale/shift from running statistics
+__global__ void bn_eval_affine_kernel(int c, const float* gamma, const float* beta,
+                                      const float* running_mean, const float* running_var,
+                                      float eps, float* scale, float* shift, float* invstd_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float invstd = 1.f / sqrtf(running_var[i] + eps);
+  const float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+  scale[i] = g * invstd;
+  shift[i] = b - running_mean[i] * g * invstd;
+  if (invstd_out) invstd_out[i] = invstd;
+}
+
+// out = relu(a*sa+ta + (b*sb+tb | b))       BasicBlock tail, SR/HRfuse.py:152-157
+__global__ void affine_add_relu_kernel(const float* __restrict__ a, const float* __restrict__ sa,
+                                       const float* __restrict__ ta, const float* __restrict__ b,
+                                       int b_ctot, int b_choff, const float* __restrict__ sb,
+                                       const float* __restrict__ tb, int nb, int c, int hw,
+                                       float* __restrict__ out, int o_ctot, int o_choff) {
+  const size_t total = static_cast<size_t>(nb) * c * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int p = i % hw;
+    const int ch = (i / hw) % c;
+    const int n = i / (static_cast<size_t>(hw) * c);
+    float v = fmaf(a[i], sa[ch], ta[ch]);
+    float r = b[(static_cast<size_t>(n) * b_ctot + b_choff + ch) * hw + p];
+    if (sb) r = fmaf(r, sb[ch], tb[ch]);
+    v = fmaxf(v + r, 0.f);
+    out[(static_cast<size_t>(n) * o_ctot + o_choff + ch) * hw + p] = v;
+  }
+}
+
+// Backward reductions of  out = relu(A + B), A = a*sa+ta (BN of a), B = b*sb+tb or b:
+//   g' = g_out * (out > 0);  sums[ch] = {sum g', sum g'*a, sum g'*b}
+// Also used for the inner BN (out = relu(a*sa+ta), no B) with `out` null: the mask is then
+// recomputed from a.
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ g_out, int g_ctot, int g_choff,
+                                     const float* __restrict__ out, int o_ctot, int o_choff,
+                                     const float* __restrict__ a, const float* __restrict__ sa,
+                                     const float* __restrict__ ta, const float* __restrict__ b,
+                                     int b_ctot, int b_choff, int nb, int c, int hw, double* sums) {
+  const int ch = blockIdx.y;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const size_t per = static_cast<size_t>(nb) * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < per;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = i / hw, p = i % hw;
+    const float av = a[(static_cast<size_t>(n) * c + ch) * hw + p];
+    float g = g_out[(static_cast<size_t>(n) * g_ctot + g_choff + ch) * hw + p];
+    bool on;
+    if (out) on = out[(static_cast<size_t>(n) * o_ctot + o_choff + ch) * hw + p] > 0.f;
+    else on = fmaf(av, sa[ch], ta[ch]) > 0.f;
+    if (!on) g = 0.f;
+    s0 += g;
+    s1 = fmaf(g, av, s1);
+    if (b) s2 = fmaf(g, b[(static_cast<size_t>(n) * b_ctot + b_choff + ch) * hw + p], s2);
+  }
+  __shared__ float red[3][32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = s0; red[1][wid] = s1; red[2][wid] = s2; }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = blockDim.x >> 5;
+    s0 = lane < nw ? red[0][lane] : 0.f;
+    s1 = lane < nw ? red[1][lane] : 0.f;
+    s2 = lane < nw ? red[2][lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      atomicAdd(sums + ch, static_cast<double>(s0));
+      atomicAdd(sums + c + ch, static_cast<double>(s1));
+      atomicAdd(sums + 2 * c + ch, static_cast<double>(s2));
+    }
+  }
+}
+
+// From the reduced sums: per-channel coefficients of  g_a = k1*g' + k2*a + k3  (training-mode BN
+// backward: g_a = gamma*invstd*(g' - mean(g') - xhat*mean(g'*xhat)); eval mode: g_a = scale*g'),
+// plus dgamma / dbeta.
+__global__ void bn_bwd_coeffs_kernel(const double* sums, int which, int c, double count,
+                                     const float* gamma, const float* mean, const float* invstd,
+                                     const float* scale_eval, int training, float* k1, float* k2,
+                                     float* k3, float* dgamma, float* dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const double sg = sums[i];
+  const double sgx = sums[(which + 1) * c + i];  // sum g'*a (which=0) or sum g'*b (which=1)
+  const double g = gamma ? gamma[i] : 1.0;
+  if (training) {
+    const double m = mean[i], is = invstd[i];
+    const double sgxhat = (sgx - m * sg) * is;          // sum g' * xhat
+    if (dgamma) dgamma[i] = static_cast<float>(sgxhat);
+    if (dbeta) dbeta[i] = static_cast<float>(sg);
+    // g_a = g*is*(g' - sg/M - (a-m)*is*sgxhat/M)
+    const double c2 = -g * is * is * sgxhat / count;
+    k1[i] = static_cast<float>(g * is);
+    k2[i] = static_cast<float>(c2);
+    k3[i] = static_cast<float>(-g * is * sg / count - c2 * m);
+  } else {
+    const double m = mean ? mean[i] : 0.0, is = invstd ? invstd[i] : 1.0;
+    if (dgamma) dgamma[i] = static_cast<float>((sgx - m * sg) * is);
+    if (dbeta) dbeta[i] = static_cast<float>(sg);
+    k1[i] = scale_eval[i];
+    k2[i] = 0.f;
+    k3[i] = 0.f;
+  }
+}
+
+// g_a = k1*g' + k2*a + k3 with g' = g_out*(mask); optionally also g_b likewise, or g_b = g'
+// (identity shortcut) accumulated/written to a view.
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ g_out, int g_ctot, int g_choff,
+                                    const float* __restrict__ out, int o_ctot, int o_choff,
+                                    const float* __restrict__ a, const float* __restrict__ sa,
+                                    const float* __restrict__ ta, const float* __restrict__ k1,
+                                    const float* __restrict__ k2, const float* __restrict__ k3,
+                                    float* __restrict__ g_a, const float* __restrict__ b, int b_ctot,
+                                    int b_choff, const float* __restrict__ kb1,
+                                    const float* __restrict__ kb2, const float* __restrict__ kb3,
+                                    float* __restrict__ g_b, int gb_ctot, int gb_choff,
+                                    int gb_accumulate, int nb, int c, int hw) {
+  const size_t total = static_cast<size_t>(nb) * c * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int p = i % hw;
+    const int ch = (i / hw) % c;
+    const int n = i / (static_cast<size_t>(hw) * c);
+    const float av = a[i];
+    float g = g_out[(static_cast<size_t>(n) * g_ctot + g_choff + ch) * hw + p];
+    bool on;
+    if (out) on = out[(static_cast<size_t>(n) * o_ctot + o_choff + ch) * hw + p] > 0.f;
+    else on = fmaf(av, sa[ch], ta[ch]) > 0.f;
+    if (!on) g = 0.f;
+    g_a[i] = fmaf(k1[ch], g, fmaf(k2[ch], av, k3[ch]));
+    if (g_b) {
+      float gb = g;
+      if (kb1) {
+        const float bv = b[(static_cast<size_t>(n) * b_ctot + b_choff + ch) * hw + p];
+        gb = fmaf(kb1[ch], g, fmaf(kb2[ch], bv, kb3[ch]));
+      }
+      const size_t o = (static_cast<size_t>(n) * gb_ctot + gb_choff + ch) * hw + p;
+      if (gb_accumulate) g_b[o] += gb; else g_b[o] = gb;
+    }
+  }
+}
+
+// 4x4 (scale x scale) block aggregation, aggregate_utils.py:29-59:
+//   out = sum(x) / (count(x > thr | x >= thr) + 1e-10)
+__global__ void aggregate_kernel(const float* __restrict__ x, int nimg, int h, int w, int step,
+                                 float thr, int strict, float* __restrict__ out) {
+  const int oh = h / step, ow = w / step;
+  const size_t total = static_cast<size_t>(nimg) * oh * ow;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ox = i % ow, oy = (i / ow) % oh;
+    const size_t n = i / (static_cast<size_t>(ow) * oh);
+    float s = 0.f, cnt = 0.f;
+    for (int dy = 0; dy < step; ++dy)
+      for (int dx = 0; dx < step; ++dx) {
+        const float v = x[(n * h + oy * step + dy) * w + ox * step + dx];
+        s += v;
+        cnt += (strict ? v > thr : v >= thr) ? 1.f : 0.f;
+      }
+    out[i] = s / (cnt + 1e-10f);
+  }
+}
+
+static int check_conv(const BhsrHeadConvDesc& d) {
+  BHSR_REQUIRE(d.x && d.weight && d.y, "head_conv: null pointer");
+  BHSR_REQUIRE(d.ksize == 1 || d.ksize == 3, "head_conv: kernel size must be 1 or 3");
+  BHSR_REQUIRE(d.nb > 0 && d.cin > 0 && d.cout > 0 && d.h > 0 && d.w > 0, "head_conv: bad shape");
+  BHSR_REQUIRE(!d.x_unshuffle || d.cin % 4 == 0, "head_conv: unshuffled input needs cin % 4 == 0");
+  BHSR_REQUIRE(!d.y_shuffle || d.cout % 4 == 0, "head_conv: shuffled output needs cout % 4 == 0");
+  BHSR_REQUIRE(d.nb <= 65535, "head_conv: batch too large");
+  return 0;
+}
+
+static ConvArgs to_args(const BhsrHeadConvDesc& d) {
+  ConvArgs a{};
+  a.x = d.x; a.x_ctot = d.x_ctot; a.x_choff = d.x_choff;
+  a.nb = d.nb; a.cin = d.cin; a.h = d.h; a.w = d.w;
+  a.x_unshuffle = d.x_unshuffle;
+  a.in_scale = d.in_scale; a.in_shift = d.in_shift; a.in_relu = d.in_relu;
+  a.wgt = d.weight; a.bias = d.bias; a.cout = d.cout;
+  a.y = d.y; a.y_ctot = d.y_ctot; a.y_choff = d.y_choff; a.y_shuffle = d.y_shuffle;
+  a.stats = d.stats; a.accumulate = d.accumulate;
+  return a;
+}
+
+}  // namespace bhsr
+
+using namespace bhsr;
+
+extern "C" int bhsr_head_conv(const BhsrHeadConvDesc* dp, void* stream_) {
+  BHSR_REQUIRE(dp, "head_conv: null descriptor");
+  int rc = check_conv(*dp);
+  if (rc) return rc;
+  const BhsrHeadConvDesc& d = *dp;
+  ConvArgs a = to_args(d);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int tiles = ((d.w + kTW - 1) / kTW) * ((d.h + kTH - 1) / kTH);
+  dim3 block(kTW, kTH);
+  if (d.cout <= 8) {
+    dim3 grid(tiles, 1, d.nb);
+    if (d.ksize == 3) conv_fwd_kernel<3, 8><<<grid, block, 0, st>>>(a);
+    else conv_fwd_kernel<1, 8><<<grid, block, 0, st>>>(a);
+  } else {
+    dim3 grid(tiles, (d.cout + 15) / 16, d.nb);
+    if (d.ksize == 3) conv_fwd_kernel<3, 16><<<grid, block, 0, st>>>(a);
+    else conv_fwd_kernel<1, 16><<<grid, block, 0, st>>>(a);
+  }
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhsr_head_conv_wgrad(const BhsrHeadConvDesc* dp, const float* dy, int32_t dy_ctot,
+                                    int32_t dy_choff, int32_t dy_unshuffle, float* dw, float* db,
+                                    void* stream_) {
+  BHSR_REQUIRE(dp && dy && dw, "head_conv_wgrad: null pointer");
+  BhsrHeadConvDesc d = *dp;
+  BHSR_REQUIRE(d.x && (d.ksize == 1 || d.ksize == 3) && d.nb > 0, "head_conv_wgrad: bad descriptor");
+  WgradArgs w{};
+  w.in = to_args(d);
+  w.dy = dy; w.dy_ctot = dy_ctot; w.dy_choff = dy_choff; w.dy_unshuffle = dy_unshuffle;
+  w.cout = d.cout; w.dw = dw; w.db = db;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  BHSR_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * d.cout * d.cin * d.ksize * d.ksize, st));
+  if (db) BHSR_CUDA_CHECK(cudaMemsetAsync(db, 0, sizeof(float) * d.cout, st));
+  const int tiles = ((d.w + kTW - 1) / kTW) * ((d.h + kTH - 1) / kTH) * d.nb;
+  int sms = device_sm_count();
+  int grid = tiles < sms * 4 ? tiles : sms * 4;
+  for (int co0 = 0; co0 < d.cout; co0 += 16)
+    for (int c0 = 0; c0 < d.cin; c0 += kCI) {
+      if (d.ksize == 3) conv_wgrad_kernel<3><<<grid, 256, 0, st>>>(w, co0, c0);
+      else conv_wgrad_kernel<1><<<grid, 256, 0, st>>>(w, co0, c0);
+    }
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhsr_bn_finalize(const double* stats, int32_t c, double count, const float* gamma,
+                                const float* beta, float eps, float momentum, float* running_mean,
+                                float* running_var, float* scale, float* shift, float* mean,
+                                float* invstd, void* stream) {
+  BHSR_REQUIRE(stats && scale && shift && c > 0 && count > 0, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(c + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, c, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
+      invstd);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhsr_bn_eval_affine(int32_t c, const float* gamma, const float* beta,
+                                   const float* running_mean, const float* running_var, float eps,
+                                   float* scale, float* shift, float* invstd, void* stream) {
+  BHSR_REQUIRE(running_mean && running_var && scale && shift && c > 0, "bn_eval_affine: bad arguments");
+  bn_eval_affine_kernel<<<(c + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      c, gamma, beta, running_mean, running_var, eps, scale, shift, invstd);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static unsigned ew_blocks(size_t total) {
+  int sms = device_sm_count();
+  size_t b = (total + 255) / 256;
+  size_t cap = static_cast<size_t>(sms > 0 ? sms : 148) * 16;
+  return static_cast<unsigned>(b < cap ? (b ? b : 1) : cap);
+}
+
+extern "C" int bhsr_affine_add_relu(const float* a, const float* sa, const float* ta,
+                                    const float* b, int32_t b_ctot, int32_t b_choff,
+                                    const float* sb, const float* tb, int32_t nb, int32_t c,
+                                    int32_t hw, float* out, int32_t o_ctot, int32_t o_choff,
+                                    void* stream) {
+  BHSR_REQUIRE(a && sa && ta && b && out, "affine_add_relu: null pointer");
+  const size_t total = static_cast<size_t>(nb) * c * hw;
+  affine_add_relu_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, sa, ta, b, b_ctot, b_choff, sb, tb, nb, c, hw, out, o_ctot, o_choff);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhsr_bn_bwd_reduce(const float* g_out, int32_t g_ctot, int32_t g_choff,
+                                  const float* out, int32_t o_ctot, int32_t o_choff, const float* a,
+                                  const float* sa, const float* ta, const float* b, int32_t b_ctot,
+                                  int32_t b_choff, int32_t nb, int32_t c, int32_t hw, double* sums,
+                                  void* stream) {
+  BHSR_REQUIRE(g_out && a && sums && (out || (sa && ta)), "bn_bwd_reduce: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BHSR_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * c, st));
+  const size_t per = static_cast<size_t>(nb) * hw;
+  unsigned bx = static_cast<unsigned>((per + 255) / 256);
+  if (bx > 256) bx = 256;
+  bn_bwd_reduce_kernel<<<dim3(bx, c), 256, 0, st>>>(g_out, g_ctot, g_choff, out, o_ctot, o_choff, a,
+                                                    sa, ta, b, b_ctot, b_choff, nb, c, hw, sums);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhsr_bn_bwd_coeffs(const double* sums, int32_t which, int32_t c, double count,
+                                  const float* gamma, const float* mean, const float* invstd,
+                                  const float* scale_eval, int32_t training, float* k1, float* k2,
+                                  float* k3, float* dgamma, float* dbeta, void* stream) {
+  BHSR_REQUIRE(sums && k1 && k2 && k3 && c > 0, "bn_bwd_coeffs: null pointer");
+  BHSR_REQUIRE(training ? (mean && invstd) : scale_eval != nullptr, "bn_bwd_coeffs: missing statistics");
+  bn_bwd_coeffs_kernel<<<(c + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, which, c, count, gamma, mean, invstd, scale_eval, training, k1, k2, k3, dgamma, dbeta);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhsr_bn_bwd_apply(const float* g_out, int32_t g_ctot, int32_t g_choff,
+                                 const float* out, int32_t o_ctot, int32_t o_choff, const float* a,
+                                 const float* sa, const float* ta, const float* k1, const float* k2,
+                                 const float* k3, float* g_a, const float* b, int32_t b_ctot,
+                                 int32_t b_choff, const float* kb1, const float* kb2,
+                                 const float* kb3, float* g_b, int32_t gb_ctot, int32_t gb_choff,
+                                 int32_t gb_accumulate, int32_t nb, int32_t c, int32_t hw,
+                                 void* stream) {
+  BHSR_REQUIRE(g_out && a && k1 && k2 && k3 && g_a && (out || (sa && ta)), "bn_bwd_apply: null pointer");
+  const size_t total = static_cast<size_t>(nb) * c * hw;
+  bn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g_out, g_ctot, g_choff, out, o_ctot, o_choff, a, sa, ta, k1, k2, k3, g_a, b, b_ctot, b_choff,
+      kb1, kb2, kb3, g_b, gb_ctot, gb_choff, gb_accumulate, nb, c, hw);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhsr_aggregate(const float* x, int32_t nimg, int32_t h, int32_t w, int32_t step,
+                              float threshold, int32_t strict, float* out, void* stream) {
+  BHSR_REQUIRE(x && out && nimg > 0 && step > 0 && h >= step && w >= step, "aggregate: bad arguments");
+  const size_t total = static_cast<size_t>(nimg) * (h / step) * (w / step);
+  aggregate_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, nimg, h, w, step, threshold, strict, out);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

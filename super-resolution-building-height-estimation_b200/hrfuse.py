@@ -1,0 +1,516 @@
+"""Drop-in HR/LR fusion head modules on the B200 kernels (reference: SR/HRfuse.py).
+
+Same classes, constructor kwargs, child names and state_dict keys as the reference
+(`Upsampler` :17-44, `BasicBlock` :109-159, `HRfeature` :164-169, `HRfuse_residual` :173-190,
+`HRupsample` :193-202, `GeoNet` :205-213, `Refine_residual` :216-228).  nn.Conv2d / nn.BatchNorm2d
+children are parameter containers; arithmetic runs in libbhsr.so (head.cu) through two
+autograd Functions — a plain conv (optionally with the PixelShuffle(2) scatter fused) and a whole
+BasicBlock (conv-BN-ReLU-conv-BN-(1x1 conv-BN)-add-ReLU) with hand-written backward kernels.
+fp32 NCHW throughout; CUDA tensors only (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from ._lib import HeadConvDesc
+
+
+# ------------------------------------------------------------------ kernel wrappers
+def _st(t):
+    return _lib.stream_ptr(t.device)
+
+
+def _prep(x: Tensor, name="x") -> Tensor:
+    _lib.require_cuda(x, name)
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous()
+
+
+def _conv(x: Tensor, w: Tensor, b: Optional[Tensor] = None, *, in_affine=None, in_relu=False,
+          y: Optional[Tensor] = None, y_shuffle=False, x_unshuffle=False, stats: Optional[Tensor] = None,
+          accumulate=False) -> Tensor:
+    """bhsr_head_conv on contiguous NCHW tensors.  x_unshuffle: x is the PixelShuffle(2)-ed layout
+    of the conv's logical input (used by backward); y_shuffle: write through PixelShuffle(2)."""
+    cout, cin, k, _ = w.shape
+    nb = x.shape[0]
+    if x_unshuffle:
+        assert x.shape[1] * 4 == cin
+        h, wd = x.shape[2] // 2, x.shape[3] // 2
+    else:
+        assert x.shape[1] == cin, (x.shape, w.shape)
+        h, wd = x.shape[2], x.shape[3]
+    if y is None:
+        shape = (nb, cout // 4, 2 * h, 2 * wd) if y_shuffle else (nb, cout, h, wd)
+        y = torch.empty(shape, dtype=torch.float32, device=x.device)
+    d = HeadConvDesc()
+    d.x, d.x_ctot, d.x_choff = x.data_ptr(), x.shape[1], 0
+    d.nb, d.cin, d.h, d.w = nb, cin, h, wd
+    d.x_unshuffle = int(x_unshuffle)
+    if in_affine is not None:
+        d.in_scale, d.in_shift = in_affine[0].data_ptr(), in_affine[1].data_ptr()
+    d.in_relu = int(in_relu)
+    d.weight, d.bias = w.data_ptr(), _lib.ptr(b)
+    d.cout, d.ksize = cout, k
+    d.y, d.y_ctot, d.y_choff = y.data_ptr(), y.shape[1], 0
+    d.y_shuffle = int(y_shuffle)
+    d.stats = _lib.ptr(stats)
+    d.accumulate = int(accumulate)
+    _lib.check(_lib.load().bhsr_head_conv(C.byref(d), _st(x)), "bhsr_head_conv")
+    return y
+
+
+def _wgrad(x: Tensor, dy: Tensor, cout: int, cin: int, k: int, *, in_affine=None, in_relu=False,
+           dy_unshuffle=False, want_db=False):
+    nb, _, h, wd = x.shape
+    d = HeadConvDesc()
+    d.x, d.x_ctot, d.x_choff = x.data_ptr(), x.shape[1], 0
+    d.nb, d.cin, d.h, d.w = nb, cin, h, wd
+    if in_affine is not None:
+        d.in_scale, d.in_shift = in_affine[0].data_ptr(), in_affine[1].data_ptr()
+    d.in_relu = int(in_relu)
+    d.cout, d.ksize = cout, k
+    dw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_db else None
+    _lib.check(_lib.load().bhsr_head_conv_wgrad(C.byref(d), dy.data_ptr(), dy.shape[1], 0, int(dy_unshuffle),
+                                                dw.data_ptr(), _lib.ptr(db), _st(x)), "bhsr_head_conv_wgrad")
+    return dw, db
+
+
+def _transpose_weight(w: Tensor) -> Tensor:
+    """Weights of the data-gradient conv: swap in/out channels, rotate the 3x3 kernel by 180 deg."""
+    return w.flip(2, 3).transpose(0, 1).contiguous()
+
+
+def _f32(n, dev):
+    return torch.empty(n, dtype=torch.float32, device=dev)
+
+
+class _BNState:
+    """scale/shift for the fused apply + mean/invstd for backward of one BatchNorm."""
+
+    __slots__ = ("scale", "shift", "mean", "invstd")
+
+
+def _bn_from_stats(stats: Tensor, count: int, bn: "_BNParams", training_update: bool) -> _BNState:
+    c = bn.gamma.numel()
+    s = _BNState()
+    s.scale, s.shift, s.mean, s.invstd = (_f32(c, stats.device) for _ in range(4))
+    rm = bn.running_mean if training_update else None
+    rv = bn.running_var if training_update else None
+    _lib.check(_lib.load().bhsr_bn_finalize(stats.data_ptr(), c, float(count), bn.gamma.data_ptr(),
+                                            bn.beta.data_ptr(), bn.eps, bn.momentum, _lib.ptr(rm),
+                                            _lib.ptr(rv), s.scale.data_ptr(), s.shift.data_ptr(),
+                                            s.mean.data_ptr(), s.invstd.data_ptr(), _st(stats)),
+               "bhsr_bn_finalize")
+    return s
+
+
+def _bn_eval(bn: "_BNParams") -> _BNState:
+    c = bn.gamma.numel()
+    dev = bn.gamma.device
+    s = _BNState()
+    s.scale, s.shift, s.invstd = _f32(c, dev), _f32(c, dev), _f32(c, dev)
+    s.mean = bn.running_mean
+    _lib.check(_lib.load().bhsr_bn_eval_affine(c, bn.gamma.data_ptr(), bn.beta.data_ptr(),
+                                               bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                               bn.eps, s.scale.data_ptr(), s.shift.data_ptr(),
+                                               s.invstd.data_ptr(), _st(bn.gamma)), "bhsr_bn_eval_affine")
+    return s
+
+
+class _BNParams:
+    """Detached views of one nn.BatchNorm2d's tensors (gamma, beta, running stats)."""
+
+    def __init__(self, gamma, beta, running_mean, running_var, eps, momentum):
+        self.gamma, self.beta = gamma, beta
+        self.running_mean, self.running_var = running_mean, running_var
+        self.eps = float(eps)
+        self.momentum = float(momentum if momentum is not None else 0.1)
+
+
+# ------------------------------------------------------------------ autograd: plain conv
+class _ConvFn(torch.autograd.Function):
+    """y = conv_k(x) + b, optionally scattered through PixelShuffle(2)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, shuffle):
+        x = _prep(x)
+        w = w.contiguous()
+        ctx.save_for_backward(x, w)
+        ctx.shuffle = bool(shuffle)
+        ctx.has_bias = b is not None
+        return _conv(x, w, b, y_shuffle=bool(shuffle))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        cout, cin, k, _ = w.shape
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = _wgrad(x, g, cout, cin, k, dy_unshuffle=ctx.shuffle, want_db=ctx.has_bias)
+        if ctx.needs_input_grad[0]:
+            dx = _conv(g, _transpose_weight(w), None, x_unshuffle=ctx.shuffle)
+        return dx, dw, db, None
+
+
+def conv2d(x, weight, bias=None, pixel_shuffle=False):
+    return _ConvFn.apply(x, weight, bias, pixel_shuffle)
+
+
+# ------------------------------------------------------------------ autograd: BasicBlock
+class _BasicBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, training, bn_cfg, w1, g1, b1, w2, g2, b2, wd, gd, bd, *buffers):
+        # buffers: rm1, rv1, rm2, rv2 [, rmd, rvd]  (updated in place in training mode)
+        x = _prep(x)
+        lib = _lib.load()
+        nb, cin, h, wdt = x.shape
+        planes = w1.shape[0]
+        dev = x.device
+        count = nb * h * wdt
+        eps, momentum = bn_cfg
+        bn1 = _BNParams(g1, b1, buffers[0], buffers[1], eps, momentum)
+        bn2 = _BNParams(g2, b2, buffers[2], buffers[3], eps, momentum)
+        bnd = _BNParams(gd, bd, buffers[4], buffers[5], eps, momentum) if wd is not None else None
+        w1c, w2c = w1.contiguous(), w2.contiguous()
+        wdc = wd.contiguous() if wd is not None else None
+
+        def stats_buf():
+            return torch.zeros(2 * planes, dtype=torch.float64, device=dev) if training else None
+
+        st1 = stats_buf()
+        c1 = _conv(x, w1c, None, stats=st1)
+        s1 = _bn_from_stats(st1, count, bn1, True) if training else _bn_eval(bn1)
+        st2 = stats_buf()
+        c2 = _conv(c1, w2c, None, in_affine=(s1.scale, s1.shift), in_relu=True, stats=st2)
+        s2 = _bn_from_stats(st2, count, bn2, True) if training else _bn_eval(bn2)
+        d = sd = None
+        if wd is not None:
+            std = stats_buf()
+            d = _conv(x, wdc, None, stats=std)
+            sd = _bn_from_stats(std, count, bnd, True) if training else _bn_eval(bnd)
+        out = torch.empty((nb, planes, h, wdt), dtype=torch.float32, device=dev)
+        short = d if d is not None else x
+        _lib.check(lib.bhsr_affine_add_relu(c2.data_ptr(), s2.scale.data_ptr(), s2.shift.data_ptr(),
+                                            short.data_ptr(), short.shape[1], 0,
+                                            sd.scale.data_ptr() if sd else None,
+                                            sd.shift.data_ptr() if sd else None,
+                                            nb, planes, h * wdt, out.data_ptr(), planes, 0, _st(x)),
+                   "bhsr_affine_add_relu")
+        ctx.training = bool(training)
+        ctx.has_ds = wd is not None
+        ctx.count = count
+        tensors = [x, c1, c2, out, w1c, w2c, g1, g2, s1.scale, s1.shift, s1.mean, s1.invstd,
+                   s2.scale, s2.shift, s2.mean, s2.invstd]
+        if ctx.has_ds:
+            tensors += [d, wdc, gd, sd.scale, sd.shift, sd.mean, sd.invstd]
+        ctx.save_for_backward(*tensors)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        t = ctx.saved_tensors
+        (x, c1, c2, out, w1, w2, g1, g2, s1_scale, s1_shift, s1_mean, s1_inv,
+         s2_scale, s2_shift, s2_mean, s2_inv) = t[:16]
+        if ctx.has_ds:
+            d, wd, gd, sd_scale, sd_shift, sd_mean, sd_inv = t[16:]
+        g_out = g_out.contiguous()
+        nb, planes, h, wdt = out.shape
+        cin = x.shape[1]
+        hw = h * wdt
+        dev = x.device
+        st = _st(x)
+        count = float(ctx.count)
+        training = int(ctx.training)
+        need_x = ctx.needs_input_grad[0]
+
+        def coeffs(sums, which, gamma, mean, inv, scale_eval):
+            k = [_f32(planes, dev) for _ in range(3)]
+            dg, db = _f32(planes, dev), _f32(planes, dev)
+            _lib.check(lib.bhsr_bn_bwd_coeffs(sums.data_ptr(), which, planes, count, gamma.data_ptr(),
+                                              mean.data_ptr(), inv.data_ptr(), scale_eval.data_ptr(),
+                                              training, k[0].data_ptr(), k[1].data_ptr(), k[2].data_ptr(),
+                                              dg.data_ptr(), db.data_ptr(), st), "bhsr_bn_bwd_coeffs")
+            return k, dg, db
+
+        # ---- tail: out = relu(bn2(c2) + shortcut)
+        sums = torch.empty(3 * planes, dtype=torch.float64, device=dev)
+        short = d if ctx.has_ds else None
+        _lib.check(lib.bhsr_bn_bwd_reduce(g_out.data_ptr(), planes, 0, out.data_ptr(), planes, 0,
+                                          c2.data_ptr(), None, None, _lib.ptr(short), planes, 0,
+                                          nb, planes, hw, sums.data_ptr(), st), "bhsr_bn_bwd_reduce")
+        k2, dg2, db2 = coeffs(sums, 0, g2, s2_mean, s2_inv, s2_scale)
+        g_c2 = torch.empty_like(c2)
+        dgd = dbd = None
+        if ctx.has_ds:
+            kd, dgd, dbd = coeffs(sums, 1, gd, sd_mean, sd_inv, sd_scale)
+            g_short = torch.empty_like(d)
+            kb = [kk.data_ptr() for kk in kd]
+            want_short = True
+        else:
+            g_short = torch.empty_like(x) if need_x else None  # identity: g_x starts as g'
+            kb = [None, None, None]
+            want_short = need_x
+        _lib.check(lib.bhsr_bn_bwd_apply(g_out.data_ptr(), planes, 0, out.data_ptr(), planes, 0,
+                                         c2.data_ptr(), None, None,
+                                         k2[0].data_ptr(), k2[1].data_ptr(), k2[2].data_ptr(),
+                                         g_c2.data_ptr(), _lib.ptr(short), planes, 0, kb[0], kb[1], kb[2],
+                                         g_short.data_ptr() if want_short else None, planes, 0, 0,
+                                         nb, planes, hw, st), "bhsr_bn_bwd_apply")
+        # ---- conv2 (input a1 = relu(bn1(c1)) is re-materialised on the fly by the input transform)
+        dw2, _ = _wgrad(c1, g_c2, planes, planes, 3, in_affine=(s1_scale, s1_shift), in_relu=True)
+        g_a1 = _conv(g_c2, _transpose_weight(w2), None)
+        # ---- bn1 + relu
+        sums1 = torch.empty(3 * planes, dtype=torch.float64, device=dev)
+        _lib.check(lib.bhsr_bn_bwd_reduce(g_a1.data_ptr(), planes, 0, None, 0, 0, c1.data_ptr(),
+                                          s1_scale.data_ptr(), s1_shift.data_ptr(), None, 0, 0,
+                                          nb, planes, hw, sums1.data_ptr(), st), "bhsr_bn_bwd_reduce")
+        k1, dg1, db1 = coeffs(sums1, 0, g1, s1_mean, s1_inv, s1_scale)
+        g_c1 = torch.empty_like(c1)
+        _lib.check(lib.bhsr_bn_bwd_apply(g_a1.data_ptr(), planes, 0, None, 0, 0, c1.data_ptr(),
+                                         s1_scale.data_ptr(), s1_shift.data_ptr(),
+                                         k1[0].data_ptr(), k1[1].data_ptr(), k1[2].data_ptr(),
+                                         g_c1.data_ptr(), None, 0, 0, None, None, None, None, 0, 0, 0,
+                                         nb, planes, hw, st), "bhsr_bn_bwd_apply")
+        # ---- conv1 / shortcut
+        dw1, _ = _wgrad(x, g_c1, planes, cin, 3)
+        dwd = None
+        gx = None
+        if ctx.has_ds:
+            dwd, _ = _wgrad(x, g_short, planes, cin, 1)
+            if need_x:
+                gx = _conv(g_c1, _transpose_weight(w1), None)
+                _conv(g_short, _transpose_weight(wd), None, y=gx, accumulate=True)
+        elif need_x:
+            gx = g_short
+            _conv(g_c1, _transpose_weight(w1), None, y=gx, accumulate=True)
+        grads = [gx, None, None, dw1, dg1, db1, dw2, dg2, db2, dwd, dgd, dbd]
+        return tuple(grads) + (None,) * 6
+
+
+# ------------------------------------------------------------------ modules (reference surface)
+def default_conv(in_channels, out_channels, kernel_size, bias=True):
+    """SR/HRfuse.py:11-14."""
+    return nn.Conv2d(in_channels, out_channels, kernel_size, padding=(kernel_size // 2), bias=bias)
+
+
+class Upsampler(nn.Sequential):
+    """SR/HRfuse.py:17-44: (conv3x3 n->4n, PixelShuffle(2)) x log2(scale); the shuffle is the
+    conv kernel's scatter epilogue (pure index permutation, bit-exact)."""
+
+    def __init__(self, conv=default_conv, scale=4, n_feats=16, bn=False, act=False, bias=True):
+        m = []
+        if (scale & (scale - 1)) == 0:
+            for _ in range(int(math.log(scale, 2))):
+                m.append(conv(n_feats, 4 * n_feats, 3, bias))
+                m.append(nn.PixelShuffle(2))
+                if bn:
+                    m.append(nn.BatchNorm2d(n_feats))
+                if act == 'relu':
+                    m.append(nn.ReLU(True))
+                elif act == 'prelu':
+                    m.append(nn.PReLU(n_feats))
+        elif scale == 3:
+            m.append(conv(n_feats, 9 * n_feats, 3, bias))
+            m.append(nn.PixelShuffle(3))
+            if bn:
+                m.append(nn.BatchNorm2d(n_feats))
+            if act == 'relu':
+                m.append(nn.ReLU(True))
+            elif act == 'prelu':
+                m.append(nn.PReLU(n_feats))
+        else:
+            raise NotImplementedError
+        super().__init__(*m)
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(m, nn.Conv2d) and isinstance(nxt, nn.PixelShuffle) and nxt.upscale_factor == 2:
+                x = conv2d(x, m.weight, m.bias, pixel_shuffle=True)
+                i += 2
+            else:
+                raise NotImplementedError(
+                    f"Upsampler layer {type(m).__name__} (scale 3 / bn / act variants) has no B200 kernel; "
+                    "the reference only instantiates the default x4 conv+PixelShuffle(2) form")
+        return x
+
+
+def conv3x3(in_planes, out_planes, stride=1, groups=1, dilation=1):
+    """SR/HRfuse.py:92-103."""
+    return nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=stride, padding=dilation, groups=groups,
+                     bias=False, dilation=dilation)
+
+
+def conv1x1(in_planes, out_planes, stride=1):
+    """SR/HRfuse.py:105-107."""
+    return nn.Conv2d(in_planes, out_planes, kernel_size=1, stride=stride, bias=False)
+
+
+class BasicBlock(nn.Module):
+    """SR/HRfuse.py:109-159."""
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, groups: int = 1, base_width: int = 64,
+                 dilation: int = 1, norm_layer: Optional[Callable[..., nn.Module]] = None,
+                 expansion: int = 1) -> None:
+        super().__init__()
+        if norm_layer is None:
+            norm_layer = nn.BatchNorm2d
+        if groups != 1 or base_width != 64:
+            raise ValueError("BasicBlock only supports groups=1 and base_width=64")
+        if dilation > 1:
+            raise NotImplementedError("Dilation > 1 not supported in BasicBlock")
+        self.conv1 = conv3x3(inplanes, planes, stride)
+        self.bn1 = norm_layer(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = conv3x3(planes, planes)
+        self.bn2 = norm_layer(planes)
+        self.downsample = None
+        self.stride = stride
+        if stride != 1 or inplanes != planes * expansion:
+            self.downsample = nn.Sequential(conv1x1(inplanes, planes * expansion, stride),
+                                            norm_layer(planes * expansion))
+
+    def forward(self, x: Tensor) -> Tensor:
+        if self.stride != 1:
+            raise NotImplementedError("BasicBlock stride != 1 has no B200 kernel (the reference uses stride 1)")
+        bns = [self.bn1, self.bn2] + ([self.downsample[1]] if self.downsample is not None else [])
+        for bn in bns:
+            if not isinstance(bn, nn.BatchNorm2d) or not bn.affine or not bn.track_running_stats:
+                raise NotImplementedError("BasicBlock kernels expect affine nn.BatchNorm2d with running stats")
+        training = self.training
+        if training:
+            for bn in bns:
+                bn.num_batches_tracked.add_(1)
+        ds = self.downsample
+        args = [x, training, (self.bn1.eps, self.bn1.momentum),
+                self.conv1.weight, self.bn1.weight, self.bn1.bias,
+                self.conv2.weight, self.bn2.weight, self.bn2.bias,
+                ds[0].weight if ds is not None else None,
+                ds[1].weight if ds is not None else None,
+                ds[1].bias if ds is not None else None,
+                self.bn1.running_mean, self.bn1.running_var, self.bn2.running_mean, self.bn2.running_var]
+        if ds is not None:
+            args += [ds[1].running_mean, ds[1].running_var]
+        else:
+            args += [None, None]
+        return _BasicBlockFn.apply(*args)
+
+
+class HRfeature(nn.Sequential):
+    """SR/HRfuse.py:164-169."""
+
+    def __init__(self, in_chans, mid_chans=64, out_chans=64):
+        super().__init__(BasicBlock(in_chans, mid_chans, stride=1),
+                         BasicBlock(mid_chans, mid_chans, stride=1),
+                         BasicBlock(mid_chans, out_chans, stride=1))
+
+
+class HRfuse_residual(nn.Module):
+    """SR/HRfuse.py:173-190."""
+
+    def __init__(self, hr_chans=16, lr_chans=16, mid_chans=16, out_chans=3, upscale=4):
+        super().__init__()
+        self.upsampler = Upsampler(scale=upscale, n_feats=lr_chans)
+        self.fuse = nn.Sequential(BasicBlock(hr_chans + lr_chans, mid_chans, stride=1),
+                                  BasicBlock(mid_chans, mid_chans, stride=1),
+                                  BasicBlock(mid_chans, mid_chans, stride=1))
+        self.conv_last = nn.Conv2d(mid_chans, out_chans, 3, 1, 1)
+
+    def forward(self, x_lr, x_hr):
+        x_lr = self.upsampler(x_lr)
+        x = self.fuse(torch.cat([x_lr, x_hr], dim=1))  # LR first, as in the reference (:187)
+        return conv2d(x, self.conv_last.weight, self.conv_last.bias)
+
+
+class HRupsample(nn.Module):
+    """SR/HRfuse.py:193-202."""
+
+    def __init__(self, lr_chans=16, out_chans=3, upscale=4):
+        super().__init__()
+        self.upsampler = Upsampler(scale=upscale, n_feats=lr_chans)
+        self.conv_last = nn.Conv2d(lr_chans, out_chans, 3, 1, 1)
+
+    def forward(self, x):
+        x = self.upsampler(x)
+        return conv2d(x, self.conv_last.weight, self.conv_last.bias)
+
+
+class GeoNet(nn.Module):
+    """SR/HRfuse.py:205-213."""
+
+    def __init__(self, in_chans=4, mid_chans=16):
+        super().__init__()
+        self.feat = nn.Sequential(BasicBlock(in_chans, mid_chans, stride=1),
+                                  BasicBlock(mid_chans, mid_chans, stride=1),
+                                  BasicBlock(mid_chans, mid_chans, stride=1))
+
+    def forward(self, x):
+        return self.feat(x)
+
+
+class Refine_residual(nn.Module):
+    """SR/HRfuse.py:216-228."""
+
+    def __init__(self, hr_chans=16, lr_chans=16, mid_chans=16, out_chans=3):
+        super().__init__()
+        self.fuse = nn.Sequential(BasicBlock(hr_chans + lr_chans, mid_chans, stride=1),
+                                  BasicBlock(mid_chans, mid_chans, stride=1),
+                                  BasicBlock(mid_chans, mid_chans, stride=1))
+        self.conv_last = nn.Conv2d(mid_chans, out_chans, 3, 1, 1)
+
+    def forward(self, x_lr, x_hr):
+        x = self.fuse(torch.cat([x_lr, x_hr], dim=1))
+        return conv2d(x, self.conv_last.weight, self.conv_last.bias)
+
+
+class _ConvBNReLUStack(nn.Sequential):
+    """The `fuse` stack of the HRfuse / HRfuse_x2 ablation heads (SR/HRfuse.py:51-57, 75-81):
+    conv3x3-BN-ReLU twice.  State-dict surface only: the ablation heads are never instantiated by
+    train.py / predict_realesanet_feature_globe.py and have no kernel schedule yet."""
+
+    def __init__(self, cin, mid):
+        super().__init__(nn.Conv2d(cin, mid, 3, 1, 1, bias=False), nn.BatchNorm2d(mid), nn.ReLU(inplace=True),
+                         nn.Conv2d(mid, mid, 3, 1, 1, bias=False), nn.BatchNorm2d(mid), nn.ReLU(inplace=True))
+
+    def forward(self, x):
+        raise NotImplementedError("HRfuse / HRfuse_x2 (ablation heads, SR/HRfuse.py:47-89) are outside the "
+                                  "B200 hot path; use HRfuse_residual")
+
+
+class HRfuse(nn.Module):
+    """SR/HRfuse.py:47-66 (ablation; parameter surface only)."""
+
+    def __init__(self, hr_channel=16, lr_channel=16, mid_channel=16, out_channel=3, upscale=4):
+        super().__init__()
+        self.fuse = _ConvBNReLUStack(hr_channel + lr_channel, mid_channel)
+        self.upsampler = Upsampler(scale=upscale, n_feats=mid_channel)
+        self.conv_last = nn.Conv2d(mid_channel, out_channel, 3, 1, 1)
+
+    def forward(self, x_lr, x_hr):
+        return self.fuse(torch.cat([x_lr, x_hr], dim=1))
+
+
+class HRfuse_x2(nn.Module):
+    """SR/HRfuse.py:69-89 (ablation; parameter surface only)."""
+
+    def __init__(self, hr_channel=16, lr_channel=16, mid_channel=16, out_channel=3, upscale=4):
+        super().__init__()
+        self.upsampler = Upsampler(scale=upscale, n_feats=mid_channel)
+        self.fuse = _ConvBNReLUStack(hr_channel + lr_channel, mid_channel)
+        self.conv_last = nn.Conv2d(mid_channel, out_channel, 3, 1, 1)
+
+    def forward(self, x_lr, x_hr):
+        return self.fuse(torch.cat([self.upsampler(x_lr), x_hr], dim=1))
