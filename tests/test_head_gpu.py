@@ -1,0 +1,178 @@
+"""GPU parity tests of the feature-aggregation head (SR/HRfuse.py, mymodels.py:259-293,
+aggregate_utils.py) — CUDA kernels through the C ABI vs the numpy oracle, the reference-generated
+goldens, and (for gradients) torch autograd of the torch-functional oracle on CPU."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from conftest import assert_close
+from oracle import ref_numpy as R
+from oracle import ref_torch as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def load_np_state(module, sd, dev):
+    module.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    return module.to(dev)
+
+
+def cuda(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def test_pixel_shuffle_scatter_bit_exact(dev):
+    """K7: the conv's PixelShuffle(2) scatter epilogue is a pure index permutation."""
+    from bhsr import hrfuse
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal((2, 8, 9, 13)).astype(np.float32)
+    w = np.zeros((8, 8, 3, 3), np.float32)
+    w[np.arange(8), np.arange(8), 1, 1] = 1.0   # identity conv
+    with torch.no_grad():
+        y = hrfuse.conv2d(cuda(x, dev), cuda(w, dev), None, pixel_shuffle=True).cpu().numpy()
+    assert np.array_equal(y, R.pixel_shuffle(x, 2))
+
+
+def test_upsampler_vs_golden(dev, golden):
+    from bhsr import hrfuse
+    sd = {}
+    synth.upsampler_state(np.random.RandomState(77), sd, "u", 16, 4)
+    m = load_np_state(hrfuse.Upsampler(scale=4, n_feats=16), {k[2:]: v for k, v in sd.items()}, dev)
+    lr = synth.features(2, 16, 16, 16, seed=22)
+    with torch.no_grad():
+        y = m(cuda(lr, dev)).cpu().numpy()
+    assert_close(y, golden["upsampler"], what="Upsampler")
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_hrfeature_and_hrfuse_vs_golden(dev, golden, training):
+    from bhsr import hrfuse
+    tag = "train" if training else "eval"
+    hr = synth.features(2, 64, 64, 64, seed=21)
+    lr = synth.features(2, 16, 16, 16, seed=22)
+    hr16 = synth.features(2, 16, 64, 64, seed=23)
+    m = load_np_state(hrfuse.HRfeature(64, 16, 16), synth.hrfeature_state(seed=31), dev)
+    m.train(training)
+    with torch.no_grad():
+        y = m(cuda(hr, dev)).cpu().numpy()
+    assert_close(y, golden[f"hrfeature_{tag}"], what=f"HRfeature {tag}")
+    if training:  # running statistics were updated exactly like nn.BatchNorm2d
+        for k, v in m.state_dict().items():
+            if "running" in k or "num_batches" in k:
+                np.testing.assert_allclose(v.cpu().numpy(), golden["hrfeature_train_buf." + k], rtol=1e-4,
+                                           atol=1e-5, err_msg=k)
+    for oc in (1, 7):
+        m = load_np_state(hrfuse.HRfuse_residual(16, 16, 16, oc, 4), synth.hrfuse_residual_state(out=oc, seed=40 + oc), dev)
+        m.train(training)
+        with torch.no_grad():
+            y = m(cuda(lr, dev), cuda(hr16, dev)).cpu().numpy()
+        assert y.shape == (2, oc, 64, 64)
+        assert_close(y, golden[f"hrfuse_out{oc}_{tag}"], what=f"HRfuse_residual out={oc} {tag}")
+
+
+def _grad_reference(sd, lr, hr16, training, oc):
+    """torch autograd through the torch-functional oracle on CPU (fp64 for a clean reference)."""
+    p = {k: torch.from_numpy(np.ascontiguousarray(v)).double().requires_grad_(v.dtype == np.float32 and "running" not in k)
+         if v.dtype != np.int64 else torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+    a = torch.from_numpy(lr).double().requires_grad_(True)
+    b = torch.from_numpy(hr16).double().requires_grad_(True)
+    y = T.hrfuse_residual(a, b, p, training=training)
+    g = torch.from_numpy(np.random.RandomState(5).standard_normal(tuple(y.shape))).double()
+    (y * g).sum().backward()
+    grads = {k: v.grad.numpy() for k, v in p.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    return y.detach().numpy(), g.numpy(), a.grad.numpy(), b.grad.numpy(), grads
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_hrfuse_residual_backward(dev, training):
+    """dgrad / wgrad / BatchNorm backward kernels vs autograd of the oracle."""
+    from bhsr import hrfuse
+    oc = 7
+    sd = synth.hrfuse_residual_state(out=oc, seed=47)
+    lr = synth.features(2, 16, 8, 8, seed=1)
+    hr16 = synth.features(2, 16, 32, 32, seed=2)
+    yref, g, ga_ref, gb_ref, grads_ref = _grad_reference(sd, lr, hr16, training, oc)
+    m = load_np_state(hrfuse.HRfuse_residual(16, 16, 16, oc, 4), sd, dev)
+    m.train(training)
+    a = cuda(lr, dev).requires_grad_(True)
+    b = cuda(hr16, dev).requires_grad_(True)
+    y = m(a, b)
+    (y * cuda(g.astype(np.float32), dev)).sum().backward()
+    assert_close(y.detach().cpu().numpy(), yref, what="forward")
+    scale = lambda r: 1e-4 * max(1.0, float(np.abs(r).max()))
+    assert_close(a.grad.cpu().numpy(), ga_ref, rtol=2e-3, atol=scale(ga_ref), what="grad x_lr")
+    assert_close(b.grad.cpu().numpy(), gb_ref, rtol=2e-3, atol=scale(gb_ref), what="grad x_hr")
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        assert_close(p.grad.cpu().numpy(), grads_ref[name], rtol=2e-3, atol=scale(grads_ref[name]), what=f"grad {name}")
+
+
+def test_srregress_head_vs_oracle(dev):
+    """hrfeat + reg + seg + aggre_height wiring of SRRegress_Cls_feature.forward (mymodels.py:270-293)
+    given the decoder features (the smp part is third-party, not under test here)."""
+    from bhsr.models import SRRegress_Cls_feature
+    net = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64,
+                                super_mid=16, upscale=4, isaggre=True, chans_build=7)
+    sd = synth.head_state(64, 16, 7, True, seed=100)
+    missing, unexpected = net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not unexpected and all(k.split(".")[0] in ("encoder", "decoder1", "decoder2") for k in missing)
+    net = net.to(dev).eval()
+    x = synth.tiles(2, 8, seed=3)
+    sf = synth.features(2, 64, 256, 256, seed=4)
+    with torch.no_grad():
+        enc = net.encoder(cuda(x, dev))
+        hfea = net.decoder1(*enc)
+        bfea = net.decoder2(*enc)
+        height, build, aggre = net(cuda(x, dev), cuda(sf, dev))
+    assert height.shape == (2, 1, 256, 256) and build.shape == (2, 7, 256, 256) and aggre.shape == (2, 1, 64, 64)
+    ref = R.srregress_head(hfea.cpu().numpy(), bfea.cpu().numpy(), sf, sd, True, acc_dtype=np.float64)
+    assert_close(height.cpu().numpy(), ref[0], what="height")
+    assert_close(build.cpu().numpy(), ref[1], what="build")
+    assert_close(aggre.cpu().numpy(), ref[2], what="height_aggre")
+    with torch.no_grad():
+        assert net.forward_unsup(cuda(x, dev), cuda(sf, dev)).shape == (2, 256, 256)
+        h2, a2 = net.forward_nobuild(cuda(x, dev), cuda(sf, dev))
+    assert torch.equal(h2, height) and torch.equal(a2, aggre)
+
+
+def test_full_pipeline_train_step(dev):
+    """train.py:243-257 in miniature: frozen RRDBNet features -> head -> weighted MSE -> backward;
+    every trainable parameter of the head receives a finite gradient."""
+    from bhsr.models import SRRegress_Cls_feature
+    from bhsr.rrdbnet import RRDBNet
+    torch.manual_seed(0)
+    net_g = RRDBNet(3, 3, scale=4, num_feat=64, num_block=1, num_grow_ch=32).to(dev).eval()
+    for p in net_g.parameters():
+        p.requires_grad = False
+    net = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64,
+                                super_mid=16, upscale=4, isaggre=True, chans_build=7).to(dev).train()
+    x = cuda(synth.tiles(2, 8, seed=9), dev)
+    with torch.no_grad():
+        hr_fea = net_g.forward_feature(x[:, [0, 1, 2]])
+    height, build, aggre = net(x, hr_fea)
+    target = torch.rand_like(height) * 30
+    weight = torch.rand_like(height)
+    loss = ((height - target) ** 2 * weight).mean() + build.mean() + aggre.mean()
+    loss.backward()
+    used = [n for n, p in net.named_parameters() if not n.startswith("encoder._conv_head") and not n.startswith("encoder._bn1")]
+    for n, p in net.named_parameters():
+        if n in used:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_aggregate_kernel_vs_golden(dev, golden):
+    from bhsr import aggregate
+    x = golden["aggregate_in"]
+    y = aggregate.aggregate_torch(cuda(x, dev), 0.25)
+    assert y.shape == (64, 64)
+    assert_close(y.cpu().numpy(), golden["aggregate_torch"], rtol=1e-6, atol=1e-6, what="aggregate_torch")
+    y2 = aggregate.aggregate_torch_gpu(cuda(x, dev), 0.25, device=dev)
+    assert y2.shape == (1, 1, 64, 64)
+    assert_close(y2.cpu().numpy(), golden["aggregate_torch_gpu"], rtol=1e-5, atol=1e-3, what="aggregate_torch_gpu")
