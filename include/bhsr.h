@@ -92,6 +92,10 @@ typedef struct BhsrConvTcDesc {
 } BhsrConvTcDesc;
 
 int bhsr_conv_tc(const BhsrConvTcDesc* desc, void* stream);
+/* Debug aid (BHSR_DEBUG_TIMING=1): per-CTA cycle counters of the last bhsr_conv_tc launch's MMA
+ * warp — {total, wait accumulator-free, wait activation tile, wait weight slab, tiles, 0,0,0};
+ * synchronises. */
+int bhsr_debug_timing(long long* host_out, int32_t n_ctas);
 
 /* bytes of the packed weight blob for one conv */
 size_t bhsr_packed_conv_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps, int32_t numerics);

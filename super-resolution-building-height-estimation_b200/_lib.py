@@ -96,6 +96,7 @@ _SIGNATURES = {
     "bhsr_device_sm_count": (C.c_int, []),
     "bhsr_device_cc": (C.c_int, []),
     "bhsr_conv_tc": (C.c_int, [C.POINTER(ConvTcDesc), C.c_void_p]),
+    "bhsr_debug_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "bhsr_packed_conv_weight_bytes": (C.c_size_t, [C.c_int32] * 4),
     "bhsr_pack_conv_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p]),

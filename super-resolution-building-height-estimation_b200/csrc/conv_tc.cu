@@ -65,6 +65,7 @@ struct ConvTcKernelParams {
   int res2_ctot, res2_choff;
   int wslots, w_resident;
   int desc_mode;
+  long long* dbg;  // optional [grid][8] cycle counters of the MMA warp (BHSR_DEBUG_TIMING)
 };
 
 template <int MB>
@@ -224,17 +225,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     const uint32_t desc_lo0 = static_cast<uint32_t>(desc_hi_lo0);  // LBO field, start = 0
     auto mk = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
     uint32_t a_it = 0, w_it = 0, tile_it = 0;
+    long long t_tempty = 0, t_afull = 0, t_wfull = 0, t_total = clock64(), tq;
+    const bool dbg = p.dbg != nullptr;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int flat_mod = (t * MT) % kPitch;
       const int as = tile_it & 1;
+      if (dbg) tq = clock64();
       mbar_wait(bar(B_TEMPTY + as), ((tile_it >> 1) & 1) ^ 1);
+      if (dbg) t_tempty += clock64() - tq;
       tc_fence_after();
       const uint32_t acc = tmem_base + as * ACC_COLS;
       uint32_t accumulate = 0;
       for (int c = 0; c < p.n_chunks; ++c, ++a_it) {
         const int st = a_it & 1;
+        if (dbg) tq = clock64();
         mbar_wait(bar(B_AFULL + st), (a_it >> 1) & 1);
+        if (dbg) t_afull += clock64() - tq;
         tc_fence_after();
         // descriptor low word of flat row 0 (tap shift 0, m-block 0) of this stage
         const uint32_t a_lo0 =
@@ -251,48 +258,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             }
           } else {
             ws = w_it % p.wslots;
+            if (dbg) tq = clock64();
             mbar_wait(bar(B_WFULL + ws), (w_it / p.wslots) & 1);
+            if (dbg) t_wfull += clock64() - tq;
             tc_fence_after();
           }
           const uint32_t b_lo = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
           const uint32_t a_lo = a_lo0 + p.tap_shift[tap] * 8;
           if (elect_one()) {
-            if (p.desc_mode == 0) {
 #pragma unroll
-              for (int mb = 0; mb < MB; ++mb) {
-                const uint32_t d_acc = acc + mb * ROWS_B;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < ksteps) {
-                    const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
-                    const uint64_t db = mk(b_lo + k * 2);
-                    umma_f16_ss(d_acc, da, db, IDESC_WIDE, k > 0 ? 1u : accumulate);
-                    if (EXACT) {
-                      const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
-                      umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
-                    }
-                  }
-                }
-              }
-            } else {
-              // TIMING EXPERIMENTS ONLY (results are wrong for desc_mode >= 3):
-              //  2: k-outer / m-block-inner issue order (independent accumulators interleaved)
-              //  3: as 2, and every k-step accumulates into its own TMEM columns
-              //  4: as 0 but every MMA targets its own TMEM columns (no dependent chains at all)
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint32_t d_acc = acc + mb * ROWS_B;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                for (int mb = 0; mb < MB; ++mb) {
-                  if (k < ksteps) {
-                    uint32_t d_acc = acc + mb * ROWS_B;
-                    if (p.desc_mode >= 3) d_acc = tmem_base + ((k * MB + mb) * ROWS_B) % (512 - ROWS_B);
-                    const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
-                    const uint64_t db = mk(b_lo + k * 2);
-                    umma_f16_ss(d_acc, da, db, IDESC_WIDE, k > 0 ? 1u : accumulate);
-                    if (EXACT) {
-                      const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
-                      umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
-                    }
+                if (k < ksteps) {
+                  const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
+                  const uint64_t db = mk(b_lo + k * 2);
+                  umma_f16_ss(d_acc, da, db, IDESC_WIDE, k > 0 ? 1u : accumulate);
+                  if (EXACT) {
+                    const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
+                    umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
                   }
                 }
               }
@@ -307,6 +292,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       }
       if (elect_one()) umma_commit(bar(B_TFULL + as));
       __syncwarp();
+    }
+    if (dbg && lane == 0) {
+      long long* o = p.dbg + blockIdx.x * 8;
+      o[0] = clock64() - t_total; o[1] = t_tempty; o[2] = t_afull; o[3] = t_wfull; o[4] = tile_it;
     }
   } else {
     // ------------------------------------------------ epilogue (warps 2..5)
@@ -407,6 +396,8 @@ static constexpr int a_stage_bytes(bool exact) {
   return TileGeom<MB>::kTileBytes * (exact ? 2 : 1);
 }
 
+static long long* g_dbg_buf = nullptr;
+
 static constexpr int kTailBytes = (8 + 2 * kMaxWSlots) * 8 + 16 + 64 * 4 + 64;
 
 static int make_act_map(CUtensorMap* tm, const void* base, int nb, int h, int w, int ctot,
@@ -487,6 +478,13 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
 
 using namespace bhsr;
 
+extern "C" int bhsr_debug_timing(long long* host_out, int32_t n_ctas) {
+  BHSR_REQUIRE(host_out && n_ctas > 0 && n_ctas <= 256, "debug_timing: bad arguments");
+  BHSR_REQUIRE(g_dbg_buf != nullptr, "debug_timing: BHSR_DEBUG_TIMING=1 was not set");
+  BHSR_CUDA_CHECK(cudaMemcpy(host_out, g_dbg_buf, sizeof(long long) * 8 * n_ctas, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" size_t bhsr_packed_conv_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps,
                                                 int32_t numerics) {
   const int chunks = (cin + 63) / 64;
@@ -553,6 +551,13 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   p.res2_lo = static_cast<const __half*>(d.res2_lo);
   p.res2_ctot = d.res2_ctot; p.res2_choff = d.res2_choff;
   p.desc_mode = d.desc_mode;
+  {
+    static const char* want = getenv("BHSR_DEBUG_TIMING");  // debug only: MMA-warp wait cycles
+    if (want && want[0] == '1') {
+      if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 256 * 8 * sizeof(long long));
+      p.dbg = g_dbg_buf;
+    }
+  }
 
   if (d.cout == 32) {
     if (exact) return launch<32, true, 1>(d, p, stream);

@@ -167,6 +167,16 @@ def run_case(name, desc_mode):
             ms = e0.elapsed_time(e1) / iters
             flops = 2.0 * nb * h * w * cout * cin * 9
             print(json.dumps({"case": name, "ms": ms, "tflops": flops / ms / 1e9}))
+            if os.environ.get("BHSR_DEBUG_TIMING") == "1":
+                import ctypes, numpy as np
+                from bhsr import _lib
+                buf = np.zeros((148, 8), dtype=np.int64)
+                _lib.check(_lib.load().bhsr_debug_timing(buf.ctypes.data, 148))
+                tiles = buf[:, 4].clip(min=1)
+                print(json.dumps({"case": name, "mma_warp_cycles_per_tile": {
+                    "total": float((buf[:, 0] / tiles).mean()), "wait_tmem_empty": float((buf[:, 1] / tiles).mean()),
+                    "wait_act": float((buf[:, 2] / tiles).mean()), "wait_weights": float((buf[:, 3] / tiles).mean()),
+                    "tiles_per_cta": float(tiles.mean())}}))
     torch.cuda.synchronize()
     err = (got - ref).abs()
     tol = 1e-5 + 1e-4 * ref.abs()  # loose here: fp16 hi/lo output quantisation is ~2^-22 relative
