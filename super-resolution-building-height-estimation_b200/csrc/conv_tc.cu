@@ -47,8 +47,7 @@ struct ConvTcKernelParams {
   int nb, h, w;
   int n_strips, tiles_per_strip, total_tiles;
   int in_choff, cin, n_chunks;
-  int ntaps;
-  int tap_shift[9];  // dy*66 + dx
+  int shift0;        // flat shift of the window's first tap: dy0*66 + dx0 (taps form a KS x KS window)
   int oh, ow, out_scale, out_oy, out_ox;
   __half* out_hi;
   __half* out_lo;
@@ -74,6 +73,10 @@ struct TileGeom {
   static constexpr int kTileBytesRaw = kRows * kPitch * 128;
   static constexpr int kTileBytes = (kTileBytesRaw + 1023) / 1024 * 1024;
 };
+
+// taps per weight slab: a whole window row, except where the slab would not fit a 2-slot ring
+template <int N, bool EXACT, int KS>
+struct SlabTaps { static constexpr int value = (EXACT && N == 64) ? 1 : KS; };
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
@@ -113,14 +116,17 @@ __device__ __forceinline__ void add_residual32(float (&v)[32], float alpha, cons
   }
 }
 
-template <int N, bool EXACT, int MB>
+template <int N, bool EXACT, int MB, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w, const ConvTcKernelParams p) {
   using G = TileGeom<MB>;
-  constexpr int ROWS_B = EXACT ? 2 * N : N;        // weight rows per tap slab (= TMEM columns)
-  constexpr int W_SLAB = ROWS_B * 128;             // bytes
+  constexpr int ROWS_B = EXACT ? 2 * N : N;        // weight rows per tap (= TMEM columns)
+  constexpr int NT = KS * KS;                      // taps: a dense KS x KS window
+  constexpr int TG = SlabTaps<N, EXACT, KS>::value;  // taps per weight slab (one barrier each)
+  constexpr int NG = NT / TG;                      // slabs per 64-channel chunk
+  constexpr int W_SLAB = TG * ROWS_B * 128;        // bytes
   constexpr int A_STAGE = G::kTileBytes * (EXACT ? 2 : 1);
   constexpr int A_TX = G::kTileBytesRaw * (EXACT ? 2 : 1);
   constexpr int ACC_COLS = MB * ROWS_B;            // TMEM columns per accumulator stage
@@ -202,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     // ------------------------------------------------ weight producer
     if (lane == 0) {
       uint32_t it = 0;
-      const int slabs = p.n_chunks * p.ntaps;
+      const int slabs = p.n_chunks * NG;
       bool first = true;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         if (p.w_resident && !first) break;
@@ -210,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
           const int ws = it % p.wslots;
           mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
           mbar_expect_tx(bar(B_WFULL + ws), W_SLAB);
-          tma_load_2d(w_base + ws * W_SLAB, &tm_w, bar(B_WFULL + ws), 0, sl * ROWS_B);
+          tma_load_2d(w_base + ws * W_SLAB, &tm_w, bar(B_WFULL + ws), 0, sl * (TG * ROWS_B));
         }
         first = false;
       }
@@ -245,13 +251,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         tc_fence_after();
         // descriptor low word of flat row 0 (tap shift 0, m-block 0) of this stage
         const uint32_t a_lo0 =
-            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1) * 8;
+            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1 + p.shift0) * 8;
         const int rem = p.cin - c * 64;
         const int ksteps = rem >= 64 ? 4 : (rem >> 4);
-        for (int tap = 0; tap < p.ntaps; ++tap, ++w_it) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g, ++w_it) {
           int ws;
           if (p.w_resident) {
-            ws = c * p.ntaps + tap;
+            ws = c * NG + g;
             if (tile_it == 0) {
               mbar_wait(bar(B_WFULL + ws), 0);
               tc_fence_after();
@@ -263,21 +270,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             if (dbg) t_wfull += clock64() - tq;
             tc_fence_after();
           }
-          const uint32_t b_lo = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
-          const uint32_t a_lo = a_lo0 + p.tap_shift[tap] * 8;
+          const uint32_t b_lo0 = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
           if (elect_one()) {
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-              const uint32_t d_acc = acc + mb * ROWS_B;
+            for (int tt = 0; tt < TG; ++tt) {
+              constexpr int kRowBytes16 = 8;  // one 128-byte flat row in descriptor units
+              const int tap = g * TG + tt;    // compile-time after unrolling
+              const uint32_t a_lo = a_lo0 + ((tap / KS) * kPitch + (tap % KS)) * kRowBytes16;
+              const uint32_t b_lo = b_lo0 + tt * (ROWS_B * 8);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < ksteps) {
-                  const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
-                  const uint64_t db = mk(b_lo + k * 2);
-                  umma_f16_ss(d_acc, da, db, IDESC_WIDE, k > 0 ? 1u : accumulate);
-                  if (EXACT) {
-                    const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
-                    umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
+              for (int mb = 0; mb < MB; ++mb) {
+                const uint32_t d_acc = acc + mb * ROWS_B;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps) {
+                    const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
+                    const uint64_t db = mk(b_lo + k * 2);
+                    umma_f16_ss(d_acc, da, db, IDESC_WIDE, (k > 0 || tt > 0) ? 1u : accumulate);
+                    if (EXACT) {
+                      const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
+                      umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
+                    }
                   }
                 }
               }
@@ -430,13 +443,14 @@ static int make_weight_map(CUtensorMap* tm, const void* base, int total_rows, in
   return 0;
 }
 
-template <int N, bool EXACT, int MB>
+template <int N, bool EXACT, int MB, int KS>
 static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream) {
   using G = TileGeom<MB>;
   constexpr int ROWS_B = EXACT ? 2 * N : N;
-  constexpr int W_SLAB = ROWS_B * 128;
+  constexpr int TG = SlabTaps<N, EXACT, KS>::value;
+  constexpr int W_SLAB = TG * ROWS_B * 128;
   constexpr int A_STAGE = G::kTileBytes * (EXACT ? 2 : 1);
-  const int slabs = p.n_chunks * p.ntaps;
+  const int slabs = p.n_chunks * (KS * KS / TG);
   int avail = kSmemLimit - 1024 /*alignment slack*/ - 2 * A_STAGE - kTailBytes;
   int wslots = avail / W_SLAB;
   if (wslots > kMaxWSlots) wslots = kMaxWSlots;
@@ -455,10 +469,10 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
   if (rc) return rc;
   rc = make_act_map(&tm_lo, EXACT ? d.in_lo : d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows);
   if (rc) return rc;
-  rc = make_weight_map(&tm_w, d.w_packed, slabs * ROWS_B, ROWS_B);
+  rc = make_weight_map(&tm_w, d.w_packed, slabs * TG * ROWS_B, TG * ROWS_B);
   if (rc) return rc;
 
-  auto kern = conv_tc_kernel<N, EXACT, MB>;
+  auto kern = conv_tc_kernel<N, EXACT, MB, KS>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     BHSR_CUDA_CHECK(
@@ -534,8 +548,13 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   p.tiles_per_strip = (d.h * kPitch + mt - 1) / mt;
   p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;
   p.in_choff = d.in_choff; p.cin = d.cin; p.n_chunks = (d.cin + 63) / 64;
-  p.ntaps = d.ntaps;
-  for (int t = 0; t < d.ntaps; ++t) p.tap_shift[t] = d.dy[t] * kPitch + d.dx[t];
+  // taps must form a dense KS x KS window in row-major order (3x3, or the 2x2 sub-pixel phases)
+  const int ks = d.ntaps == 9 ? 3 : (d.ntaps == 4 ? 2 : 0);
+  BHSR_REQUIRE(ks != 0, "conv_tc: ntaps must be 9 (3x3) or 4 (2x2 phase), got %d", d.ntaps);
+  for (int t = 0; t < d.ntaps; ++t)
+    BHSR_REQUIRE(d.dy[t] == d.dy[0] + t / ks && d.dx[t] == d.dx[0] + t % ks,
+                 "conv_tc: taps must be a dense %dx%d window in row-major order", ks, ks);
+  p.shift0 = d.dy[0] * kPitch + d.dx[0];
   p.oh = d.oh; p.ow = d.ow; p.out_scale = d.out_scale; p.out_oy = d.out_oy; p.out_ox = d.out_ox;
   p.out_hi = static_cast<__half*>(d.out_hi);
   p.out_lo = static_cast<__half*>(d.out_lo);
@@ -559,11 +578,16 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
     }
   }
 
+#define BHSR_DISPATCH(NN, EX, MBV)                                          \
+  return ks == 3 ? launch<NN, EX, MBV, 3>(d, p, stream) : launch<NN, EX, MBV, 2>(d, p, stream)
   if (d.cout == 32) {
-    if (exact) return launch<32, true, 1>(d, p, stream);
-    return mb == 2 ? launch<32, false, 2>(d, p, stream) : launch<32, false, 1>(d, p, stream);
+    if (exact) { BHSR_DISPATCH(32, true, 1); }
+    if (mb == 2) { BHSR_DISPATCH(32, false, 2); }
+    BHSR_DISPATCH(32, false, 1);
   } else {
-    if (exact) return launch<64, true, 1>(d, p, stream);
-    return mb == 2 ? launch<64, false, 2>(d, p, stream) : launch<64, false, 1>(d, p, stream);
+    if (exact) { BHSR_DISPATCH(64, true, 1); }
+    if (mb == 2) { BHSR_DISPATCH(64, false, 2); }
+    BHSR_DISPATCH(64, false, 1);
   }
+#undef BHSR_DISPATCH
 }

@@ -1,0 +1,175 @@
+"""Data-parallel harness around the hot path: one process per GPU,
+`torch.distributed` for plumbing, ONE collective per training step.
+
+* `MSE_adapt_weight`, `CE_DICE_adapt_weight` — the uncertainty-weighted losses applied right
+  after the hot path (losses_pytorch/selfloss.py:81-90, 145-168; the reference hard-codes
+  device="cuda" for log_var, here it follows the `device` argument).
+* `FlatGradAllReduce` — all trainable gradients live in one flat fp32 bucket (each `p.grad` is a
+  view into it), so a step needs a single NCCL all-reduce over NVLink (sum, then 1/world).
+* `train_step` — train.py:243-257 for one batch: frozen RRDBNet features under no_grad, head
+  forward, three weighted losses, backward, all-reduce, optimiser step.  No per-step host sync.
+* `predict_shard` — predict_realesanet_feature_globe.py:167-177 for the tiles of one rank:
+  features, head, clamp/round to uint16 (height*10) and softmax*255 (uint16), sharded rank::world.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class Dice(nn.Module):
+    """losses_pytorch/selfloss.py:6-17."""
+
+    def forward(self, pred, target):
+        smooth = 1.
+        num = pred.size(0)
+        m1 = pred.reshape(num, -1)
+        m2 = target.reshape(num, -1)
+        intersection = (m1 * m2).sum()
+        return 1 - (2. * intersection + smooth) / (m1.sum() + m2.sum() + smooth)
+
+
+class MSE_adapt_weight(nn.Module):
+    """mean(weight * (x - y)^2) * exp(-log_var) + log_var   (selfloss.py:81-90)."""
+
+    def __init__(self, log_var=0.0, device="cuda"):
+        super().__init__()
+        self.log_var = nn.Parameter(torch.tensor(float(log_var), device=device))
+
+    def forward(self, inputs, targets, weight):
+        loss = F.mse_loss(inputs, targets, reduction='none')
+        loss = (loss * weight).mean()
+        return loss * torch.exp(-self.log_var) + self.log_var
+
+
+class CE_DICE_adapt_weight(nn.Module):
+    """weighted CE + Dice on P(class>0), uncertainty weighted (selfloss.py:145-168)."""
+
+    def __init__(self, log_var=0.0, device="cuda"):
+        super().__init__()
+        self.ce = nn.CrossEntropyLoss(reduction='none')
+        self.dice = Dice()
+        self.log_var = nn.Parameter(torch.tensor(float(log_var), device=device))
+
+    def forward(self, pmask, rmask, weight):
+        loss_ce = (self.ce(pmask, rmask) * weight).mean()
+        p = pmask.softmax(dim=1)[:, 1:].sum(dim=1)
+        loss = loss_ce + self.dice(p, (rmask > 0))
+        return loss * torch.exp(-self.log_var) + self.log_var
+
+
+def shard_indices(n: int, rank: int, world: int) -> range:
+    """Tiles of rank `rank`: n items dealt round-robin (rank::world), SURVEY §8e."""
+    return range(rank, n, world)
+
+
+def broadcast_module(module: nn.Module, src: int = 0, group=None) -> None:
+    """DDP-style start: parameters and buffers of rank `src` to every rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+class FlatGradAllReduce:
+    """One flat fp32 gradient bucket for `params`; `p.grad` are views into it."""
+
+    def __init__(self, params: Iterable[nn.Parameter], group=None):
+        self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.group = group
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("FlatGradAllReduce expects fp32 parameters on one device")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @property
+    def numel(self) -> int:
+        return self.flat.numel()
+
+    def zero_(self) -> None:
+        """Use instead of optimizer.zero_grad(): keeps the views, zeroes the bucket."""
+        self.flat.zero_()
+        for p in self.params:  # an optimiser may have set grads to None
+            if p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or \
+                    p.grad.data_ptr() >= self.flat.data_ptr() + self.flat.numel() * 4:
+                raise RuntimeError("a parameter's .grad left the flat bucket; call optimizer.zero_grad(set_to_none=False) "
+                                   "or FlatGradAllReduce.zero_() only")
+
+    def all_reduce(self) -> None:
+        """Sum over ranks then average — the step's single collective."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(self.group)
+            if world > 1:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / world)
+
+
+def train_step(net_g, net, criterion: Sequence[nn.Module], optimizer, bucket: Optional[FlatGradAllReduce],
+               lr: torch.Tensor, height: torch.Tensor, height_aggre: torch.Tensor, build: torch.Tensor,
+               weight: torch.Tensor, weight_aggre: torch.Tensor, rgbseq=(0, 1, 2)) -> torch.Tensor:
+    """One iteration of train_epoch_aggre_weight (train.py:243-257); returns the (device) loss."""
+    with torch.no_grad():
+        hr_fea = net_g.forward_feature(lr[:, list(rgbseq)])
+    height_pred, build_pred, height_pred_aggre = net(lr, hr_fea)
+    height_pred = height_pred.squeeze(1)
+    height_pred_aggre = height_pred_aggre.squeeze(1)
+    loss = criterion[0](height_pred, height, weight) + \
+        criterion[1](height_pred_aggre, height_aggre, weight_aggre) + \
+        criterion[2](build_pred, build, weight)
+    if bucket is not None:
+        bucket.zero_()
+    else:
+        optimizer.zero_grad()
+    loss.backward()
+    if bucket is not None:
+        bucket.all_reduce()
+    optimizer.step()
+    return loss.detach()
+
+
+@torch.no_grad()
+def predict_shard(net_g, net, tiles: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """predict_realesanet_feature_globe.py:167-177 on a batch of tiles already on the GPU:
+    returns (height*10 as uint16-valued int32 [B,1,256,256], softmax*255 as int32 [B,K,256,256])
+    — torch has no uint16 arithmetic; values are the reference's uint16 numbers."""
+    hr_fea = net_g.forward_feature(tiles[:, :3])
+    ypred, build_pred = net(tiles, hr_fea)[:2]
+    ypred = torch.round(ypred.clamp_min(0) * 10).to(torch.int32)
+    build = torch.round(torch.softmax(build_pred, dim=1) * 255).to(torch.int32)
+    return ypred, build
+
+
+def synthetic_labels(nb: int, device, stats: Optional[torch.Tensor] = None, seed: int = 0,
+                     hir=(0, 3, 12, 21, 30, 60, 90, 256)):
+    """Synthetic targets shaped like the loader's (BH_loader.py:327-392): uint8-valued heights
+    (mostly zero), height-level classes via the `hir` LUT, inverse-sqrt-frequency weights, and the
+    4x4 aggregated height / weight."""
+    from .aggregate import aggregate_torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    h = torch.rand((nb, 256, 256), generator=g) * 60
+    h = torch.where(torch.rand((nb, 256, 256), generator=g) < 0.8245, torch.zeros(()), h).floor()
+    lut = torch.zeros(256, dtype=torch.long)
+    for i in range(len(hir) - 1):
+        lut[hir[i]:hir[i + 1]] = i
+    build = lut[h.long()]
+    if stats is None:
+        w_levels = torch.tensor([0.08743518, 0.26821995, 0.32067124, 0.73515255, 0.98135007, 1.60267172, 3.0044993])
+    else:
+        w_levels = stats
+    weight = w_levels[build]
+    h, build, weight = h.to(device), build.to(device), weight.to(device)
+    h_aggre = aggregate_torch(h.unsqueeze(1), 0.25).reshape(nb, 64, 64)
+    w_aggre = aggregate_torch(weight.unsqueeze(1), 0.25).reshape(nb, 64, 64)
+    return h, h_aggre, build, weight, w_aggre

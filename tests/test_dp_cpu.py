@@ -1,0 +1,93 @@
+"""Host-side logic of the data-parallel harness on CPU: world_size-2 gloo processes."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bhsr  # noqa: F401
+    from bhsr import dp
+    torch.manual_seed(100 + rank)          # different init per rank on purpose
+    net = nn.Sequential(nn.Linear(6, 5), nn.BatchNorm1d(5), nn.Linear(5, 1))
+    dp.broadcast_module(net, src=0)
+    bucket = dp.FlatGradAllReduce(net.parameters())
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    crit = dp.MSE_adapt_weight(0.0, device="cpu")
+    torch.manual_seed(7)
+    x_all, y_all = torch.randn(8, 6), torch.randn(8, 1)
+    idx = list(dp.shard_indices(8, rank, world))
+    for _ in range(3):
+        bucket.zero_()
+        loss = crit(net(x_all[idx]), y_all[idx], torch.ones(len(idx), 1))
+        loss.backward()
+        bucket.all_reduce()
+        opt.step()
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        out.put(([g.numpy() for g in gathered], bucket.numel, idx))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_all_reduce_keeps_replicas_in_sync():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    params, numel, idx0 = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(params[0], params[1]), "replicas diverged: gradients were not averaged identically"
+    assert numel == 6 * 5 + 5 + 5 + 5 + 5 + 1 and idx0 == [0, 2, 4, 6]
+
+
+def test_losses_match_their_closed_forms():
+    import bhsr  # noqa: F401
+    from bhsr import dp
+    from oracle import ref_numpy as R
+    rng = np.random.RandomState(0)
+    pred, tgt, w = (rng.rand(2, 8, 8).astype(np.float32) for _ in range(3))
+    crit = dp.MSE_adapt_weight(0.3, device="cpu")
+    got = crit(torch.from_numpy(pred), torch.from_numpy(tgt), torch.from_numpy(w)).item()
+    assert abs(got - R.weighted_mse_adapt(pred, tgt, w, 0.3)) < 1e-6
+    logits = torch.from_numpy(rng.standard_normal((2, 7, 8, 8)).astype(np.float32))
+    labels = torch.from_numpy(rng.randint(0, 7, (2, 8, 8)))
+    ce = dp.CE_DICE_adapt_weight(0.0, device="cpu")
+    val = ce(logits, labels, torch.from_numpy(w))
+    p = logits.softmax(1)[:, 1:].sum(1)
+    dice = 1 - (2 * (p * (labels > 0)).sum() + 1) / (p.sum() + (labels > 0).sum() + 1)
+    ref = (torch.nn.functional.cross_entropy(logits, labels, reduction="none") * torch.from_numpy(w)).mean() + dice
+    assert abs(val.item() - ref.item()) < 1e-6
+
+
+def test_bucket_guards_against_detached_grads():
+    import bhsr  # noqa: F401
+    from bhsr import dp
+    lin = nn.Linear(3, 2)
+    b = dp.FlatGradAllReduce(lin.parameters())
+    lin(torch.ones(1, 3)).sum().backward()
+    assert b.flat.abs().sum() > 0 and lin.weight.grad.data_ptr() == b.flat.data_ptr()
+    torch.optim.SGD(lin.parameters(), lr=0.1).zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError):
+        b.zero_()
