@@ -63,20 +63,23 @@ struct ConvTcKernelParams {
   const __half* res2_lo;
   int res2_ctot, res2_choff;
   int wslots, w_resident;
+  int astages;       // activation ring depth (2..kMaxAStages)
+  int pdl;           // launched with programmatic stream serialization
   int desc_mode;
   long long* dbg;  // optional [grid][8] cycle counters of the MMA warp (BHSR_DEBUG_TIMING)
 };
 
-template <int MB>
+// CH = input channels per shared-memory chunk: 64 (128-byte pixel rows, SWIZZLE_128B) in fast
+// numerics, 32 (64-byte rows, SWIZZLE_64B) in exact numerics, where every tile exists twice
+// (hi and lo planes) and the halved rows keep a 2-3 stage ring plus a weight ring in 227 KB.
+template <int MB, int CH>
 struct TileGeom {
+  static constexpr int kRowBytes = CH * 2;
   static constexpr int kRows = (MB == 1) ? 5 : 7;  // halo tile rows covering 128*MB + 2*67 px
-  static constexpr int kTileBytesRaw = kRows * kPitch * 128;
+  static constexpr int kTileBytesRaw = kRows * kPitch * kRowBytes;
   static constexpr int kTileBytes = (kTileBytesRaw + 1023) / 1024 * 1024;
 };
-
-// taps per weight slab: a whole window row, except where the slab would not fit a 2-slot ring
-template <int N, bool EXACT, int KS>
-struct SlabTaps { static constexpr int value = (EXACT && N == 64) ? 1 : KS; };
+constexpr int kMaxAStages = 4;
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
@@ -121,12 +124,17 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w, const ConvTcKernelParams p) {
-  using G = TileGeom<MB>;
+  constexpr int CH = EXACT ? 32 : 64;              // input channels per chunk
+  using G = TileGeom<MB, CH>;
+  constexpr int RB = G::kRowBytes;                 // bytes per pixel row in shared memory
+  constexpr int RB16 = RB / 16;                    // ... in descriptor (16-byte) units
+  constexpr int KSTEPS = CH / 16;                  // MMA k-steps per chunk
   constexpr int ROWS_B = EXACT ? 2 * N : N;        // weight rows per tap (= TMEM columns)
   constexpr int NT = KS * KS;                      // taps: a dense KS x KS window
-  constexpr int TG = SlabTaps<N, EXACT, KS>::value;  // taps per weight slab (one barrier each)
-  constexpr int NG = NT / TG;                      // slabs per 64-channel chunk
-  constexpr int W_SLAB = TG * ROWS_B * 128;        // bytes
+  constexpr int TG = KS;                           // taps per weight slab (one window row, one barrier)
+  constexpr int NG = NT / TG;                      // slabs per chunk
+  constexpr int W_TAP = ROWS_B * RB;               // bytes of one tap's weight tile
+  constexpr int W_SLAB = TG * W_TAP;               // bytes
   constexpr int A_STAGE = G::kTileBytes * (EXACT ? 2 : 1);
   constexpr int A_TX = G::kTileBytesRaw * (EXACT ? 2 : 1);
   constexpr int ACC_COLS = MB * ROWS_B;            // TMEM columns per accumulator stage
@@ -140,12 +148,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t a_base = smem_base;
-  const uint32_t w_base = a_base + 2 * A_STAGE;
-  uint8_t* tail = smem + 2 * A_STAGE + p.wslots * W_SLAB;
+  const int NS = p.astages;
+  const uint32_t w_base = a_base + NS * A_STAGE;
+  uint8_t* tail = smem + NS * A_STAGE + p.wslots * W_SLAB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   // barrier indices
   auto bar = [&](int i) { return smem_u32(bars + i); };
-  constexpr int B_AFULL = 0, B_AEMPTY = 2, B_TFULL = 4, B_TEMPTY = 6, B_WFULL = 8;
+  constexpr int B_AFULL = 0, B_AEMPTY = kMaxAStages, B_TFULL = 2 * kMaxAStages,
+                B_TEMPTY = B_TFULL + 2, B_WFULL = B_TFULL + 4;
   const int B_WEMPTY = B_WFULL + kMaxWSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_WFULL + 2 * kMaxWSlots);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
@@ -154,9 +164,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxAStages; ++i) {
       mbar_init(bar(B_AFULL + i), 1);
       mbar_init(bar(B_AEMPTY + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(bar(B_TFULL + i), 1);
       mbar_init(bar(B_TEMPTY + i), 128);
     }
@@ -178,6 +190,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: the prologue above (and the weight producer's first loads —
+  // weights are never written by a kernel) overlaps the previous layer's tail; activations,
+  // residuals and outputs are only touched after the previous grid has fully completed.
+  if (p.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp != 6) asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 
   const int first_tile = blockIdx.x;
   const int tile_step = gridDim.x;
@@ -193,13 +212,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int n = sn / p.n_strips;
         const int r0 = (t * MT) / kPitch - 1;
         for (int c = 0; c < p.n_chunks; ++c, ++it) {
-          const int st = it & 1;
-          mbar_wait(bar(B_AEMPTY + st), ((it >> 1) & 1) ^ 1);
+          const int st = it % NS;
+          mbar_wait(bar(B_AEMPTY + st), ((it / NS) & 1) ^ 1);
           mbar_expect_tx(bar(B_AFULL + st), A_TX);
           const uint32_t dst = a_base + st * A_STAGE;
-          tma_load_4d(dst, &tm_a_hi, bar(B_AFULL + st), p.in_choff + c * 64, s * kStrip - 1, r0, n);
+          tma_load_4d(dst, &tm_a_hi, bar(B_AFULL + st), p.in_choff + c * CH, s * kStrip - 1, r0, n);
           if (EXACT)
-            tma_load_4d(dst + G::kTileBytes, &tm_a_lo, bar(B_AFULL + st), p.in_choff + c * 64,
+            tma_load_4d(dst + G::kTileBytes, &tm_a_lo, bar(B_AFULL + st), p.in_choff + c * CH,
                         s * kStrip - 1, r0, n);
         }
       }
@@ -216,7 +235,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
           const int ws = it % p.wslots;
           mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
           mbar_expect_tx(bar(B_WFULL + ws), W_SLAB);
-          tma_load_2d(w_base + ws * W_SLAB, &tm_w, bar(B_WFULL + ws), 0, sl * (TG * ROWS_B));
+#pragma unroll
+          for (int tt = 0; tt < TG; ++tt)
+            tma_load_2d(w_base + ws * W_SLAB + tt * W_TAP, &tm_w, bar(B_WFULL + ws), 0,
+                        (sl * TG + tt) * ROWS_B);
         }
         first = false;
       }
@@ -226,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     // The whole warp walks the loop (warp-uniform control flow keeps the descriptor arithmetic
     // on the uniform datapath); one elected lane issues the tcgen05 instructions.  Descriptors
     // are advanced by adding to their low word: +2 per 16-channel k-step (32 B), +8 per flat row.
-    const uint64_t desc_hi_lo0 = make_sw128_desc(0, 0);
+    const uint64_t desc_hi_lo0 = make_kmajor_desc<RB>(0);
     const uint32_t desc_hi = static_cast<uint32_t>(desc_hi_lo0 >> 32);
     const uint32_t desc_lo0 = static_cast<uint32_t>(desc_hi_lo0);  // LBO field, start = 0
     auto mk = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
@@ -244,16 +266,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       const uint32_t acc = tmem_base + as * ACC_COLS;
       uint32_t accumulate = 0;
       for (int c = 0; c < p.n_chunks; ++c, ++a_it) {
-        const int st = a_it & 1;
+        const int st = a_it % NS;
         if (dbg) tq = clock64();
-        mbar_wait(bar(B_AFULL + st), (a_it >> 1) & 1);
+        mbar_wait(bar(B_AFULL + st), (a_it / NS) & 1);
         if (dbg) t_afull += clock64() - tq;
         tc_fence_after();
         // descriptor low word of flat row 0 (tap shift 0, m-block 0) of this stage
         const uint32_t a_lo0 =
-            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1 + p.shift0) * 8;
-        const int rem = p.cin - c * 64;
-        const int ksteps = rem >= 64 ? 4 : (rem >> 4);
+            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1 + p.shift0) * RB16;
+        const int rem = p.cin - c * CH;
+        const int ksteps = rem >= CH ? KSTEPS : (rem >> 4);
 #pragma unroll
         for (int g = 0; g < NG; ++g, ++w_it) {
           int ws;
@@ -274,21 +296,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
           if (elect_one()) {
 #pragma unroll
             for (int tt = 0; tt < TG; ++tt) {
-              constexpr int kRowBytes16 = 8;  // one 128-byte flat row in descriptor units
               const int tap = g * TG + tt;    // compile-time after unrolling
-              const uint32_t a_lo = a_lo0 + ((tap / KS) * kPitch + (tap % KS)) * kRowBytes16;
-              const uint32_t b_lo = b_lo0 + tt * (ROWS_B * 8);
+              const uint32_t a_lo = a_lo0 + ((tap / KS) * kPitch + (tap % KS)) * RB16;
+              const uint32_t b_lo = b_lo0 + tt * (W_TAP >> 4);
 #pragma unroll
               for (int mb = 0; mb < MB; ++mb) {
                 const uint32_t d_acc = acc + mb * ROWS_B;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < KSTEPS; ++k) {
                   if (k < ksteps) {
-                    const uint64_t da = mk(a_lo + mb * (128 * 8) + k * 2);
+                    const uint64_t da = mk(a_lo + mb * (128 * RB16) + k * 2);
                     const uint64_t db = mk(b_lo + k * 2);
                     umma_f16_ss(d_acc, da, db, IDESC_WIDE, (k > 0 || tt > 0) ? 1u : accumulate);
                     if (EXACT) {
-                      const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * 8) + k * 2);
+                      const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * RB16) + k * 2);
                       umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
                     }
                   }
@@ -404,40 +425,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 }
 
 // ------------------------------------------------------------------ host side
-template <int MB>
-static constexpr int a_stage_bytes(bool exact) {
-  return TileGeom<MB>::kTileBytes * (exact ? 2 : 1);
-}
-
 static long long* g_dbg_buf = nullptr;
 
-static constexpr int kTailBytes = (8 + 2 * kMaxWSlots) * 8 + 16 + 64 * 4 + 64;
+static constexpr int kTailBytes = (2 * kMaxAStages + 4 + 2 * kMaxWSlots) * 8 + 16 + 64 * 4 + 64;
 
 static int make_act_map(CUtensorMap* tm, const void* base, int nb, int h, int w, int ctot,
-                        int box_rows) {
+                        int box_rows, int ch) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return BHSR_ECUDA;
   cuuint64_t dims[4] = {(cuuint64_t)ctot, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)nb};
   cuuint64_t strides[3] = {(cuuint64_t)ctot * 2, (cuuint64_t)w * ctot * 2,
                            (cuuint64_t)h * w * ctot * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)kPitch, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[4] = {(cuuint32_t)ch, (cuuint32_t)kPitch, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(act) -> %d", (int)r);
   return 0;
 }
 
-static int make_weight_map(CUtensorMap* tm, const void* base, int total_rows, int box_rows) {
+static int make_weight_map(CUtensorMap* tm, const void* base, int total_rows, int box_rows,
+                           int ch) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return BHSR_ECUDA;
-  cuuint64_t dims[2] = {64, (cuuint64_t)total_rows};
-  cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint64_t dims[2] = {(cuuint64_t)ch, (cuuint64_t)total_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)ch, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(w) -> %d", (int)r);
   return 0;
@@ -445,16 +464,27 @@ static int make_weight_map(CUtensorMap* tm, const void* base, int total_rows, in
 
 template <int N, bool EXACT, int MB, int KS>
 static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream) {
-  using G = TileGeom<MB>;
+  constexpr int CH = EXACT ? 32 : 64;
+  using G = TileGeom<MB, CH>;
   constexpr int ROWS_B = EXACT ? 2 * N : N;
-  constexpr int TG = SlabTaps<N, EXACT, KS>::value;
-  constexpr int W_SLAB = TG * ROWS_B * 128;
+  constexpr int TG = KS;
+  constexpr int W_SLAB = TG * ROWS_B * G::kRowBytes;
   constexpr int A_STAGE = G::kTileBytes * (EXACT ? 2 : 1);
   const int slabs = p.n_chunks * (KS * KS / TG);
-  int avail = kSmemLimit - 1024 /*alignment slack*/ - 2 * A_STAGE - kTailBytes;
-  int wslots = avail / W_SLAB;
+  // shared-memory plan: as deep an activation ring as possible while the weight ring keeps
+  // >= min(slabs, 4) slots; weights stay resident when the whole layer fits
+  auto slots_for = [&](int ns) {
+    const int avail = kSmemLimit - 1024 /*alignment slack*/ - ns * A_STAGE - kTailBytes;
+    return avail < 0 ? 0 : avail / W_SLAB;
+  };
+  int astages = 2, wslots = slots_for(2);
+  bool picked = false;
+  for (int ns = kMaxAStages; ns >= 2 && !picked; --ns)   // 1st choice: whole layer resident
+    if (slots_for(ns) >= slabs) { astages = ns; wslots = slots_for(ns); picked = true; }
+  for (int ns = kMaxAStages; ns >= 2 && !picked; --ns)   // 2nd: a ring of at least 4 slabs
+    if (slots_for(ns) >= 4) { astages = ns; wslots = slots_for(ns); picked = true; }
   if (wslots > kMaxWSlots) wslots = kMaxWSlots;
-  if (wslots < 2) return set_error(BHSR_EINVAL, "conv_tc: no room for weight ring");
+  if (wslots < 2 && wslots < slabs) return set_error(BHSR_EINVAL, "conv_tc: no room for weight ring");
   p.w_resident = slabs <= wslots ? 1 : 0;
   {
     static const char* force = getenv("BHSR_DEBUG_FORCE_STREAM");  // debug knob: never resident
@@ -462,14 +492,15 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
   }
   if (p.w_resident) wslots = slabs;
   p.wslots = wslots;
-  const int smem_bytes = 1024 + 2 * A_STAGE + wslots * W_SLAB + kTailBytes;
+  p.astages = astages;
+  const int smem_bytes = 1024 + astages * A_STAGE + wslots * W_SLAB + kTailBytes;
 
   CUtensorMap tm_hi, tm_lo, tm_w;
-  int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows);
+  int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, CH);
   if (rc) return rc;
-  rc = make_act_map(&tm_lo, EXACT ? d.in_lo : d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows);
+  rc = make_act_map(&tm_lo, EXACT ? d.in_lo : d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, CH);
   if (rc) return rc;
-  rc = make_weight_map(&tm_w, d.w_packed, slabs * TG * ROWS_B, TG * ROWS_B);
+  rc = make_weight_map(&tm_w, d.w_packed, p.n_chunks * KS * KS * ROWS_B, ROWS_B, CH);
   if (rc) return rc;
 
   auto kern = conv_tc_kernel<N, EXACT, MB, KS>;
@@ -483,8 +514,19 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
   if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_w, p);
-  BHSR_CUDA_CHECK(cudaGetLastError());
+  static const char* no_pdl = getenv("BHSR_NO_PDL");
+  p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  BHSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));
   return 0;
 }
 
@@ -501,9 +543,11 @@ extern "C" int bhsr_debug_timing(long long* host_out, int32_t n_ctas) {
 
 extern "C" size_t bhsr_packed_conv_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps,
                                                 int32_t numerics) {
-  const int chunks = (cin + 63) / 64;
-  const int rows = numerics == BHSR_NUMERICS_EXACT_F16X3 ? 2 * cout : cout;
-  return static_cast<size_t>(chunks) * ntaps * rows * 64 * sizeof(__half);
+  const bool exact = numerics == BHSR_NUMERICS_EXACT_F16X3;
+  const int ch = exact ? 32 : 64;  // channels per chunk (conv_tc.cu: CH)
+  const int chunks = (cin + ch - 1) / ch;
+  const int rows = exact ? 2 * cout : cout;
+  return static_cast<size_t>(chunks) * ntaps * rows * ch * sizeof(__half);
 }
 
 extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
@@ -513,10 +557,12 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   BHSR_REQUIRE(d.cout == 32 || d.cout == 64, "conv_tc: cout must be 32 or 64 (got %d)", d.cout);
   BHSR_REQUIRE(d.w > 0 && d.h > 0 && d.nb > 0, "conv_tc: empty input");
   BHSR_REQUIRE(d.cin > 0 && d.cin % 16 == 0, "conv_tc: cin must be a multiple of 16 (got %d)", d.cin);
-  BHSR_REQUIRE(d.in_ctot % 64 == 0 && d.in_choff % 64 == 0 &&
-                   d.in_choff + (d.cin + 63) / 64 * 64 <= d.in_ctot,
-               "conv_tc: input channel window [%d,+%d) must sit on 64-channel chunks of %d",
-               d.in_choff, d.cin, d.in_ctot);
+  const bool exact_ = d.numerics == BHSR_NUMERICS_EXACT_F16X3;
+  const int ch_ = exact_ ? 32 : 64;
+  BHSR_REQUIRE(d.in_ctot % ch_ == 0 && d.in_choff % ch_ == 0 &&
+                   d.in_choff + (d.cin + ch_ - 1) / ch_ * ch_ <= d.in_ctot,
+               "conv_tc: input channel window [%d,+%d) must sit on %d-channel chunks of %d",
+               d.in_choff, d.cin, ch_, d.in_ctot);
   BHSR_REQUIRE(d.ntaps >= 1 && d.ntaps <= 9, "conv_tc: ntaps out of range");
   BHSR_REQUIRE(d.out_scale == 1 || d.out_scale == 2, "conv_tc: out_scale must be 1 or 2");
   BHSR_REQUIRE(d.oh >= d.h * d.out_scale && d.ow >= d.w * d.out_scale, "conv_tc: output too small");
@@ -538,8 +584,8 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
                  "conv_tc: tap offsets must be in [-1,1]");
 
   int mb = d.mblocks;
-  if (mb == 0) mb = exact ? 1 : 2;
-  BHSR_REQUIRE(mb == 1 || (mb == 2 && !exact), "conv_tc: mblocks must be 1, or 2 in fast mode");
+  if (mb == 0) mb = 2;
+  BHSR_REQUIRE(mb == 1 || mb == 2, "conv_tc: mblocks must be 1 or 2");
 
   ConvTcKernelParams p{};
   p.nb = d.nb; p.h = d.h; p.w = d.w;
@@ -547,7 +593,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   const int mt = 128 * mb;
   p.tiles_per_strip = (d.h * kPitch + mt - 1) / mt;
   p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;
-  p.in_choff = d.in_choff; p.cin = d.cin; p.n_chunks = (d.cin + 63) / 64;
+  p.in_choff = d.in_choff; p.cin = d.cin; p.n_chunks = (d.cin + ch_ - 1) / ch_;
   // taps must form a dense KS x KS window in row-major order (3x3, or the 2x2 sub-pixel phases)
   const int ks = d.ntaps == 9 ? 3 : (d.ntaps == 4 ? 2 : 0);
   BHSR_REQUIRE(ks != 0, "conv_tc: ntaps must be 9 (3x3) or 4 (2x2 phase), got %d", d.ntaps);
@@ -581,11 +627,11 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
 #define BHSR_DISPATCH(NN, EX, MBV)                                          \
   return ks == 3 ? launch<NN, EX, MBV, 3>(d, p, stream) : launch<NN, EX, MBV, 2>(d, p, stream)
   if (d.cout == 32) {
-    if (exact) { BHSR_DISPATCH(32, true, 1); }
+    if (exact) { if (mb == 2) { BHSR_DISPATCH(32, true, 2); } BHSR_DISPATCH(32, true, 1); }
     if (mb == 2) { BHSR_DISPATCH(32, false, 2); }
     BHSR_DISPATCH(32, false, 1);
   } else {
-    if (exact) { BHSR_DISPATCH(64, true, 1); }
+    if (exact) { if (mb == 2) { BHSR_DISPATCH(64, true, 2); } BHSR_DISPATCH(64, true, 1); }
     if (mb == 2) { BHSR_DISPATCH(64, false, 2); }
     BHSR_DISPATCH(64, false, 1);
   }

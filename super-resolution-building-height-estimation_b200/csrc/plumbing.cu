@@ -14,20 +14,22 @@ __device__ __forceinline__ void split2(float v, __half& hi, __half& lo) {
 }
 
 // ---------------------------------------------------------------- weight packing
-// packed[(chunk*ntaps + tap)*rows + row][64]; rows = cout (fast) or 2*cout (exact: hi | lo').
+// packed[(chunk*ntaps + tap)*rows + row][ch]; rows = cout (fast) or 2*cout (exact: hi | lo');
+// ch = channels per chunk = 64 (fast) or 32 (exact), matching conv_tc.cu.
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int cout, int cin,
                                          int fold_phase, int exact, __half* __restrict__ out,
                                          int ntaps, size_t total) {
   size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int rows = exact ? 2 * cout : cout;
-  const int k = idx & 63;
-  size_t r = idx >> 6;
+  const int chw = exact ? 32 : 64;
+  const int k = idx % chw;
+  size_t r = idx / chw;
   const int row = r % rows;
   r /= rows;
   const int tap = r % ntaps;
   const int chunk = r / ntaps;
-  const int ch = chunk * 64 + k;
+  const int ch = chunk * chw + k;
   const int n = row % cout;
   const int part = row / cout;
   float v = 0.f;

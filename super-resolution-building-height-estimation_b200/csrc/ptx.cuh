@@ -170,6 +170,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t start, uint32_t bas
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;
 }
+// Same for a row pitch of ROWB bytes: 128 -> SWIZZLE_128B (8-row groups 1024 B apart),
+// 64 -> SWIZZLE_64B (layout code 4, 8-row groups 512 B apart).
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t start) {
+  static_assert(ROWB == 128 || ROWB == 64, "row pitch must be 64 or 128 bytes");
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((start >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8 * ROWB) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(ROWB == 128 ? 2 : 4) << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16: fp16 A/B (K-major), fp32 D, M=128, N given.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);

@@ -6,8 +6,12 @@ timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -25 gpurun_out/pytest_gpu.log
 if [ -n "$PROBE_CASES" ]; then
-  CASES="$PROBE_CASES" MODES=0 bash tools/run_probe.sh > gpurun_out/probe_cases.log 2>&1
-  grep -E '"ms"|rc=' gpurun_out/probe_cases.log
+  OUT=gpurun_out/exp.log; : > $OUT
+  for c in $PROBE_CASES; do
+    echo "== $c" >> $OUT
+    BHSR_DEBUG_TIMING=1 timeout 180 python tools/probe_conv_tc.py $c 0 2>/dev/null | grep -E '"ms"|cycles' >> $OUT
+  done
+  cat $OUT | cut -c1-330
 fi
 if [ -n "$BENCH" ]; then
   timeout 900 python bench.py $BENCH > gpurun_out/bench.log 2>&1
