@@ -66,7 +66,7 @@ typedef struct BhsrConvTcDesc {
   const void* in_hi;
   const void* in_lo;        /* used only by BHSR_NUMERICS_EXACT_F16X3 */
   int32_t nb, h, w;         /* any size; the kernel walks 64-pixel-wide strips */
-  int32_t in_ctot, in_choff, cin; /* cin multiple of 16; in_ctot multiple of 64 */
+  int32_t in_ctot, in_choff, cin; /* cin multiple of 32; in_ctot multiple of the chunk width (64 fast, 32 exact) */
   /* packed weights from bhsr_pack_conv_weights (same numerics mode, same tap table) */
   const void* w_packed;
   int32_t cout;             /* 32 or 64 */
@@ -119,12 +119,14 @@ int bhsr_planes_to_nchw_f32(const void* in_hi, const void* in_lo, int32_t nb, in
 
 /* Direct fp32 3x3 convolution on CUDA cores for the thin ends of the net (K=27 or N=3):
  * conv_first (SR/rrdbnet_arch.py:232) reads fp32 NCHW with an arbitrary batch/channel stride
- * (so x[:, :3] views need no copy) and writes planes; conv_last (:222) reads planes and
+ * (so x[:, :3] views need no copy) and writes planes to one or two destinations (out2_* may be
+ * NULL; cout must be 64); conv_last (:222) reads planes and
  * writes fp32 NCHW.  lrelu_in applies LeakyReLU(0.2) to the input (forward(): :221). */
 int bhsr_conv3x3_first(const float* x, int64_t x_stride_n, int64_t x_stride_c, int64_t x_stride_h,
                        int64_t x_stride_w, int32_t nb, int32_t cin, int32_t h, int32_t w,
                        const float* weight, const float* bias, int32_t cout, void* out_hi,
-                       void* out_lo, int32_t out_ctot, int32_t out_choff, void* stream);
+                       void* out_lo, int32_t out_ctot, int32_t out_choff, void* out2_hi,
+                       void* out2_lo, int32_t out2_ctot, int32_t out2_choff, void* stream);
 int bhsr_conv3x3_last(const void* in_hi, const void* in_lo, int32_t in_ctot, int32_t in_choff,
                       int32_t nb, int32_t cin, int32_t h, int32_t w, int32_t lrelu_in,
                       const float* weight, const float* bias, int32_t cout, float* y, void* stream);

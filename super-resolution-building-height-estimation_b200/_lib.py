@@ -106,7 +106,7 @@ _SIGNATURES = {
                                 [C.c_void_p, C.c_void_p]),
     "bhsr_conv3x3_first": (C.c_int, [C.c_void_p] + [C.c_int64] * 4 + [C.c_int32] * 4 +
                            [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
-                            C.c_int32, C.c_void_p]),
+                            C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "bhsr_conv3x3_last": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 +
                           [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "bhsr_rrdbnet_packed_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),

@@ -32,6 +32,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -159,6 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   const int B_WEMPTY = B_WFULL + kMaxWSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_WFULL + 2 * kMaxWSlots);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + 64);  // 4 epilogue warps x 32 rows x 80 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -276,35 +279,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1 + p.shift0) * RB16;
         const int rem = p.cin - c * CH;
         const int ksteps = rem >= CH ? KSTEPS : (rem >> 4);
+        // The slab loop is instantiated twice (full chunk / half chunk of channels) so the
+        // unrolled MMA stream has no per-instruction predicates or branches.
+        auto issue_chunk = [&](auto ksteps_tag) {
+          constexpr int KST = decltype(ksteps_tag)::value;
 #pragma unroll
-        for (int g = 0; g < NG; ++g, ++w_it) {
-          int ws;
-          if (p.w_resident) {
-            ws = c * NG + g;
-            if (tile_it == 0) {
-              mbar_wait(bar(B_WFULL + ws), 0);
+          for (int g = 0; g < NG; ++g, ++w_it) {
+            int ws;
+            if (p.w_resident) {
+              ws = c * NG + g;
+              if (tile_it == 0) {
+                mbar_wait(bar(B_WFULL + ws), 0);
+                tc_fence_after();
+              }
+            } else {
+              ws = w_it % p.wslots;
+              if (dbg) tq = clock64();
+              mbar_wait(bar(B_WFULL + ws), (w_it / p.wslots) & 1);
+              if (dbg) t_wfull += clock64() - tq;
               tc_fence_after();
             }
-          } else {
-            ws = w_it % p.wslots;
-            if (dbg) tq = clock64();
-            mbar_wait(bar(B_WFULL + ws), (w_it / p.wslots) & 1);
-            if (dbg) t_wfull += clock64() - tq;
-            tc_fence_after();
-          }
-          const uint32_t b_lo0 = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
-          if (elect_one()) {
+            const uint32_t b_lo0 = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
+            if (elect_one()) {
 #pragma unroll
-            for (int tt = 0; tt < TG; ++tt) {
-              const int tap = g * TG + tt;    // compile-time after unrolling
-              const uint32_t a_lo = a_lo0 + ((tap / KS) * kPitch + (tap % KS)) * RB16;
-              const uint32_t b_lo = b_lo0 + tt * (W_TAP >> 4);
+              for (int tt = 0; tt < TG; ++tt) {
+                const int tap = g * TG + tt;    // compile-time after unrolling
+                const uint32_t a_lo = a_lo0 + ((tap / KS) * kPitch + (tap % KS)) * RB16;
+                const uint32_t b_lo = b_lo0 + tt * (W_TAP >> 4);
 #pragma unroll
-              for (int mb = 0; mb < MB; ++mb) {
-                const uint32_t d_acc = acc + mb * ROWS_B;
+                for (int mb = 0; mb < MB; ++mb) {
+                  const uint32_t d_acc = acc + mb * ROWS_B;
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
-                  if (k < ksteps) {
+                  for (int k = 0; k < KST; ++k) {
                     const uint64_t da = mk(a_lo + mb * (128 * RB16) + k * 2);
                     const uint64_t db = mk(b_lo + k * 2);
                     umma_f16_ss(d_acc, da, db, IDESC_WIDE, (k > 0 || tt > 0) ? 1u : accumulate);
@@ -315,12 +321,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                   }
                 }
               }
+              if (!p.w_resident) umma_commit(bar(B_WEMPTY + ws));
             }
-            if (!p.w_resident) umma_commit(bar(B_WEMPTY + ws));
+            __syncwarp();
+            accumulate = 1;
           }
-          __syncwarp();
-          accumulate = 1;
-        }
+        };
+        if (ksteps == KSTEPS) issue_chunk(std::integral_constant<int, KSTEPS>{});
+        else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
         if (elect_one()) umma_commit(bar(B_AEMPTY + st));
         __syncwarp();
       }
@@ -375,38 +383,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += s_bias[cc * 32 + j];
+          if (p.epilogue & BHSR_EPI_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
+          }
           if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += s_bias[cc * 32 + j];
-            if (p.epilogue & BHSR_EPI_LRELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
-            }
             if (p.epilogue & BHSR_EPI_RES1)
               add_residual32(v, p.alpha1, p.res1_hi, p.res1_lo,
                              in_pix * p.res1_ctot + p.res1_choff + cc * 32);
             if (p.epilogue & BHSR_EPI_RES2)
               add_residual32(v, p.alpha2, p.res2_hi, p.res2_lo,
                              in_pix * p.res2_ctot + p.res2_choff + cc * 32);
-            if (nchw) {
+          }
+          if (nchw) {
+            if (valid) {
               const size_t plane = static_cast<size_t>(p.oh) * p.ow;
               float* o = p.out_f32 + (static_cast<size_t>(n) * p.out_ctot + p.out_choff + cc * 32) *
                                          plane + static_cast<size_t>(oy) * p.ow + ox;
 #pragma unroll
               for (int j = 0; j < 32; ++j) o[j * plane] = v[j];
-            } else {
-              const size_t off = out_pix * p.out_ctot + p.out_choff + cc * 32;
-              uint4* oh4 = reinterpret_cast<uint4*>(p.out_hi + off);
-              uint4* ol4 = p.out_lo ? reinterpret_cast<uint4*>(p.out_lo + off) : nullptr;
+            }
+          } else {
+            // Store transpose: a lane owns one pixel (64 B of this 32-channel slice).  Written
+            // directly, every 16-byte store instruction would touch 32 different lines; staged
+            // through shared memory, a store instruction covers 8 pixels x 64 B (8 lines).
+            uint8_t* stg = s_stage + (warp - 2) * (32 * 80);
+            const uint32_t pix32 = valid ? static_cast<uint32_t>(out_pix) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+              __half* dst_plane = part == 0 ? p.out_hi : p.out_lo;
+              if (dst_plane == nullptr) break;  // warp-uniform
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 __align__(16) __half hh[8];
-                __align__(16) __half ll[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) split_hi_lo(v[g * 8 + j], hh[j], ll[j]);
-                oh4[g] = *reinterpret_cast<const uint4*>(hh);
-                if (ol4) ol4[g] = *reinterpret_cast<const uint4*>(ll);
+                for (int j = 0; j < 8; ++j) {
+                  const float x = v[g * 8 + j];
+                  const __half hi = __float2half_rn(x);
+                  hh[j] = part == 0 ? hi : __float2half_rn((x - __half2float(hi)) * 2048.f);
+                }
+                *reinterpret_cast<uint4*>(stg + lane * 80 + g * 16) = *reinterpret_cast<const uint4*>(hh);
               }
+              __syncwarp();
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const int src = 8 * j4 + (lane >> 2);
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + src * 80 + (lane & 3) * 16);
+                const uint32_t pp = __shfl_sync(0xffffffffu, pix32, src);
+                if (pp != 0xFFFFFFFFu) {
+                  __half* o = dst_plane + static_cast<size_t>(pp) * p.out_ctot + p.out_choff + cc * 32 +
+                              (lane & 3) * 8;
+                  *reinterpret_cast<uint4*>(o) = val;
+                }
+              }
+              __syncwarp();
             }
           }
         }
@@ -427,7 +459,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 // ------------------------------------------------------------------ host side
 static long long* g_dbg_buf = nullptr;
 
-static constexpr int kTailBytes = (2 * kMaxAStages + 4 + 2 * kMaxWSlots) * 8 + 16 + 64 * 4 + 64;
+static constexpr int kStageBytes = 4 * 32 * 80;  // epilogue store-transpose staging
+static constexpr int kTailBytes = (2 * kMaxAStages + 4 + 2 * kMaxWSlots) * 8 + 16 + 64 * 4 + 64 + kStageBytes;
 
 static int make_act_map(CUtensorMap* tm, const void* base, int nb, int h, int w, int ctot,
                         int box_rows, int ch) {
@@ -556,7 +589,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BHSR_REQUIRE(d.cout == 32 || d.cout == 64, "conv_tc: cout must be 32 or 64 (got %d)", d.cout);
   BHSR_REQUIRE(d.w > 0 && d.h > 0 && d.nb > 0, "conv_tc: empty input");
-  BHSR_REQUIRE(d.cin > 0 && d.cin % 16 == 0, "conv_tc: cin must be a multiple of 16 (got %d)", d.cin);
+  BHSR_REQUIRE(d.cin > 0 && d.cin % 32 == 0, "conv_tc: cin must be a multiple of 32 (got %d)", d.cin);
   const bool exact_ = d.numerics == BHSR_NUMERICS_EXACT_F16X3;
   const int ch_ = exact_ ? 32 : 64;
   BHSR_REQUIRE(d.in_ctot % ch_ == 0 && d.in_choff % ch_ == 0 &&

@@ -113,56 +113,66 @@ __global__ void planes_to_nchw_kernel(const __half* __restrict__ in_hi,
 }
 
 // ---------------------------------------------------------------- conv_first (K = cin*9)
-// thread = (pixel, group of 8 output channels); weights and bias staged in shared memory.
-__global__ void conv3x3_first_kernel(const float* __restrict__ x, long long sn, long long sc,
-                                     long long sh, long long sw, int nb, int cin, int h, int w,
-                                     const float* __restrict__ weight, const float* __restrict__ bias,
-                                     int cout, __half* __restrict__ out_hi,
-                                     __half* __restrict__ out_lo, int ctot, int choff) {
-  extern __shared__ float sw_[];  // [cin*9][cout] then bias[cout]
+// thread = pixel: the cin*9 inputs are read once (coalesced along x across the warp), every
+// weight is a shared-memory broadcast, and the 64-channel NHWC pixel is written to up to two
+// destinations (the long-skip copy and the first RDB's concat buffer) from the same registers.
+template <int COUT>
+__global__ void __launch_bounds__(128)
+conv3x3_first_kernel(const float* __restrict__ x, long long sn, long long sc, long long sh,
+                     long long sw, int nb, int cin, int h, int w, const float* __restrict__ weight,
+                     const float* __restrict__ bias, __half* __restrict__ out_hi,
+                     __half* __restrict__ out_lo, int ctot, int choff, __half* __restrict__ out2_hi,
+                     __half* __restrict__ out2_lo, int ctot2, int choff2) {
+  extern __shared__ float sw_[];  // [cin*9][COUT] then bias[COUT]
   const int kk = cin * 9;
-  for (int i = threadIdx.x; i < kk * cout; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kk * COUT; i += blockDim.x) {
     const int o = i / kk, k = i % kk;  // weight is [cout][cin][3][3] = [cout][kk]
-    sw_[k * cout + o] = weight[i];
+    sw_[k * COUT + o] = weight[i];
   }
-  float* sb = sw_ + kk * cout;
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  float* sb = sw_ + kk * COUT;
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int groups = cout / 8;
-  const size_t total = static_cast<size_t>(nb) * h * w * groups;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int g = idx % groups;
-    size_t pix = idx / groups;
+  const size_t total = static_cast<size_t>(nb) * h * w;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int px = pix % w;
     const int py = (pix / w) % h;
     const int n = pix / (static_cast<size_t>(w) * h);
-    float acc[8];
+    float acc[COUT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[g * 8 + j];
+    for (int j = 0; j < COUT; ++j) acc[j] = sb[j];
     for (int ci = 0; ci < cin; ++ci) {
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = py + ky - 1;
-        if (yy < 0 || yy >= h) continue;
+      for (int t = 0; t < 9; ++t) {
+        const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = x[n * sn + ci * sc + yy * sh + xx * sw];
+        const float4* wr = reinterpret_cast<const float4*>(sw_ + (ci * 9 + t) * COUT);
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xx = px + kx - 1;
-          if (xx < 0 || xx >= w) continue;
-          const float v = x[n * sn + ci * sc + yy * sh + xx * sw];
-          const float* wr = sw_ + ((ci * 3 + ky) * 3 + kx) * cout + g * 8;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+        for (int j = 0; j < COUT / 4; ++j) {
+          const float4 wv = wr[j];
+          acc[4 * j + 0] = fmaf(v, wv.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(v, wv.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, wv.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(v, wv.w, acc[4 * j + 3]);
         }
       }
     }
-    __align__(16) __half hh[8];
-    __align__(16) __half ll[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split2(acc[j], hh[j], ll[j]);
-    const size_t o = pix * ctot + choff + g * 8;
-    *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hh);
-    if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(ll);
+    for (int g = 0; g < COUT / 8; ++g) {
+      __align__(16) __half hh[8];
+      __align__(16) __half ll[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split2(acc[g * 8 + j], hh[j], ll[j]);
+      const size_t o = pix * ctot + choff + g * 8;
+      *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hh);
+      if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(ll);
+      if (out2_hi) {
+        const size_t o2 = pix * ctot2 + choff2 + g * 8;
+        *reinterpret_cast<uint4*>(out2_hi + o2) = *reinterpret_cast<const uint4*>(hh);
+        if (out2_lo) *reinterpret_cast<uint4*>(out2_lo + o2) = *reinterpret_cast<const uint4*>(ll);
+      }
+    }
   }
 }
 
@@ -279,23 +289,25 @@ extern "C" int bhsr_conv3x3_first(const float* x, int64_t sn, int64_t sc, int64_
                                   int32_t nb, int32_t cin, int32_t h, int32_t w,
                                   const float* weight, const float* bias, int32_t cout,
                                   void* out_hi, void* out_lo, int32_t out_ctot, int32_t out_choff,
-                                  void* stream) {
+                                  void* out2_hi, void* out2_lo, int32_t out2_ctot,
+                                  int32_t out2_choff, void* stream) {
   BHSR_REQUIRE(x && weight && out_hi, "conv3x3_first: null pointer");
-  BHSR_REQUIRE(cout % 8 == 0 && out_ctot % 8 == 0 && out_choff % 8 == 0,
-               "conv3x3_first: cout/out_ctot/out_choff must be multiples of 8");
+  BHSR_REQUIRE(cout == 64, "conv3x3_first: cout must be 64 (num_feat), got %d", cout);
+  BHSR_REQUIRE(out_ctot % 8 == 0 && out_choff % 8 == 0 && (!out2_hi || (out2_ctot % 8 == 0 && out2_choff % 8 == 0)),
+               "conv3x3_first: output channel offset/stride must be multiples of 8");
   const size_t smem = (static_cast<size_t>(cin) * 9 * cout + cout) * sizeof(float);
-  BHSR_REQUIRE(smem <= 160 * 1024, "conv3x3_first: cin*cout too large (%d x %d)", cin, cout);
+  BHSR_REQUIRE(smem <= 160 * 1024, "conv3x3_first: cin too large (%d)", cin);
   if (smem > 48 * 1024)
-    BHSR_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_first_kernel,
+    BHSR_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_first_kernel<64>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  const size_t total = static_cast<size_t>(nb) * h * w * (cout / 8);
+  const size_t total = static_cast<size_t>(nb) * h * w;
   int sms = device_sm_count();
-  size_t blocks = (total + 255) / 256;
+  size_t blocks = (total + 127) / 128;
   if (blocks > static_cast<size_t>(sms) * 8) blocks = static_cast<size_t>(sms) * 8;
-  conv3x3_first_kernel<<<static_cast<unsigned>(blocks), 256, smem,
-                         static_cast<cudaStream_t>(stream)>>>(
-      x, sn, sc, sh, sw, nb, cin, h, w, weight, bias, cout, static_cast<__half*>(out_hi),
-      static_cast<__half*>(out_lo), out_ctot, out_choff);
+  conv3x3_first_kernel<64><<<static_cast<unsigned>(blocks), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, sn, sc, sh, sw, nb, cin, h, w, weight, bias, static_cast<__half*>(out_hi),
+      static_cast<__half*>(out_lo), out_ctot, out_choff, static_cast<__half*>(out2_hi),
+      static_cast<__half*>(out2_lo), out2_ctot, out2_choff);
   BHSR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

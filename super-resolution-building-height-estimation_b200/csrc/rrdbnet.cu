@@ -178,13 +178,10 @@ extern "C" int bhsr_rrdbnet_forward(const BhsrRrdbNetDesc* dp, const float* x, i
   size_t poff = 0, boff = 0;
   int rc;
 
-  // conv_first -> long-skip copy and the first RDB's x0 (K = 27: CUDA cores, done twice rather
-  // than adding a copy kernel; 0.15% of the FLOPs)
+  // conv_first -> the long-skip copy and the first RDB's x0, one launch (K = 27: CUDA cores)
   rc = bhsr_conv3x3_first(x, sn, sc, sh, sw, d.nb, d.num_in_ch, d.h, d.w, d.conv_first_w,
-                          d.conv_first_b, 64, ws.feat.hi, ws.feat.lo, 64, 0, stream);
-  if (rc) return rc;
-  rc = bhsr_conv3x3_first(x, sn, sc, sh, sw, d.nb, d.num_in_ch, d.h, d.w, d.conv_first_w,
-                          d.conv_first_b, 64, ws.buf[0].hi, ws.buf[0].lo, 192, 0, stream);
+                          d.conv_first_b, 64, ws.feat.hi, ws.feat.lo, 64, 0, ws.buf[0].hi,
+                          ws.buf[0].lo, 192, 0, stream);
   if (rc) return rc;
 
   auto base_desc = [&](const Planes& in, int in_ctot, int cin, int cout, int h, int w) {

@@ -145,7 +145,7 @@ def conv3x3_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Te
     _lib.check(_lib.load().bhsr_conv3x3_first(x.data_ptr(), sn, sc, sh, sw, nb, cin, h, w,
                                               weight.data_ptr(), _lib.ptr(bias), cout,
                                               out_hi.data_ptr(), _lib.ptr(out_lo), out_hi.shape[3],
-                                              out_choff, _lib.stream_ptr(x.device)),
+                                              out_choff, None, None, 0, 0, _lib.stream_ptr(x.device)),
                "bhsr_conv3x3_first")
 
 

@@ -28,7 +28,9 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.bhsr_version() == 100
     # size queries are host-only and must work without a GPU
-    assert lib.bhsr_packed_conv_weight_bytes(32, 96, 9, 0) == 2 * 9 * 64 * 64 * 2
+    # exact: 3 chunks of 32 channels x 9 taps x (hi+lo) 64 rows x 32 ch; fast: 2 chunks of 64 x 9 x 32 rows x 64
+    assert lib.bhsr_packed_conv_weight_bytes(32, 96, 9, 0) == 3 * 9 * 64 * 32 * 2
+    assert lib.bhsr_packed_conv_weight_bytes(32, 96, 9, 1) == 2 * 9 * 32 * 64 * 2
     assert lib.bhsr_rrdbnet_bias_floats(23) == 23 * 3 * (4 * 32 + 64) + 4 * 64
     assert lib.bhsr_rrdbnet_workspace_bytes(1, 64, 64, 1) > 0
 
