@@ -208,15 +208,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     // ------------------------------------------------ activation producer
     if (lane == 0) {
       uint32_t it = 0;
+      int st = 0, ph = 1;  // empty barriers start "free": wait on the opposite parity
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const int t = tile % p.tiles_per_strip;
         const int sn = tile / p.tiles_per_strip;
         const int s = sn % p.n_strips;
         const int n = sn / p.n_strips;
         const int r0 = (t * MT) / kPitch - 1;
-        for (int c = 0; c < p.n_chunks; ++c, ++it) {
-          const int st = it % NS;
-          mbar_wait(bar(B_AEMPTY + st), ((it / NS) & 1) ^ 1);
+        for (int c = 0; c < p.n_chunks; ++c, ++it, st = (st + 1 == NS ? 0 : st + 1), ph ^= (st == 0)) {
+          mbar_wait(bar(B_AEMPTY + st), ph);
+          if ((p.desc_mode & 2) && it >= static_cast<uint32_t>(NS)) {  // timing experiment only
+            mbar_arrive(bar(B_AFULL + st));
+            continue;
+          }
           mbar_expect_tx(bar(B_AFULL + st), A_TX);
           const uint32_t dst = a_base + st * A_STAGE;
           tma_load_4d(dst, &tm_a_hi, bar(B_AFULL + st), p.in_choff + c * CH, s * kStrip - 1, r0, n);
@@ -258,27 +262,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     uint32_t a_it = 0, w_it = 0, tile_it = 0;
     long long t_tempty = 0, t_afull = 0, t_wfull = 0, t_total = clock64(), tq;
     const bool dbg = p.dbg != nullptr;
+    // Early probes.  A barrier test costs ~100 cycles even when the phase is long complete, and
+    // the tensor queue is shallow: waiting right before the MMAs that need the data drains it.
+    // So every barrier the NEXT step needs is probed (non-blocking try_wait) before the current
+    // step's MMAs are issued — the probe's latency hides behind their issue — and only a probe
+    // that came back "not yet" falls through to the blocking wait.
+    uint32_t ok_t = 0, ok_a = 0, ok_w = 0;
+    const int my_tiles = (p.total_tiles - first_tile + tile_step - 1) / tile_step;
+    // ring positions are advanced incrementally (no integer division on the issue path)
+    int st = 0, a_ph = 0;   // activation stage / phase parity
+    int ws_r = 0, w_ph = 0; // weight slot / phase parity (streaming mode)
+    const int wslots = p.wslots;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int flat_mod = (t * MT) % kPitch;
       const int as = tile_it & 1;
-      if (dbg) tq = clock64();
-      mbar_wait(bar(B_TEMPTY + as), ((tile_it >> 1) & 1) ^ 1);
-      if (dbg) t_tempty += clock64() - tq;
+      if (!ok_t) {
+        if (dbg) tq = clock64();
+        mbar_wait(bar(B_TEMPTY + as), ((tile_it >> 1) & 1) ^ 1);
+        if (dbg) t_tempty += clock64() - tq;
+      }
+      ok_t = 0;
       tc_fence_after();
       const uint32_t acc = tmem_base + as * ACC_COLS;
       uint32_t accumulate = 0;
       for (int c = 0; c < p.n_chunks; ++c, ++a_it) {
-        const int st = a_it % NS;
-        if (dbg) tq = clock64();
-        mbar_wait(bar(B_AFULL + st), (a_it / NS) & 1);
-        if (dbg) t_afull += clock64() - tq;
+        if (!ok_a) {
+          if (dbg) tq = clock64();
+          mbar_wait(bar(B_AFULL + st), a_ph);
+          if (dbg) t_afull += clock64() - tq;
+        }
+        ok_a = 0;
+        int st_next = st + 1, a_ph_next = a_ph;
+        if (st_next == NS) { st_next = 0; a_ph_next ^= 1; }
         tc_fence_after();
         // descriptor low word of flat row 0 (tap shift 0, m-block 0) of this stage
         const uint32_t a_lo0 =
             desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1 + p.shift0) * RB16;
         const int rem = p.cin - c * CH;
         const int ksteps = rem >= CH ? KSTEPS : (rem >> 4);
+        const bool last_chunk = (c + 1 == p.n_chunks);
         // The slab loop is instantiated twice (full chunk / half chunk of channels) so the
         // unrolled MMA stream has no per-instruction predicates or branches.
         auto issue_chunk = [&](auto ksteps_tag) {
@@ -293,12 +316,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 tc_fence_after();
               }
             } else {
-              ws = w_it % p.wslots;
-              if (dbg) tq = clock64();
-              mbar_wait(bar(B_WFULL + ws), (w_it / p.wslots) & 1);
-              if (dbg) t_wfull += clock64() - tq;
+              ws = ws_r;
+              if (!ok_w) {
+                if (dbg) tq = clock64();
+                mbar_wait(bar(B_WFULL + ws), w_ph);
+                if (dbg) t_wfull += clock64() - tq;
+              }
+              ok_w = 0;
               tc_fence_after();
+              if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }   // next slab (may belong to the next tile)
             }
+            // barriers probed from inside the tap blocks: tap 0 -> next weight slab, tap 1 -> next
+            // activation stage, tap 2 -> the next tile's accumulator (only consumed where relevant)
+            const bool more_tiles = tile_it + 1 < static_cast<uint32_t>(my_tiles);
+            const uint32_t nt = tile_it + 1;
+            const uint32_t pb[3] = {bar(B_WFULL + (p.w_resident ? ws : ws_r)), bar(B_AFULL + st_next),
+                                    bar(B_TEMPTY + (nt & 1))};
+            const uint32_t pp[3] = {static_cast<uint32_t>(p.w_resident ? 0 : w_ph),
+                                    static_cast<uint32_t>(a_ph_next), ((nt >> 1) & 1) ^ 1};
+            uint32_t okv[3] = {0, 0, 0};
             const uint32_t b_lo0 = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
             if (elect_one()) {
 #pragma unroll
@@ -306,24 +342,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 const int tap = g * TG + tt;    // compile-time after unrolling
                 const uint32_t a_lo = a_lo0 + ((tap / KS) * kPitch + (tap % KS)) * RB16;
                 const uint32_t b_lo = b_lo0 + tt * (W_TAP >> 4);
-#pragma unroll
-                for (int mb = 0; mb < MB; ++mb) {
-                  const uint32_t d_acc = acc + mb * ROWS_B;
-#pragma unroll
-                  for (int k = 0; k < KST; ++k) {
-                    const uint64_t da = mk(a_lo + mb * (128 * RB16) + k * 2);
-                    const uint64_t db = mk(b_lo + k * 2);
-                    umma_f16_ss(d_acc, da, db, IDESC_WIDE, (k > 0 || tt > 0) ? 1u : accumulate);
-                    if (EXACT) {
-                      const uint64_t dl = mk(a_lo + (G::kTileBytes >> 4) + mb * (128 * RB16) + k * 2);
-                      umma_f16_ss(d_acc + N, dl, db, IDESC_N, 1u);
-                    }
-                  }
-                }
+                okv[tt] = issue_tap<EXACT, MB, KST, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N>(
+                    a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, tt > 0 ? 1u : accumulate, pb[tt],
+                    pp[tt]);
               }
               if (!p.w_resident) umma_commit(bar(B_WEMPTY + ws));
             }
             __syncwarp();
+            if (!p.w_resident) ok_w = __any_sync(0xffffffffu, okv[0]);
+            if (g == NG - 1) {
+              if (!last_chunk || more_tiles) ok_a = __any_sync(0xffffffffu, okv[1]);
+              if (TG >= 3 && last_chunk && more_tiles) ok_t = __any_sync(0xffffffffu, okv[2]);
+            }
             accumulate = 1;
           }
         };
@@ -331,6 +361,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
         if (elect_one()) umma_commit(bar(B_AEMPTY + st));
         __syncwarp();
+        st = st_next;
+        a_ph = a_ph_next;
       }
       if (elect_one()) umma_commit(bar(B_TFULL + as));
       __syncwarp();
@@ -353,6 +385,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       const int as = tile_it & 1;
       mbar_wait(bar(B_TFULL + as), (tile_it >> 1) & 1);
       tc_fence_after();
+      if (p.desc_mode & 1) {  // timing experiment only: skip the epilogue work
+        tc_fence_before();
+        mbar_arrive(bar(B_TEMPTY + as));
+        continue;
+      }
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
         const int f = t * MT + mb * 128 + row;

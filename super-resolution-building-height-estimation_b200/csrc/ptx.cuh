@@ -56,8 +56,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must trap (launch error surfaced to the host) instead of
 // hanging the device. ~4e9 cycles is seconds; a healthy wait is microseconds.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -66,6 +65,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------- TMA
@@ -186,6 +189,64 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t start) {
 // Instruction descriptor, kind::f16: fp16 A/B (K-major), fp32 D, M=128, N given.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+
+// ---------------------------------------------------------------- fused issue block
+// All MMAs of ONE filter tap (MB m-blocks x KST k-steps, x2 in exact numerics) as a single asm
+// block that ALSO starts a non-blocking mbarrier test at its top and materialises the test's
+// result at its bottom.  A barrier test has ~100 cycles of latency even when the phase is long
+// complete; written this way the latency overlaps the MMA issue instead of draining the
+// (shallow) tensor-core queue in front of the next step.
+//   a_lo / b_lo : low words of the A / B shared-memory descriptors of (m-block 0, k-step 0)
+//   desc_hi     : common high word;  d_acc: TMEM address of m-block 0's accumulator
+//   acc_first   : 0 -> the k-step-0 MMAs overwrite the accumulator, else accumulate
+//   MBS16 = descriptor units between m-blocks (128 rows), LO16 = hi -> lo tile distance,
+//   ROWS = TMEM columns per m-block, NN = column offset of the lo accumulator
+#define BHSR_TAP_PRE                                                                   \
+  "{\n.reg .pred pacc, ptrue, pw;\n.reg .b32 alo, blo, d, dn, al2;\n.reg .b64 da, db, dl;\n" \
+  "setp.ne.b32 pacc, %7, 0;\nsetp.eq.b32 ptrue, 0, 0;\n"                               \
+  "mbarrier.try_wait.parity.shared::cta.b64 pw, [%8], %9;\n"                          \
+  "mov.b32 alo, %1;\nmov.b32 blo, %2;\nmov.b32 d, %4;\n"
+#define BHSR_TAP_POST "selp.u32 %0, 1, 0, pw;\n}\n"
+#define BHSR_STEP_F(ACC)                                                               \
+  "mov.b64 da, {alo, %3};\nmov.b64 db, {blo, %3};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [d], da, db, %5, " ACC ";\n"                     \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_STEP_E(ACC)                                                               \
+  "mov.b64 da, {alo, %3};\nmov.b64 db, {blo, %3};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [d], da, db, %5, " ACC ";\n"                     \
+  "add.u32 al2, alo, %11;\nmov.b64 dl, {al2, %3};\nadd.u32 dn, d, %13;\n"              \
+  "tcgen05.mma.cta_group::1.kind::f16 [dn], dl, db, %6, ptrue;\n"                      \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_NEXT_MB "add.u32 alo, alo, %10;\nsub.u32 blo, blo, %14;\nadd.u32 d, d, %12;\n"
+#define BHSR_K1(S) S("pacc")
+#define BHSR_K2(S) S("pacc") S("ptrue")
+#define BHSR_K4(S) S("pacc") S("ptrue") S("ptrue") S("ptrue")
+#define BHSR_TAP_ASM(BODY)                                                             \
+  asm volatile(BHSR_TAP_PRE BODY BHSR_TAP_POST                                         \
+               : "=r"(ok)                                                              \
+               : "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(d_acc), "r"(idesc_wide), "r"(idesc_n), \
+                 "r"(acc_first), "r"(probe_bar), "r"(probe_parity), "n"(MBS16 - 2 * KST),       \
+                 "n"(LO16), "n"(ROWS), "n"(NN), "n"(2 * KST)                             \
+               : "memory")
+
+template <bool EXACT, int MB, int KST, int MBS16, int LO16, int ROWS, int NN>
+__device__ __forceinline__ uint32_t issue_tap(uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t d_acc, uint32_t idesc_wide, uint32_t idesc_n,
+                                              uint32_t acc_first, uint32_t probe_bar,
+                                              uint32_t probe_parity) {
+  uint32_t ok;
+  if constexpr (!EXACT && MB == 1 && KST == 4) BHSR_TAP_ASM(BHSR_K4(BHSR_STEP_F));
+  else if constexpr (!EXACT && MB == 1 && KST == 2) BHSR_TAP_ASM(BHSR_K2(BHSR_STEP_F));
+  else if constexpr (!EXACT && MB == 2 && KST == 4) BHSR_TAP_ASM(BHSR_K4(BHSR_STEP_F) BHSR_NEXT_MB BHSR_K4(BHSR_STEP_F));
+  else if constexpr (!EXACT && MB == 2 && KST == 2) BHSR_TAP_ASM(BHSR_K2(BHSR_STEP_F) BHSR_NEXT_MB BHSR_K2(BHSR_STEP_F));
+  else if constexpr (EXACT && MB == 1 && KST == 2) BHSR_TAP_ASM(BHSR_K2(BHSR_STEP_E));
+  else if constexpr (EXACT && MB == 1 && KST == 1) BHSR_TAP_ASM(BHSR_K1(BHSR_STEP_E));
+  else if constexpr (EXACT && MB == 2 && KST == 2) BHSR_TAP_ASM(BHSR_K2(BHSR_STEP_E) BHSR_NEXT_MB BHSR_K2(BHSR_STEP_E));
+  else if constexpr (EXACT && MB == 2 && KST == 1) BHSR_TAP_ASM(BHSR_K1(BHSR_STEP_E) BHSR_NEXT_MB BHSR_K1(BHSR_STEP_E));
+  else static_assert(KST < 0, "unsupported issue_tap variant");
+  return ok;
 }
 
 }  // namespace bhsr

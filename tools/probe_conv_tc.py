@@ -63,6 +63,8 @@ def run_case(name, desc_mode):
         "time_exact64_c192": dict(nb=64, cout=64, cin=192, exact=True, lrelu=False, res=1, time=True),
         "time_fast32_mb1": dict(nb=64, mb=1, time=True),
     }
+    cases["time_exact32_mb2"] = dict(nb=64, exact=True, mb=2, time=True)
+    cases["time_exact64_c192_mb2"] = dict(nb=64, cout=64, cin=192, exact=True, mb=2, lrelu=False, res=1, time=True)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
