@@ -121,7 +121,7 @@ __device__ __forceinline__ void add_residual32(float (&v)[32], float alpha, cons
   }
 }
 
-template <int N, bool EXACT, int MB, int KS>
+template <int N, bool EXACT, int MB, int KS, bool WRES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo,
@@ -133,7 +133,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   constexpr int KSTEPS = CH / 16;                  // MMA k-steps per chunk
   constexpr int ROWS_B = EXACT ? 2 * N : N;        // weight rows per tap (= TMEM columns)
   constexpr int NT = KS * KS;                      // taps: a dense KS x KS window
-  constexpr int TG = KS;                           // taps per weight slab (one window row, one barrier)
+  // taps per weight slab (one barrier each): a window row when weights stream through the ring,
+  // the whole window when the layer's weights are resident (WRES) — fewer, longer issue bursts
+  constexpr int TG = WRES ? NT : KS;
   constexpr int NG = NT / TG;                      // slabs per chunk
   constexpr int W_TAP = ROWS_B * RB;               // bytes of one tap's weight tile
   constexpr int W_SLAB = TG * W_TAP;               // bytes
@@ -217,10 +219,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int r0 = (t * MT) / kPitch - 1;
         for (int c = 0; c < p.n_chunks; ++c, ++it, st = (st + 1 == NS ? 0 : st + 1), ph ^= (st == 0)) {
           mbar_wait(bar(B_AEMPTY + st), ph);
-          if ((p.desc_mode & 2) && it >= static_cast<uint32_t>(NS)) {  // timing experiment only
-            mbar_arrive(bar(B_AFULL + st));
-            continue;
-          }
           mbar_expect_tx(bar(B_AFULL + st), A_TX);
           const uint32_t dst = a_base + st * A_STAGE;
           tma_load_4d(dst, &tm_a_hi, bar(B_AFULL + st), p.in_choff + c * CH, s * kStrip - 1, r0, n);
@@ -235,19 +233,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (lane == 0) {
       uint32_t it = 0;
       const int slabs = p.n_chunks * NG;
-      bool first = true;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-        if (p.w_resident && !first) break;
         for (int sl = 0; sl < slabs; ++sl, ++it) {
-          const int ws = it % p.wslots;
-          mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
+          const int ws = WRES ? sl : static_cast<int>(it % p.wslots);
+          if (!WRES) mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
           mbar_expect_tx(bar(B_WFULL + ws), W_SLAB);
 #pragma unroll
           for (int tt = 0; tt < TG; ++tt)
             tma_load_2d(w_base + ws * W_SLAB + tt * W_TAP, &tm_w, bar(B_WFULL + ws), 0,
                         (sl * TG + tt) * ROWS_B);
         }
-        first = false;
+        if (WRES) break;  // resident: loaded once, kept for every tile of this CTA
       }
     }
   } else if (warp == 1) {
@@ -259,20 +255,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     const uint32_t desc_hi = static_cast<uint32_t>(desc_hi_lo0 >> 32);
     const uint32_t desc_lo0 = static_cast<uint32_t>(desc_hi_lo0);  // LBO field, start = 0
     auto mk = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
-    uint32_t a_it = 0, w_it = 0, tile_it = 0;
-    long long t_tempty = 0, t_afull = 0, t_wfull = 0, t_total = clock64(), tq;
+    uint32_t tile_it = 0;
+#ifdef BHSR_TIMING
+    long long t_tempty = 0, t_afull = 0, t_wfull = 0, t_total = clock64(), tq = 0;
     const bool dbg = p.dbg != nullptr;
+#else
+    long long t_tempty = 0, t_afull = 0, t_wfull = 0, tq = 0;
+    constexpr bool dbg = false;
+#endif
     // Early probes.  A barrier test costs ~100 cycles even when the phase is long complete, and
     // the tensor queue is shallow: waiting right before the MMAs that need the data drains it.
-    // So every barrier the NEXT step needs is probed (non-blocking try_wait) before the current
-    // step's MMAs are issued — the probe's latency hides behind their issue — and only a probe
-    // that came back "not yet" falls through to the blocking wait.
+    // So every barrier the NEXT step needs is tested from inside the current step's issue block
+    // (see issue_tap in ptx.cuh) and only a test that came back "not yet" falls through to the
+    // blocking wait.
     uint32_t ok_t = 0, ok_a = 0, ok_w = 0;
     const int my_tiles = (p.total_tiles - first_tile + tile_step - 1) / tile_step;
+    const int n_chunks = p.n_chunks, cin = p.cin, shift0 = p.shift0, wslots = p.wslots;
+    const bool leader = lane == 0;
     // ring positions are advanced incrementally (no integer division on the issue path)
     int st = 0, a_ph = 0;   // activation stage / phase parity
     int ws_r = 0, w_ph = 0; // weight slot / phase parity (streaming mode)
-    const int wslots = p.wslots;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int flat_mod = (t * MT) % kPitch;
@@ -285,31 +287,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       ok_t = 0;
       tc_fence_after();
       const uint32_t acc = tmem_base + as * ACC_COLS;
+      const bool more_tiles = tile_it + 1 < static_cast<uint32_t>(my_tiles);
+      const uint32_t bar_t_next = bar(B_TEMPTY + ((tile_it + 1) & 1));
+      const uint32_t par_t_next = (((tile_it + 1) >> 1) & 1) ^ 1;
       uint32_t accumulate = 0;
-      for (int c = 0; c < p.n_chunks; ++c, ++a_it) {
+      for (int c = 0; c < n_chunks; ++c) {
         if (!ok_a) {
           if (dbg) tq = clock64();
           mbar_wait(bar(B_AFULL + st), a_ph);
           if (dbg) t_afull += clock64() - tq;
         }
         ok_a = 0;
+        tc_fence_after();
         int st_next = st + 1, a_ph_next = a_ph;
         if (st_next == NS) { st_next = 0; a_ph_next ^= 1; }
-        tc_fence_after();
-        // descriptor low word of flat row 0 (tap shift 0, m-block 0) of this stage
+        const uint32_t bar_a_next = bar(B_AFULL + st_next);
+        // descriptor low word of flat row 0 (first tap, m-block 0) of this stage
         const uint32_t a_lo0 =
-            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1 + p.shift0) * RB16;
-        const int rem = p.cin - c * CH;
-        const int ksteps = rem >= CH ? KSTEPS : (rem >> 4);
-        const bool last_chunk = (c + 1 == p.n_chunks);
+            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (flat_mod + kPitch + 1 + shift0) * RB16;
+        const int rem = cin - c * CH;
+        const bool last_chunk = (c + 1 == n_chunks);
         // The slab loop is instantiated twice (full chunk / half chunk of channels) so the
         // unrolled MMA stream has no per-instruction predicates or branches.
         auto issue_chunk = [&](auto ksteps_tag) {
           constexpr int KST = decltype(ksteps_tag)::value;
 #pragma unroll
-          for (int g = 0; g < NG; ++g, ++w_it) {
+          for (int g = 0; g < NG; ++g) {
             int ws;
-            if (p.w_resident) {
+            uint32_t bar_w_next = bar_a_next, par_w_next = a_ph_next;  // placeholder when resident
+            if (WRES) {
               ws = c * NG + g;
               if (tile_it == 0) {
                 mbar_wait(bar(B_WFULL + ws), 0);
@@ -325,52 +331,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
               ok_w = 0;
               tc_fence_after();
               if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }   // next slab (may belong to the next tile)
+              bar_w_next = bar(B_WFULL + ws_r);
+              par_w_next = w_ph;
             }
-            // barriers probed from inside the tap blocks: tap 0 -> next weight slab, tap 1 -> next
-            // activation stage, tap 2 -> the next tile's accumulator (only consumed where relevant)
-            const bool more_tiles = tile_it + 1 < static_cast<uint32_t>(my_tiles);
-            const uint32_t nt = tile_it + 1;
-            const uint32_t pb[3] = {bar(B_WFULL + (p.w_resident ? ws : ws_r)), bar(B_AFULL + st_next),
-                                    bar(B_TEMPTY + (nt & 1))};
-            const uint32_t pp[3] = {static_cast<uint32_t>(p.w_resident ? 0 : w_ph),
-                                    static_cast<uint32_t>(a_ph_next), ((nt >> 1) & 1) ^ 1};
-            uint32_t okv[3] = {0, 0, 0};
+            // probe slots of the tap blocks: [0] next weight slab, [1] next activation stage,
+            // [2] the next tile's accumulator; a slot is only consumed where it is meaningful
             const uint32_t b_lo0 = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
-            if (elect_one()) {
+            uint32_t okbits = 0;
+            if (leader) {
 #pragma unroll
               for (int tt = 0; tt < TG; ++tt) {
                 const int tap = g * TG + tt;    // compile-time after unrolling
                 const uint32_t a_lo = a_lo0 + ((tap / KS) * kPitch + (tap % KS)) * RB16;
                 const uint32_t b_lo = b_lo0 + tt * (W_TAP >> 4);
-                okv[tt] = issue_tap<EXACT, MB, KST, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N>(
-                    a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, tt > 0 ? 1u : accumulate, pb[tt],
-                    pp[tt]);
+                const int slot = tt < 3 ? tt : 1;
+                const uint32_t pbar = slot == 0 ? bar_w_next : (slot == 1 ? bar_a_next : bar_t_next);
+                const uint32_t ppar = slot == 0 ? par_w_next
+                                                : (slot == 1 ? static_cast<uint32_t>(a_ph_next) : par_t_next);
+                const uint32_t ok = issue_tap<EXACT, MB, KST, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N>(
+                    a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, tt > 0 ? 1u : accumulate, pbar, ppar);
+                if (tt < 3) okbits |= ok << tt;
               }
-              if (!p.w_resident) umma_commit(bar(B_WEMPTY + ws));
+              if (!WRES) umma_commit(bar(B_WEMPTY + ws));
             }
-            __syncwarp();
-            if (!p.w_resident) ok_w = __any_sync(0xffffffffu, okv[0]);
+            okbits = __reduce_or_sync(0xffffffffu, okbits);
+            if (!WRES) ok_w = okbits & 1u;
             if (g == NG - 1) {
-              if (!last_chunk || more_tiles) ok_a = __any_sync(0xffffffffu, okv[1]);
-              if (TG >= 3 && last_chunk && more_tiles) ok_t = __any_sync(0xffffffffu, okv[2]);
+              if (!last_chunk || more_tiles) ok_a = (okbits >> 1) & 1u;
+              if (TG >= 3 && last_chunk && more_tiles) ok_t = (okbits >> 2) & 1u;
             }
             accumulate = 1;
           }
         };
-        if (ksteps == KSTEPS) issue_chunk(std::integral_constant<int, KSTEPS>{});
+        if (rem >= CH) issue_chunk(std::integral_constant<int, KSTEPS>{});
         else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
-        if (elect_one()) umma_commit(bar(B_AEMPTY + st));
+        if (leader) umma_commit(bar(B_AEMPTY + st));
         __syncwarp();
         st = st_next;
         a_ph = a_ph_next;
       }
-      if (elect_one()) umma_commit(bar(B_TFULL + as));
+      if (leader) umma_commit(bar(B_TFULL + as));
       __syncwarp();
     }
+#ifdef BHSR_TIMING
     if (dbg && lane == 0) {
       long long* o = p.dbg + blockIdx.x * 8;
       o[0] = clock64() - t_total; o[1] = t_tempty; o[2] = t_afull; o[3] = t_wfull; o[4] = tile_it;
     }
+#endif
+    (void)t_tempty; (void)t_afull; (void)t_wfull; (void)tq;
   } else {
     // ------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -385,11 +394,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       const int as = tile_it & 1;
       mbar_wait(bar(B_TFULL + as), (tile_it >> 1) & 1);
       tc_fence_after();
-      if (p.desc_mode & 1) {  // timing experiment only: skip the epilogue work
-        tc_fence_before();
-        mbar_arrive(bar(B_TEMPTY + as));
-        continue;
-      }
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
         const int f = t * MT + mb * 128 + row;
@@ -532,12 +536,36 @@ static int make_weight_map(CUtensorMap* tm, const void* base, int total_rows, in
   return 0;
 }
 
+template <int N, bool EXACT, int MB, int KS, bool WRES>
+static int launch_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
+                         const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
+  auto kern = conv_tc_kernel<N, EXACT, MB, KS, WRES>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    BHSR_CUDA_CHECK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  BHSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));
+  return 0;
+}
+
 template <int N, bool EXACT, int MB, int KS>
 static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream) {
   constexpr int CH = EXACT ? 32 : 64;
   using G = TileGeom<MB, CH>;
   constexpr int ROWS_B = EXACT ? 2 * N : N;
-  constexpr int TG = KS;
+  constexpr int TG = KS;  // streaming granularity; a resident layer occupies the same bytes
   constexpr int W_SLAB = TG * ROWS_B * G::kRowBytes;
   constexpr int A_STAGE = G::kTileBytes * (EXACT ? 2 : 1);
   const int slabs = p.n_chunks * (KS * KS / TG);
@@ -573,31 +601,17 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
   rc = make_weight_map(&tm_w, d.w_packed, p.n_chunks * KS * KS * ROWS_B, ROWS_B, CH);
   if (rc) return rc;
 
-  auto kern = conv_tc_kernel<N, EXACT, MB, KS>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    BHSR_CUDA_CHECK(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set = true;
-  }
   int sms = device_sm_count();
   if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
   static const char* no_pdl = getenv("BHSR_NO_PDL");
   p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = p.pdl ? 1 : 0;
-  BHSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));
-  return 0;
+  if (p.w_resident) {
+    p.wslots = p.n_chunks;  // resident kernels use one slot (and barrier) per chunk
+    return launch_kernel<N, EXACT, MB, KS, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  }
+  return launch_kernel<N, EXACT, MB, KS, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
 }
 
 }  // namespace bhsr
