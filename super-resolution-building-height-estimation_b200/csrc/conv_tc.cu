@@ -271,7 +271,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     uint32_t ok_t = 0, ok_a = 0, ok_w = 0;
     const int my_tiles = (p.total_tiles - first_tile + tile_step - 1) / tile_step;
     const int n_chunks = p.n_chunks, cin = p.cin, shift0 = p.shift0, wslots = p.wslots;
-    const bool leader = lane == 0;
     // ring positions are advanced incrementally (no integer division on the issue path)
     int st = 0, a_ph = 0;   // activation stage / phase parity
     int ws_r = 0, w_ph = 0; // weight slot / phase parity (streaming mode)
@@ -338,7 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             // [2] the next tile's accumulator; a slot is only consumed where it is meaningful
             const uint32_t b_lo0 = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
             uint32_t okbits = 0;
-            if (leader) {
+            if (elect_one()) {  // elect.sync: the compiler keeps the block on the uniform datapath
 #pragma unroll
               for (int tt = 0; tt < TG; ++tt) {
                 const int tap = g * TG + tt;    // compile-time after unrolling
@@ -365,12 +364,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         };
         if (rem >= CH) issue_chunk(std::integral_constant<int, KSTEPS>{});
         else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
-        if (leader) umma_commit(bar(B_AEMPTY + st));
+        if (elect_one()) umma_commit(bar(B_AEMPTY + st));
         __syncwarp();
         st = st_next;
         a_ph = a_ph_next;
       }
-      if (leader) umma_commit(bar(B_TFULL + as));
+      if (elect_one()) umma_commit(bar(B_TFULL + as));
       __syncwarp();
     }
 #ifdef BHSR_TIMING
