@@ -21,11 +21,11 @@
 // operand, so they are one MMA with the two weight tiles stacked along N (N -> 2N).
 //
 // Warp roles (224 threads, 1 CTA per SM, persistent over tiles):
-//   warp 0 lane 0 : TMA producer for activation halo tiles   (ring of 2 stages)
-//   warp 1 lane 0 : tcgen05.mma issuer; warp 1 also owns the TMEM allocation
-//   warps 2..5    : epilogue (TMEM -> registers -> bias/LeakyReLU/residual -> global)
-//   warp 6 lane 0 : TMA producer for weight tiles (ring of `wslots` per-tap slabs; when the
+//   warps 0..3    : epilogue (TMEM -> registers -> bias/LeakyReLU/residual -> global)
+//   warp 4 lane 0 : TMA producer for activation halo tiles   (ring of 2-4 stages)
+//   warp 5 lane 0 : TMA producer for weight tiles (ring of per-window-row slabs; when the
 //                   whole layer fits the ring the weights are loaded once and stay resident)
+//   warp 6        : tcgen05.mma issuer (elected lane); also owns the TMEM allocation
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -42,6 +42,9 @@ namespace bhsr {
 constexpr int kPitch = 66;          // strip width 64 + 2 halo columns
 constexpr int kStrip = 64;
 constexpr int kThreads = 224;
+// warp roles (see header): the MMA issuer gets the highest warp index of its scheduler partition —
+// the arbiter favours higher warp ids, and the issuer must never be starved by an epilogue warp
+constexpr int kWarpProdA = 4, kWarpProdW = 5, kWarpMma = 6;  // warps 0..3 = epilogue
 constexpr int kMaxWSlots = 32;
 constexpr int kSmemLimit = 232448;  // 227 KB
 
@@ -187,7 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     tma_prefetch_desc(&tm_w);
   }
   if (threadIdx.x < N) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
@@ -200,13 +203,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   // residuals and outputs are only touched after the previous grid has fully completed.
   if (p.pdl) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (warp != 6) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (warp != kWarpProdW) asm volatile("griddepcontrol.wait;" ::: "memory");
   }
 
   const int first_tile = blockIdx.x;
   const int tile_step = gridDim.x;
 
-  if (warp == 0) {
+  if (warp == kWarpProdA) {
     // ------------------------------------------------ activation producer
     if (lane == 0) {
       uint32_t it = 0;
@@ -228,7 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == kWarpProdW) {
     // ------------------------------------------------ weight producer
     if (lane == 0) {
       uint32_t it = 0;
@@ -246,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         if (WRES) break;  // resident: loaded once, kept for every tile of this CTA
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ------------------------------------------------ MMA issuer
     // The whole warp walks the loop (warp-uniform control flow keeps the descriptor arithmetic
     // on the uniform datapath); one elected lane issues the tcgen05 instructions.  Descriptors
@@ -380,8 +383,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #endif
     (void)t_tempty; (void)t_afull; (void)t_wfull; (void)tq;
   } else {
-    // ------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------ epilogue (warps 0..3)
+    const int q = warp;  // TMEM lane quarter this warp may access (warp id % 4)
     const int row = q * 32 + lane;
     uint32_t tile_it = 0;
     const bool nchw = (p.epilogue & BHSR_EPI_OUT_NCHW_F32) != 0;
@@ -449,7 +452,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             // Store transpose: a lane owns one pixel (64 B of this 32-channel slice).  Written
             // directly, every 16-byte store instruction would touch 32 different lines; staged
             // through shared memory, a store instruction covers 8 pixels x 64 B (8 lines).
-            uint8_t* stg = s_stage + (warp - 2) * (32 * 80);
+            uint8_t* stg = s_stage + warp * (32 * 80);
             const uint32_t pix32 = valid ? static_cast<uint32_t>(out_pix) : 0xFFFFFFFFu;
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
@@ -490,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

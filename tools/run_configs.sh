@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import torch; torch.zeros(1).cuda()" > /dev/null 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
+for c in 3 5; do
+  timeout 900 python tools/bench_configs.py --config $c > gpurun_out/config$c.log 2>&1; echo "config $c rc=$?"; tail -2 gpurun_out/config$c.log | cut -c1-600
+done
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log 2>&1; tail -1 gpurun_out/bench_reference.log | cut -c1-400
