@@ -124,7 +124,9 @@ __device__ __forceinline__ void add_residual32(float (&v)[32], float alpha, cons
   }
 }
 
-template <int N, bool EXACT, int MB, int KS, bool WRES>
+// WMODE: how the weights reach shared memory — 0: streamed, one window row (KS taps) per ring
+// slot; 1: streamed, a whole window (KS*KS taps) per slot; 2: resident (loaded once per CTA).
+template <int N, bool EXACT, int MB, int KS, int WMODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo,
@@ -138,7 +140,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   constexpr int NT = KS * KS;                      // taps: a dense KS x KS window
   // taps per weight slab (one barrier each): a window row when weights stream through the ring,
   // the whole window when the layer's weights are resident (WRES) — fewer, longer issue bursts
-  constexpr int TG = WRES ? NT : KS;
+  constexpr bool WRES = WMODE == 2;
+  constexpr int TG = WMODE == 0 ? KS : NT;
   constexpr int NG = NT / TG;                      // slabs per chunk
   constexpr int W_TAP = ROWS_B * RB;               // bytes of one tap's weight tile
   constexpr int W_SLAB = TG * W_TAP;               // bytes
@@ -538,10 +541,10 @@ static int make_weight_map(CUtensorMap* tm, const void* base, int total_rows, in
   return 0;
 }
 
-template <int N, bool EXACT, int MB, int KS, bool WRES>
+template <int N, bool EXACT, int MB, int KS, int WMODE>
 static int launch_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
                          const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
-  auto kern = conv_tc_kernel<N, EXACT, MB, KS, WRES>;
+  auto kern = conv_tc_kernel<N, EXACT, MB, KS, WMODE>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     BHSR_CUDA_CHECK(
@@ -590,10 +593,24 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
     static const char* force = getenv("BHSR_DEBUG_FORCE_STREAM");  // debug knob: never resident
     if (force && force[0] == '1' && wslots >= 2) { p.w_resident = 0; if (wslots > 4) wslots = 4; }
   }
-  if (p.w_resident) wslots = slabs;
+  int wmode = p.w_resident ? 2 : 0;
+  int w_bytes = wslots * W_SLAB;
+  if (p.w_resident) {
+    w_bytes = slabs * W_SLAB;
+    wslots = p.n_chunks;  // resident kernels use one slot (and barrier) per chunk
+  } else if (wslots * W_SLAB >= 2 * KS * W_SLAB) {
+    // streaming, and two whole-window slabs fit: fewer, longer issue bursts (one wait per chunk)
+    static const char* small = getenv("BHSR_DEBUG_ROW_SLABS");
+    if (!(small && small[0] == '1')) {
+      wmode = 1;
+      wslots = (wslots * W_SLAB) / (KS * W_SLAB);
+      if (wslots > 3) wslots = 3;
+      w_bytes = wslots * KS * W_SLAB;
+    }
+  }
   p.wslots = wslots;
   p.astages = astages;
-  const int smem_bytes = 1024 + astages * A_STAGE + wslots * W_SLAB + kTailBytes;
+  const int smem_bytes = 1024 + astages * A_STAGE + w_bytes + kTailBytes;
 
   CUtensorMap tm_hi, tm_lo, tm_w;
   int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, CH);
@@ -609,11 +626,9 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
   static const char* no_pdl = getenv("BHSR_NO_PDL");
   p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
-  if (p.w_resident) {
-    p.wslots = p.n_chunks;  // resident kernels use one slot (and barrier) per chunk
-    return launch_kernel<N, EXACT, MB, KS, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
-  }
-  return launch_kernel<N, EXACT, MB, KS, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  if (wmode == 2) return launch_kernel<N, EXACT, MB, KS, 2>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  if (wmode == 1) return launch_kernel<N, EXACT, MB, KS, 1>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  return launch_kernel<N, EXACT, MB, KS, 0>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
 }
 
 }  // namespace bhsr
