@@ -599,9 +599,11 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
     w_bytes = slabs * W_SLAB;
     wslots = p.n_chunks;  // resident kernels use one slot (and barrier) per chunk
   } else if (wslots * W_SLAB >= 2 * KS * W_SLAB) {
-    // streaming, and two whole-window slabs fit: fewer, longer issue bursts (one wait per chunk)
-    static const char* small = getenv("BHSR_DEBUG_ROW_SLABS");
-    if (!(small && small[0] == '1')) {
+    // streaming, and two whole-window slabs fit: fewer, longer issue bursts (one wait per chunk).
+    // Measured on B200 (profiles/r01_summary.md): no gain over row slabs — the shallower ring
+    // (2 slots) costs what the longer bursts save — so it is opt-in.
+    static const char* big = getenv("BHSR_WINDOW_SLABS");
+    if (big && big[0] == '1') {
       wmode = 1;
       wslots = (wslots * W_SLAB) / (KS * W_SLAB);
       if (wslots > 3) wslots = 3;
