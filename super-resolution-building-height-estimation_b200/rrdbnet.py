@@ -252,6 +252,8 @@ class _RRDBNetBase(nn.Module):
         if cin != first.in_channels:
             raise RuntimeError(f"expected input with {first.in_channels} channels, got {cin}")
         dev = x.device
+        if nb == 0 or h == 0 or w == 0:  # empty batch: nothing to launch (nn.Conv2d returns empty too)
+            return torch.empty((nb, 64 if feature else last.out_channels, 4 * h, 4 * w), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             packed, biases = self._get_packed(dev)
             ws = self._get_workspace(dev, nb, h, w, feature)

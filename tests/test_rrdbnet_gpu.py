@@ -264,6 +264,23 @@ def test_rrdbnet_views_ragged_sizes_and_batch_independence(dev):
     assert torch.equal(alone[0], fea[1]) and torch.equal(again, fea)
 
 
+def test_rrdbnet_tiny_and_empty_inputs(dev):
+    """Edge cases: images smaller than one MMA tile / one TMA box, and an empty batch."""
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_block=1, seed=9)
+    net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=1, num_grow_ch=32), sd, dev)
+    for h, w in ((1, 1), (3, 5), (8, 8), (65, 2)):
+        x = synth.tiles(2, 3, h, w, seed=h * 10 + w)
+        with torch.no_grad():
+            y = net.forward_feature(cuda(x, dev)).cpu().numpy()
+        assert y.shape == (2, 64, 4 * h, 4 * w)
+        assert_close(y, R.rrdbnet_forward_feature(x, sd, acc_dtype=np.float64), what=f"{h}x{w} input")
+    with torch.no_grad():
+        e = net.forward_feature(torch.zeros(0, 3, 64, 64, device=dev))
+        e2 = net(torch.zeros(0, 3, 64, 64, device=dev))
+    assert e.shape == (0, 64, 256, 256) and e2.shape == (0, 3, 256, 256)
+
+
 def test_rrdbnet_full_batch_properties(dev):
     """BASELINE config 2 size (B=64, 23 blocks): run-to-run determinism and batch independence."""
     from bhsr import rrdbnet
