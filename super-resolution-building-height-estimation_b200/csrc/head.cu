@@ -53,31 +53,40 @@ __device__ __forceinline__ float load_in(const ConvArgs& a, int n, int c, int yy
 }
 
 // ------------------------------------------------------------------ forward conv (also dgrad)
+// Block = 256 threads on a 32 x 32 pixel tile; a thread owns 4 consecutive pixels x CT output
+// channels (register tile): per input channel it reads its 3 x 6 input window once and every
+// weight as a float4 broadcast, ~11 FMAs per shared-memory load.  Input rows are padded to a
+// stride = 1 (mod 4) words so the 8 x 4 thread footprint of a warp is bank-conflict free.
+constexpr int kFT = 32;  // forward tile edge (pixels)
 template <int K, int CT>
-__global__ void __launch_bounds__(kTW * kTH)
+__global__ void __launch_bounds__(256)
 conv_fwd_kernel(const ConvArgs a) {
   constexpr int P = K / 2;
-  constexpr int IW = kTW + 2 * P, IH = kTH + 2 * P;
-  __shared__ float s_in[kCI][IH][IW + 1];
-  __shared__ float s_w[kCI][K * K][CT];
-  const int tiles_x = (a.w + kTW - 1) / kTW;
-  const int tx0 = (blockIdx.x % tiles_x) * kTW, ty0 = (blockIdx.x / tiles_x) * kTH;
+  constexpr int IW = kFT + 2 * P, IH = kFT + 2 * P;
+  constexpr int RS = (K == 3) ? 37 : 33;
+  __shared__ float s_in[kCI][IH][RS];
+  __shared__ __align__(16) float s_w[kCI][K * K][CT];
+  const int tiles_x = (a.w + kFT - 1) / kFT;
+  const int tx0 = (blockIdx.x % tiles_x) * kFT, ty0 = (blockIdx.x / tiles_x) * kFT;
   const int co0 = blockIdx.y * CT;
   const int n = blockIdx.z;
-  const int tid = threadIdx.y * kTW + threadIdx.x;
-  float acc[CT];
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;     // 8 x 32 threads; pixels (ty0+ty, tx0+4*tx .. +3)
+  float acc[4][CT];
 #pragma unroll
-  for (int j = 0; j < CT; ++j) acc[j] = 0.f;
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < CT; ++j) acc[q][j] = 0.f;
 
   for (int c0 = 0; c0 < a.cin; c0 += kCI) {
-    for (int i = tid; i < kCI * IH * IW; i += kTW * kTH) {
+    for (int i = tid; i < kCI * IH * IW; i += 256) {
       const int ci = i / (IH * IW), r = i % (IH * IW);
       const int yy = r / IW, xx = r % IW;
       float v = 0.f;
       if (c0 + ci < a.cin) v = load_in(a, n, c0 + ci, ty0 + yy - P, tx0 + xx - P);
       s_in[ci][yy][xx] = v;
     }
-    for (int i = tid; i < kCI * K * K * CT; i += kTW * kTH) {
+    for (int i = tid; i < kCI * K * K * CT; i += 256) {
       const int j = i % CT, t = (i / CT) % (K * K), ci = i / (CT * K * K);
       float v = 0.f;
       if (c0 + ci < a.cin && co0 + j < a.cout)
@@ -85,51 +94,85 @@ conv_fwd_kernel(const ConvArgs a) {
       s_w[ci][t][j] = v;
     }
     __syncthreads();
-#pragma unroll
+#pragma unroll 2
     for (int ci = 0; ci < kCI; ++ci) {
+      float in[K][4 + 2 * P];
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+        for (int c = 0; c < 4 + 2 * P; ++c) in[ky][c] = s_in[ci][ty + ky][4 * tx + c];
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
-          const float v = s_in[ci][threadIdx.y + ky][threadIdx.x + kx];
-          const float* wr = s_w[ci][ky * K + kx];
+          float wv[CT];
+          const float4* wr = reinterpret_cast<const float4*>(s_w[ci][ky * K + kx]);
 #pragma unroll
-          for (int j = 0; j < CT; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+          for (int j4 = 0; j4 < CT / 4; ++j4) {
+            const float4 t4 = wr[j4];
+            wv[4 * j4] = t4.x; wv[4 * j4 + 1] = t4.y; wv[4 * j4 + 2] = t4.z; wv[4 * j4 + 3] = t4.w;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v = in[ky][q + kx];
+#pragma unroll
+            for (int j = 0; j < CT; ++j) acc[q][j] = fmaf(v, wv[j], acc[q][j]);
+          }
         }
       }
     }
     __syncthreads();
   }
 
-  const int px = tx0 + threadIdx.x, py = ty0 + threadIdx.y;
-  const bool valid = px < a.w && py < a.h;
+  const int py = ty0 + ty, px0 = tx0 + 4 * tx;
+  const bool row_ok = py < a.h;
 #pragma unroll
   for (int j = 0; j < CT; ++j) {
     const int co = co0 + j;
     if (co >= a.cout) break;
-    float v = acc[j] + (a.bias ? a.bias[co] : 0.f);
+    const float b = a.bias ? a.bias[co] : 0.f;
+    float v[4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = acc[q][j] + b;
+      if (row_ok && px0 + q < a.w) { s1 += v[q]; s2 = fmaf(v[q], v[q], s2); }
+    }
     if (a.stats) {
-      float s1 = valid ? v : 0.f, s2 = valid ? v * v : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
       }
-      if (threadIdx.x == 0) {
+      if ((tid & 31) == 0) {
         atomicAdd(a.stats + co, static_cast<double>(s1));
         atomicAdd(a.stats + a.cout + co, static_cast<double>(s2));
       }
     }
-    if (valid) {
-      size_t o;
-      if (a.y_shuffle) {
-        const int cs = co >> 2, i = (co >> 1) & 1, jj = co & 1;
-        o = ((static_cast<size_t>(n) * a.y_ctot + a.y_choff + cs) * (2 * a.h) + 2 * py + i) *
-                (2 * a.w) + 2 * px + jj;
-      } else {
-        o = ((static_cast<size_t>(n) * a.y_ctot + a.y_choff + co) * a.h + py) * a.w + px;
+    if (!row_ok) continue;
+    if (a.y_shuffle) {
+      const int cs = co >> 2, i = (co >> 1) & 1, jj = co & 1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (px0 + q >= a.w) break;
+        const size_t o = ((static_cast<size_t>(n) * a.y_ctot + a.y_choff + cs) * (2 * a.h) + 2 * py + i) *
+                             (2 * a.w) + 2 * (px0 + q) + jj;
+        if (a.accumulate) a.y[o] += v[q]; else a.y[o] = v[q];
       }
-      if (a.accumulate) a.y[o] += v; else a.y[o] = v;
+    } else {
+      const size_t o = ((static_cast<size_t>(n) * a.y_ctot + a.y_choff + co) * a.h + py) * a.w + px0;
+      if (px0 + 3 < a.w && (o & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
+        float4* dst = reinterpret_cast<float4*>(a.y + o);
+        float4 r = make_float4(v[0], v[1], v[2], v[3]);
+        if (a.accumulate) { const float4 old = *dst; r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+        *dst = r;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (px0 + q >= a.w) break;
+          if (a.accumulate) a.y[o + q] += v[q]; else a.y[o + q] = v[q];
+        }
+      }
     }
   }
 }
@@ -159,35 +202,53 @@ __device__ __forceinline__ float load_dy(const WgradArgs& a, int n, int c, int y
 template <int K>
 __global__ void __launch_bounds__(256)
 conv_wgrad_kernel(const WgradArgs a, int co0, int c0) {
+  // GEMM view per 32x8 pixel tile: C[16 co][kCI*K*K (ci,tap)] += dy[co][p] * x'[ci][p + tap].
+  // Threads form `kSlices` pixel slices of (2 co-groups x COLG column-groups); a thread keeps an
+  // 8 co x 6 column register tile over every pixel of its slice (48 FMAs per 14 shared loads),
+  // slices are combined in shared memory and added to global dw once per block.
   constexpr int P = K / 2;
   constexpr int KK = K * K;
   constexpr int CT = 16;
   constexpr int IW = kTW + 2 * P, IH = kTH + 2 * P;
-  constexpr int NB = kCI * KK;                 // B columns (ci,tap)
-  constexpr int NBT = (NB + 2) / 3;            // column triples
+  constexpr int NCOL = kCI * KK;
+  constexpr int COLG = (NCOL + 5) / 6;
+  constexpr int TPS = 2 * COLG;               // threads per slice
+  constexpr int kSlices = 256 / TPS;
+  constexpr int DYS = kTH * (kTW + 1) + 1;     // s_dy channel stride (odd: the two co-groups hit different banks)
   __shared__ float s_in[kCI][IH][IW + 1];
-  __shared__ float s_dy[CT][kTH][kTW + 1];
+  __shared__ float s_dy[CT * DYS];
+  __shared__ float s_red[CT][NCOL + 1];
+  __shared__ float s_db[CT];
   const int tid = threadIdx.x;
-  const int rp = tid / NBT;                    // row pair 0..7 -> co = 2*rp, 2*rp+1
-  const int ct = tid % NBT;
-  const bool active = rp < CT / 2;
-  int col_ci[3], col_ky[3], col_kx[3];
+  const int slice = tid / TPS, g = tid % TPS;
+  const int cg = g / COLG, colg = g % COLG;
+  const bool active = slice < kSlices;
+  int off[6];  // shared-memory offset of column j's input sample relative to the pixel
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    int col = ct * 3 + j;
-    if (col >= NB) col = NB - 1;
-    col_ci[j] = col / KK;
-    col_ky[j] = (col % KK) / K;
-    col_kx[j] = (col % KK) % K;
+  for (int j = 0; j < 6; ++j) {
+    int col = colg * 6 + j;
+    if (col >= NCOL) col = NCOL - 1;
+    const int ci = col / KK, t = col % KK;
+    off[j] = (ci * IH + t / K) * (IW + 1) + t % K;
   }
-  float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  float dbacc = 0.f;
+  for (int i = tid; i < CT * (NCOL + 1); i += 256) (&s_red[0][0])[i] = 0.f;
+  if (tid < CT) s_db[tid] = 0.f;
+  float acc[8][6];
+  float dbacc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    dbacc[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[r][j] = 0.f;
+  }
   const int tiles_x = (a.in.w + kTW - 1) / kTW, tiles_y = (a.in.h + kTH - 1) / kTH;
   const int tiles = tiles_x * tiles_y * a.in.nb;
+  const float* sin_flat = &s_in[0][0][0];
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int n = tile / (tiles_x * tiles_y);
     const int tr = tile % (tiles_x * tiles_y);
     const int tx0 = (tr % tiles_x) * kTW, ty0 = (tr / tiles_x) * kTH;
+    __syncthreads();
     for (int i = tid; i < kCI * IH * IW; i += 256) {
       const int ci = i / (IH * IW), r = i % (IH * IW);
       const int yy = r / IW, xx = r % IW;
@@ -200,46 +261,46 @@ conv_wgrad_kernel(const WgradArgs a, int co0, int c0) {
       const int yy = r / kTW, xx = r % kTW;
       float v = 0.f;
       if (co0 + co < a.cout) v = load_dy(a, n, co0 + co, ty0 + yy, tx0 + xx);
-      s_dy[co][yy][xx] = v;
+      s_dy[co * DYS + yy * (kTW + 1) + xx] = v;
     }
     __syncthreads();
     if (active) {
-      for (int yy = 0; yy < kTH; ++yy) {
-#pragma unroll 8
-        for (int xx = 0; xx < kTW; ++xx) {
-          const float d0 = s_dy[2 * rp][yy][xx], d1 = s_dy[2 * rp + 1][yy][xx];
+      for (int pidx = slice; pidx < kTH * kTW; pidx += kSlices) {
+        const int yy = pidx / kTW, xx = pidx % kTW;
+        const int pbase = yy * (IW + 1) + xx;
+        float xv[6], d[8];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const float v = s_in[col_ci[j]][yy + col_ky[j]][xx + col_kx[j]];
-            acc[0][j] = fmaf(d0, v, acc[0][j]);
-            acc[1][j] = fmaf(d1, v, acc[1][j]);
-          }
+        for (int j = 0; j < 6; ++j) xv[j] = sin_flat[pbase + off[j]];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) d[r] = s_dy[(cg * 8 + r) * DYS + yy * (kTW + 1) + xx];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (colg == 0) dbacc[r] += d[r];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) acc[r][j] = fmaf(d[r], xv[j], acc[r][j]);
         }
       }
     }
-    if (a.db && c0 == 0 && tid < CT) {  // bias gradient: one thread per output channel
-      float s = 0.f;
-      for (int yy = 0; yy < kTH; ++yy)
-        for (int xx = 0; xx < kTW; ++xx) s += s_dy[tid][yy][xx];
-      dbacc += s;
-    }
-    __syncthreads();
   }
   if (active) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int co = co0 + 2 * rp + r;
+    for (int r = 0; r < 8; ++r) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int col = ct * 3 + j;
-        const int ci = c0 + col_ci[j];
-        if (col < NB && co < a.cout && ci < a.in.cin)
-          atomicAdd(a.dw + (static_cast<size_t>(co) * a.in.cin + ci) * KK + col_ky[j] * K + col_kx[j],
-                    acc[r][j]);
+      for (int j = 0; j < 6; ++j) {
+        const int col = colg * 6 + j;
+        if (col < NCOL) atomicAdd(&s_red[cg * 8 + r][col], acc[r][j]);
       }
+      if (colg == 0) atomicAdd(&s_db[cg * 8 + r], dbacc[r]);
     }
   }
-  if (a.db && c0 == 0 && tid < CT && co0 + tid < a.cout) atomicAdd(a.db + co0 + tid, dbacc);
+  __syncthreads();
+  for (int i = tid; i < CT * NCOL; i += 256) {
+    const int co = co0 + i / NCOL, col = i % NCOL;
+    const int ci = c0 + col / KK, t = col % KK;
+    if (co < a.cout && ci < a.in.cin)
+      atomicAdd(a.dw + (static_cast<size_t>(co) * a.in.cin + ci) * KK + t, s_red[i / NCOL][col]);
+  }
+  if (a.db && c0 == 0 && tid < CT && co0 + tid < a.cout) atomicAdd(a.db + co0 + tid, s_db[tid]);
 }
 
 // ------------------------------------------------------------------ BatchNorm pieces
@@ -479,8 +540,8 @@ extern "C" int bhsr_head_conv(const BhsrHeadConvDesc* dp, void* stream_) {
   const BhsrHeadConvDesc& d = *dp;
   ConvArgs a = to_args(d);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  const int tiles = ((d.w + kTW - 1) / kTW) * ((d.h + kTH - 1) / kTH);
-  dim3 block(kTW, kTH);
+  const int tiles = ((d.w + kFT - 1) / kFT) * ((d.h + kFT - 1) / kFT);
+  dim3 block(256);
   if (d.cout <= 8) {
     dim3 grid(tiles, 1, d.nb);
     if (d.ksize == 3) conv_fwd_kernel<3, 8><<<grid, block, 0, st>>>(a);
