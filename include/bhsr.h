@@ -45,7 +45,9 @@ enum {
   BHSR_EPI_LRELU = 1,      /* v = v > 0 ? v : 0.2 v            (rrdbnet_arch.py:137-140, 219-220) */
   BHSR_EPI_RES1 = 2,       /* v = v * alpha1 + res1            (rrdbnet_arch.py:143, 217)         */
   BHSR_EPI_RES2 = 4,       /* v = v * alpha2 + res2  (after 1) (rrdbnet_arch.py:167)              */
-  BHSR_EPI_OUT_NCHW_F32 = 8 /* write fp32 NCHW instead of fp16 planes (rrdbnet_arch.py:238)      */
+  BHSR_EPI_OUT_NCHW_F32 = 8, /* write fp32 NCHW instead of fp16 planes (rrdbnet_arch.py:238)     */
+  BHSR_EPI_RELU = 16,      /* v = max(v, 0) after the residual adds (HRfuse.py:146-157)          */
+  BHSR_EPI_SHUFFLE2 = 32   /* scatter through nn.PixelShuffle(2) into planes (HRfuse.py:24)      */
 };
 
 int bhsr_version(void);
@@ -71,6 +73,8 @@ typedef struct BhsrConvTcDesc {
   const void* w_packed;
   int32_t cout;             /* 32 or 64 */
   const float* bias;        /* [cout] or NULL */
+  const float* scale;       /* [cout] or NULL: v = acc*scale + bias (eval-mode BatchNorm folded in) */
+  int32_t cout_valid;       /* channels actually stored (0 = cout); padded rows of the MMA are dropped */
   /* tap table: output(y,x) = sum_t W_t . in(y+dy[t], x+dx[t]); zero outside the image */
   int32_t ntaps;            /* 1..9 */
   int8_t dy[9], dx[9];

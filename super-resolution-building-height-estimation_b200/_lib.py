@@ -22,6 +22,8 @@ EPI_LRELU = 1
 EPI_RES1 = 2
 EPI_RES2 = 4
 EPI_OUT_NCHW_F32 = 8
+EPI_RELU = 16
+EPI_SHUFFLE2 = 32
 
 
 class BhsrError(RuntimeError):
@@ -38,6 +40,8 @@ class ConvTcDesc(C.Structure):
         ("w_packed", C.c_void_p),
         ("cout", C.c_int32),
         ("bias", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("cout_valid", C.c_int32),
         ("ntaps", C.c_int32),
         ("dy", C.c_int8 * 9), ("dx", C.c_int8 * 9),
         ("oh", C.c_int32), ("ow", C.c_int32), ("out_scale", C.c_int32),

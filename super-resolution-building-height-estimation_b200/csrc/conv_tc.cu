@@ -59,6 +59,8 @@ struct ConvTcKernelParams {
   int out_ctot, out_choff;
   float* out_f32;
   const float* bias;
+  const float* scale;   // optional per-output-channel multiplier (folded BatchNorm)
+  int cout_valid;       // output channels actually stored (<= N)
   int epilogue;
   float alpha1, alpha2;
   const __half* res1_hi;
@@ -169,7 +171,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   const int B_WEMPTY = B_WFULL + kMaxWSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_WFULL + 2 * kMaxWSlots);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + 64);  // 4 epilogue warps x 32 rows x 80 B
+  float* s_scale = s_bias + 64;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_scale + 64);  // 4 epilogue warps x 32 rows x 80 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,7 +195,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (EXACT) tma_prefetch_desc(&tm_a_lo);
     tma_prefetch_desc(&tm_w);
   }
-  if (threadIdx.x < N) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < N) {
+    s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+  }
   if (warp == kWarpMma) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
@@ -429,8 +435,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           }
+          if (cc * 32 >= p.cout_valid) continue;  // padded output channels: nothing to store (uniform)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += s_bias[cc * 32 + j];
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[cc * 32 + j], s_bias[cc * 32 + j]);
           if (p.epilogue & BHSR_EPI_LRELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
@@ -443,13 +450,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
               add_residual32(v, p.alpha2, p.res2_hi, p.res2_lo,
                              in_pix * p.res2_ctot + p.res2_choff + cc * 32);
           }
+          if (p.epilogue & BHSR_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          const int nvalid = p.cout_valid - cc * 32;  // >= 1 here; >= 32 means the whole slice
           if (nchw) {
             if (valid) {
               const size_t plane = static_cast<size_t>(p.oh) * p.ow;
               float* o = p.out_f32 + (static_cast<size_t>(n) * p.out_ctot + p.out_choff + cc * 32) *
                                          plane + static_cast<size_t>(oy) * p.ow + ox;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) o[j * plane] = v[j];
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) o[j * plane] = v[j];
+            }
+          } else if (p.epilogue & BHSR_EPI_SHUFFLE2) {
+            // nn.PixelShuffle(2) scatter (SR/HRfuse.py:24): conv channel 4c'+2i+j of pixel (y,x)
+            // becomes channel c' of pixel (2y+i, 2x+j).  This 32-channel slice holds 8 consecutive c'
+            // for each of the four sub-pixels: one 16-byte store per sub-pixel and plane.
+            if (valid) {
+#pragma unroll
+              for (int sub = 0; sub < 4; ++sub) {
+                __align__(16) __half hh[8];
+                __align__(16) __half ll[8];
+#pragma unroll
+                for (int k8 = 0; k8 < 8; ++k8) split_hi_lo(v[4 * k8 + sub], hh[k8], ll[k8]);
+                const size_t opix = (static_cast<size_t>(n) * p.oh + 2 * py + (sub >> 1)) * p.ow + 2 * px + (sub & 1);
+                const size_t off = opix * p.out_ctot + p.out_choff + cc * 8;
+                *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hh);
+                if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(ll);
+              }
             }
           } else {
             // Store transpose: a lane owns one pixel (64 B of this 32-channel slice).  Written
@@ -478,7 +508,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 const int src = 8 * j4 + (lane >> 2);
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + src * 80 + (lane & 3) * 16);
                 const uint32_t pp = __shfl_sync(0xffffffffu, pix32, src);
-                if (pp != 0xFFFFFFFFu) {
+                if (pp != 0xFFFFFFFFu && (lane & 3) * 8 < nvalid) {
                   __half* o = dst_plane + static_cast<size_t>(pp) * p.out_ctot + p.out_choff + cc * 32 +
                               (lane & 3) * 8;
                   *reinterpret_cast<uint4*>(o) = val;
@@ -506,7 +536,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 static long long* g_dbg_buf = nullptr;
 
 static constexpr int kStageBytes = 4 * 32 * 80;  // epilogue store-transpose staging
-static constexpr int kTailBytes = (2 * kMaxAStages + 4 + 2 * kMaxWSlots) * 8 + 16 + 64 * 4 + 64 + kStageBytes;
+static constexpr int kTailBytes = (2 * kMaxAStages + 4 + 2 * kMaxWSlots) * 8 + 16 + 2 * 64 * 4 + 64 + kStageBytes;
 
 static int make_act_map(CUtensorMap* tm, const void* base, int nb, int h, int w, int ctot,
                         int box_rows, int ch) {
@@ -659,7 +689,13 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BHSR_REQUIRE(d.cout == 32 || d.cout == 64, "conv_tc: cout must be 32 or 64 (got %d)", d.cout);
   BHSR_REQUIRE(d.w > 0 && d.h > 0 && d.nb > 0, "conv_tc: empty input");
-  BHSR_REQUIRE(d.cin > 0 && d.cin % 32 == 0, "conv_tc: cin must be a multiple of 32 (got %d)", d.cin);
+  BHSR_REQUIRE(d.cin > 0 && d.cin % (d.numerics == BHSR_NUMERICS_EXACT_F16X3 ? 16 : 32) == 0,
+               "conv_tc: cin must be a multiple of 16 (exact) / 32 (fast), got %d", d.cin);
+  BHSR_REQUIRE(d.cout_valid >= 0 && d.cout_valid <= d.cout, "conv_tc: cout_valid out of range");
+  if (d.epilogue & BHSR_EPI_SHUFFLE2)
+    BHSR_REQUIRE(!(d.epilogue & BHSR_EPI_OUT_NCHW_F32) && d.out_scale == 1 && d.oh >= 2 * d.h && d.ow >= 2 * d.w &&
+                     (d.cout_valid == 0 || d.cout_valid % 32 == 0),
+                 "conv_tc: pixel-shuffle epilogue needs plane output of twice the size and whole 32-channel slices");
   const bool exact_ = d.numerics == BHSR_NUMERICS_EXACT_F16X3;
   const int ch_ = exact_ ? 32 : 64;
   BHSR_REQUIRE(d.in_ctot % ch_ == 0 && d.in_choff % ch_ == 0 &&
@@ -674,8 +710,8 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   BHSR_REQUIRE(!exact || d.in_lo, "conv_tc: exact numerics needs the lo plane");
   const bool nchw = (d.epilogue & BHSR_EPI_OUT_NCHW_F32) != 0;
   BHSR_REQUIRE(nchw ? d.out_f32 != nullptr : d.out_hi != nullptr, "conv_tc: null output");
-  BHSR_REQUIRE(nchw || (d.out_ctot % 8 == 0 && d.out_choff % 8 == 0),
-               "conv_tc: output channel offset/stride must be multiples of 8");
+  BHSR_REQUIRE(nchw || (d.out_ctot % 8 == 0 && d.out_choff % 8 == 0 && (d.cout_valid % 8 == 0)),
+               "conv_tc: output channel offset/stride/count must be multiples of 8");
   if (d.epilogue & BHSR_EPI_RES1)
     BHSR_REQUIRE(d.res1_hi && d.out_scale == 1 && d.res1_ctot % 8 == 0 && d.res1_choff % 8 == 0,
                  "conv_tc: bad res1");
@@ -710,6 +746,8 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   p.out_ctot = d.out_ctot; p.out_choff = d.out_choff;
   p.out_f32 = d.out_f32;
   p.bias = d.bias;
+  p.scale = d.scale;
+  p.cout_valid = d.cout_valid > 0 ? d.cout_valid : d.cout;
   p.epilogue = d.epilogue;
   p.alpha1 = d.alpha1; p.alpha2 = d.alpha2;
   p.res1_hi = static_cast<const __half*>(d.res1_hi);

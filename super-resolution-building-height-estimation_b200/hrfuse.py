@@ -12,13 +12,14 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Callable, Optional
 
 import torch
 from torch import Tensor, nn
 
-from . import _lib
-from ._lib import HeadConvDesc
+from . import _lib, ops
+from ._lib import NUMERICS_EXACT, HeadConvDesc
 
 
 # ------------------------------------------------------------------ kernel wrappers
@@ -297,6 +298,114 @@ class _BasicBlockFn(torch.autograd.Function):
         return tuple(grads) + (None,) * 6
 
 
+# ------------------------------------------------------------------ eval-mode tensor-core path
+# With BatchNorm in eval mode and no autograd graph to build (predict_realesanet_feature_globe.py,
+# vtest_epoch in train.py), conv + BN (+ReLU, +shortcut) is one conv with a per-channel
+# scale/shift epilogue: the head then runs on the same tcgen05 kernel as the RRDB trunk
+# (`exact` numerics), on NHWC hi/lo planes, with 16-channel outputs padded to the MMA's N = 32.
+TC_EVAL = os.environ.get("BHSR_HEAD_TC", "1") != "0"   # set False to keep eval on the fp32 CUDA-core kernels
+
+
+def _tc_eligible(module: nn.Module, *tensors) -> bool:
+    if not TC_EVAL or module.training or not all(t.is_cuda for t in tensors):
+        return False
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or
+                                    any(p.requires_grad for p in module.parameters())):
+        return False
+    return True
+
+
+def _planes(nb, h, w, c, dev):
+    return (torch.empty((nb, h, w, c), dtype=torch.float16, device=dev),
+            torch.empty((nb, h, w, c), dtype=torch.float16, device=dev))
+
+
+def _cache_get(module: nn.Module, build):
+    """Packed weights / folded BN vectors of `module`, rebuilt when any tensor changed."""
+    key = tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    cached = module.__dict__.get("_tc_cache")
+    if cached is None or cached[0] != key:
+        cached = (key, build())
+        module.__dict__["_tc_cache"] = cached
+    return cached[1]
+
+
+def _pad_cout(n: int) -> int:
+    if n > 64:
+        raise NotImplementedError("tensor-core head path supports at most 64 output channels")
+    return 32 if n <= 32 else 64
+
+
+def _pack3x3(w: Tensor, cout_pad: int) -> Tensor:
+    """OIHW (1x1 or 3x3) -> zero-padded [cout_pad, cin, 3, 3] -> packed blob (exact numerics)."""
+    w = w.detach().float()
+    if w.shape[2] == 1:
+        w = torch.nn.functional.pad(w, (1, 1, 1, 1))  # a 1x1 conv is the centre tap of a 3x3
+    full = torch.zeros((cout_pad, w.shape[1], 3, 3), dtype=torch.float32, device=w.device)
+    full[: w.shape[0]] = w
+    return ops.pack_conv_weights(full, NUMERICS_EXACT)
+
+
+def _padvec(v: Optional[Tensor], n: int, dev) -> Tensor:
+    out = torch.zeros(n, dtype=torch.float32, device=dev)
+    if v is not None:
+        out[: v.numel()] = v.detach().float()
+    return out
+
+
+def _bn_fold(bn: nn.BatchNorm2d, cout_pad: int):
+    s = _bn_eval(_BNParams(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, bn.momentum))
+    return _padvec(s.scale, cout_pad, s.scale.device), _padvec(s.shift, cout_pad, s.scale.device)
+
+
+def _basic_block_tc(blk: "BasicBlock", xin, cin: int):
+    """Eval-mode BasicBlock on planes: returns (hi, lo) planes whose first `planes` channels are valid."""
+    planes_out = blk.conv1.out_channels
+    cp = _pad_cout(planes_out)
+    if cin % 16 or planes_out % 16:
+        raise NotImplementedError("tensor-core head path needs channel counts that are multiples of 16")
+
+    def build():
+        dev = blk.conv1.weight.device
+        d = {"w1": _pack3x3(blk.conv1.weight, cp), "w2": _pack3x3(blk.conv2.weight, cp)}
+        d["s1"], d["t1"] = _bn_fold(blk.bn1, cp)
+        d["s2"], d["t2"] = _bn_fold(blk.bn2, cp)
+        if blk.downsample is not None:
+            d["wd"] = _pack3x3(blk.downsample[0].weight, cp)
+            d["sd"], d["td"] = _bn_fold(blk.downsample[1], cp)
+        return d
+
+    c = _cache_get(blk, build)
+    nb, h, w, _ = xin[0].shape
+    dev = xin[0].device
+    ctot = 32 if cp == 32 else 64
+    c1 = _planes(nb, h, w, ctot, dev)
+    ops.conv_tc(xin[0], xin[1], 0, cin, c["w1"], cp, c["t1"], ops.PLAIN_TAPS, c1[0], c1[1], scale=c["s1"],
+                cout_valid=planes_out, relu=True, numerics=NUMERICS_EXACT)
+    if blk.downsample is not None:
+        d = _planes(nb, h, w, ctot, dev)
+        ops.conv_tc(xin[0], xin[1], 0, cin, c["wd"], cp, c["td"], ops.PLAIN_TAPS, d[0], d[1], scale=c["sd"],
+                    cout_valid=planes_out, numerics=NUMERICS_EXACT)
+        res = (d[0], d[1], 0)
+    else:
+        if xin[0].shape[3] < cp:
+            raise NotImplementedError("identity shortcut needs an input plane at least as wide as the padded output")
+        res = (xin[0], xin[1], 0)
+    out = _planes(nb, h, w, ctot, dev)
+    ops.conv_tc(c1[0], c1[1], 0, planes_out, c["w2"], cp, c["t2"], ops.PLAIN_TAPS, out[0], out[1], scale=c["s2"],
+                cout_valid=planes_out, res1=res, alpha1=1.0, relu=True, numerics=NUMERICS_EXACT)
+    return out
+
+
+def _to_planes(x: Tensor, ctot: int, choff: int = 0, dst=None):
+    x = _prep(x)
+    nb, c, h, w = x.shape
+    if dst is None:
+        dst = _planes(nb, h, w, ctot, x.device)
+    ops.nchw_to_planes(x, dst[0], dst[1], choff)
+    return dst
+
+
 # ------------------------------------------------------------------ modules (reference surface)
 def default_conv(in_channels, out_channels, kernel_size, bias=True):
     """SR/HRfuse.py:11-14."""
@@ -417,6 +526,23 @@ class HRfeature(nn.Sequential):
                          BasicBlock(mid_chans, mid_chans, stride=1),
                          BasicBlock(mid_chans, out_chans, stride=1))
 
+    def _tc_supported(self):
+        blks = list(self)
+        return all(isinstance(b, BasicBlock) and b.stride == 1 and b.conv1.in_channels % 16 == 0 and
+                   b.conv1.out_channels % 16 == 0 and b.conv1.out_channels <= 64 and
+                   (b.downsample is not None or b.conv1.in_channels <= 32 or b.conv1.in_channels == 64)
+                   for b in blks)
+
+    def forward(self, x):
+        if _tc_eligible(self, x) and self._tc_supported() and x.shape[1] % 32 == 0:
+            cur = _to_planes(x, x.shape[1])
+            cin = x.shape[1]
+            for blk in self:
+                cur = _basic_block_tc(blk, cur, cin)
+                cin = blk.conv1.out_channels
+            return ops.planes_to_nchw(cur[0], cur[1], cin, 0)
+        return super().forward(x)
+
 
 class HRfuse_residual(nn.Module):
     """SR/HRfuse.py:173-190."""
@@ -429,7 +555,56 @@ class HRfuse_residual(nn.Module):
                                   BasicBlock(mid_chans, mid_chans, stride=1))
         self.conv_last = nn.Conv2d(mid_chans, out_chans, 3, 1, 1)
 
+    def _forward_tc(self, x_lr, x_hr):
+        """Eval path on planes: Upsampler convs scatter through PixelShuffle(2) straight into the
+        LR half of the 32-channel concat buffer, the HR features are laid beside them, the three
+        BasicBlocks and conv_last run on the tensor-core kernel."""
+        lr_c, hr_c = x_lr.shape[1], x_hr.shape[1]
+        nb, _, h, w = x_lr.shape
+        dev = x_lr.device
+        convs = [m for m in self.upsampler if isinstance(m, nn.Conv2d)]
+
+        def build():
+            return {"up": [(_pack3x3(m.weight, 64), _padvec(m.bias, 64, dev)) for m in convs],
+                    "last": (_pack3x3(self.conv_last.weight, 32), _padvec(self.conv_last.bias, 32, dev))}
+
+        c = self.__dict__.get("_tc_own")
+        key = tuple((t.data_ptr(), t._version) for t in [m.weight for m in convs] + [m.bias for m in convs] +
+                    [self.conv_last.weight, self.conv_last.bias])
+        if c is None or c[0] != key:
+            c = (key, build())
+            self.__dict__["_tc_own"] = c
+        c = c[1]
+        cur = _to_planes(x_lr, 32)
+        for i, (wp, b) in enumerate(c["up"]):
+            h, w = 2 * h, 2 * w
+            nxt = _planes(nb, h, w, 32, dev)
+            ops.conv_tc(cur[0], cur[1], 0, lr_c, wp, 64, b, ops.PLAIN_TAPS, nxt[0], nxt[1], out_choff=0,
+                        shuffle2=True, numerics=NUMERICS_EXACT)
+            cur = nxt
+        _to_planes(x_hr, 32, choff=lr_c, dst=cur)          # torch.cat([x_lr, x_hr], 1): LR first (:187)
+        cin = lr_c + hr_c
+        for blk in self.fuse:
+            cur = _basic_block_tc(blk, cur, cin)
+            cin = blk.conv1.out_channels
+        oc = self.conv_last.out_channels
+        out = torch.empty((nb, oc, h, w), dtype=torch.float32, device=dev)
+        wp, b = c["last"]
+        ops.conv_tc(cur[0], cur[1], 0, cin, wp, 32, b, ops.PLAIN_TAPS, None, None, out_f32=out, cout_valid=oc,
+                    numerics=NUMERICS_EXACT)
+        return out
+
+    def _tc_supported(self, x_lr, x_hr):
+        convs = [m for m in self.upsampler if isinstance(m, nn.Conv2d)]
+        shuffles = [m for m in self.upsampler if isinstance(m, nn.PixelShuffle)]
+        return (len(convs) == len(shuffles) == len(self.upsampler) // 2 and all(s.upscale_factor == 2 for s in shuffles)
+                and x_lr.shape[1] == 16 and x_hr.shape[1] == 16 and all(m.out_channels == 64 for m in convs)
+                and all(b.conv1.out_channels == 16 and b.stride == 1 for b in self.fuse)
+                and self.conv_last.out_channels <= 32)
+
     def forward(self, x_lr, x_hr):
+        if _tc_eligible(self, x_lr, x_hr) and self._tc_supported(x_lr, x_hr):
+            return self._forward_tc(x_lr, x_hr)
         x_lr = self.upsampler(x_lr)
         x = self.fuse(torch.cat([x_lr, x_hr], dim=1))  # LR first, as in the reference (:187)
         return conv2d(x, self.conv_last.weight, self.conv_last.bias)

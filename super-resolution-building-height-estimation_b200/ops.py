@@ -10,8 +10,8 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_LRELU, EPI_OUT_NCHW_F32, EPI_RES1, EPI_RES2, NUMERICS, NUMERICS_EXACT,
-                   NUMERICS_FAST, ConvTcDesc)
+from ._lib import (EPI_LRELU, EPI_OUT_NCHW_F32, EPI_RELU, EPI_RES1, EPI_RES2, EPI_SHUFFLE2, NUMERICS,
+                   NUMERICS_EXACT, NUMERICS_FAST, ConvTcDesc)
 
 PLAIN_TAPS: Tuple[Tuple[int, int], ...] = tuple((ky - 1, kx - 1) for ky in range(3) for kx in range(3))
 
@@ -64,7 +64,8 @@ def conv_tc(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: int, c
             res1: Optional[Tuple[torch.Tensor, Optional[torch.Tensor], int]] = None, alpha1: float = 1.0,
             res2: Optional[Tuple[torch.Tensor, Optional[torch.Tensor], int]] = None, alpha2: float = 1.0,
             numerics: int = NUMERICS_EXACT, mblocks: int = 0, max_ctas: int = 0,
-            desc_mode: int = 0) -> None:
+            desc_mode: int = 0, scale: Optional[torch.Tensor] = None, cout_valid: int = 0,
+            relu: bool = False, shuffle2: bool = False) -> None:
     """Enqueue one tensor-core convolution on the current stream (bhsr_conv_tc)."""
     _lib.require_cuda(in_hi, "in_hi")
     nb, h, w, ctot = in_hi.shape
@@ -76,6 +77,8 @@ def conv_tc(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: int, c
     d.w_packed = w_packed.data_ptr()
     d.cout = cout
     d.bias = _lib.ptr(bias)
+    d.scale = _lib.ptr(scale)
+    d.cout_valid = cout_valid
     d.ntaps = len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.dy[i] = dy
@@ -95,6 +98,10 @@ def conv_tc(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: int, c
     d.out_ctot, d.out_choff = octot, out_choff
     if lrelu:
         epi |= EPI_LRELU
+    if relu:
+        epi |= EPI_RELU
+    if shuffle2:
+        epi |= EPI_SHUFFLE2
     if res1 is not None:
         epi |= EPI_RES1
         d.res1_hi, d.res1_lo = res1[0].data_ptr(), _lib.ptr(res1[1])

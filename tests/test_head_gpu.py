@@ -77,6 +77,34 @@ def test_hrfeature_and_hrfuse_vs_golden(dev, golden, training):
         assert_close(y, golden[f"hrfuse_out{oc}_{tag}"], what=f"HRfuse_residual out={oc} {tag}")
 
 
+@pytest.mark.parametrize("shape", [(1, 5, 7), (3, 9, 20), (2, 33, 17)])
+def test_head_eval_tensor_core_vs_cuda_core_and_oracle(dev, shape, monkeypatch):
+    """Eval mode under no_grad runs the head on the tcgen05 conv (BN folded into the epilogue);
+    it must agree with the fp32 CUDA-core kernels and with the oracle on ragged sizes."""
+    from bhsr import hrfuse
+    nb, h, w = shape
+    oc = 7
+    sd = synth.hrfuse_residual_state(out=oc, seed=61)
+    sdf = synth.hrfeature_state(seed=62)
+    lr = synth.features(nb, 16, h, w, seed=3)
+    hr = synth.features(nb, 64, 4 * h, 4 * w, seed=4)
+    fuse = load_np_state(hrfuse.HRfuse_residual(16, 16, 16, oc, 4), sd, dev).eval()
+    feat = load_np_state(hrfuse.HRfeature(64, 16, 16), sdf, dev).eval()
+    outs = {}
+    for tc in (True, False):
+        monkeypatch.setattr(hrfuse, "TC_EVAL", tc)
+        with torch.no_grad():
+            f = feat(cuda(hr, dev))
+            outs[tc] = (f.cpu().numpy(), fuse(cuda(lr, dev), f).cpu().numpy())
+    pf = {k: torch.from_numpy(np.ascontiguousarray(v)).double() if v.dtype != np.int64 else torch.from_numpy(v) for k, v in sdf.items()}
+    pr = {k: torch.from_numpy(np.ascontiguousarray(v)).double() if v.dtype != np.int64 else torch.from_numpy(v) for k, v in sd.items()}
+    f_ref = T.hrfeature(torch.from_numpy(hr).double(), pf, training=False)
+    y_ref = T.hrfuse_residual(torch.from_numpy(lr).double(), f_ref, pr, training=False)
+    for tc in (True, False):
+        assert_close(outs[tc][0], f_ref.numpy(), what=f"HRfeature tc={tc}")
+        assert_close(outs[tc][1], y_ref.numpy(), what=f"HRfuse_residual tc={tc}")
+
+
 def _grad_reference(sd, lr, hr16, training, oc):
     """torch autograd through the torch-functional oracle on CPU (fp64 for a clean reference)."""
     p = {k: torch.from_numpy(np.ascontiguousarray(v)).double().requires_grad_(v.dtype == np.float32 and "running" not in k)
