@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbhsr.so")
+# BHSR_LIB selects another build of the same library (e.g. the -DBHSR_TIMING profiling build)
+LIB_PATH = os.environ.get("BHSR_LIB") or os.path.join(_HERE, "lib", "libbhsr.so")
 
 NUMERICS_EXACT = 0  # BHSR_NUMERICS_EXACT_F16X3
 NUMERICS_FAST = 1   # BHSR_NUMERICS_FAST_F16

@@ -22,8 +22,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, timing: bool = False) -> str:
+    """timing=True builds lib/libbhsr_timing.so with the in-kernel cycle counters (-DBHSR_TIMING);
+    select it at run time with BHSR_LIB=<path> BHSR_DEBUG_TIMING=1 (profiling only)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if timing:
+        out = LIB.replace("libbhsr.so", "libbhsr_timing.so")
+        cmd = [os.environ.get("NVCC", "nvcc")] + FLAGS + ["-DBHSR_TIMING", "-o", out] + srcs
+        print("[bhsr build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        return out
     if not force and not needs_build():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -35,4 +43,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv, timing="--timing" in sys.argv)

@@ -73,6 +73,7 @@ struct ConvTcKernelParams {
   int astages;       // activation ring depth (2..kMaxAStages)
   int pdl;           // launched with programmatic stream serialization
   int desc_mode;
+  int nomma;         // BHSR_TIMING builds only: skip the MMAs (measures the TMA supply rate alone)
   long long* dbg;  // optional [grid][8] cycle counters of the MMA warp (BHSR_DEBUG_TIMING)
 };
 
@@ -126,6 +127,99 @@ __device__ __forceinline__ void add_residual32(float (&v)[32], float alpha, cons
   }
 }
 
+// Everything after the accumulator read for ONE 32-channel slice `cc` of one output pixel per
+// lane: scale/bias, LeakyReLU, residuals, ReLU, then the store (fp32 NCHW, PixelShuffle scatter,
+// or hi/lo NHWC planes through the per-warp store-transpose staging buffer).  Shared by the
+// per-tap kernel and the dx-in-N kernel below.
+__device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, float (&v)[32], int cc,
+                                               bool valid, int n, int py, int px, size_t in_pix,
+                                               size_t out_pix, int oy, int ox, int warp, int lane,
+                                               bool nchw, uint8_t* s_stage, const float* s_bias,
+                                               const float* s_scale) {
+  if (cc * 32 >= p.cout_valid) return;  // padded output channels: nothing to store (uniform)
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[cc * 32 + j], s_bias[cc * 32 + j]);
+  if (p.epilogue & BHSR_EPI_LRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
+  }
+  if (valid) {
+    if (p.epilogue & BHSR_EPI_RES1)
+      add_residual32(v, p.alpha1, p.res1_hi, p.res1_lo,
+                     in_pix * p.res1_ctot + p.res1_choff + cc * 32);
+    if (p.epilogue & BHSR_EPI_RES2)
+      add_residual32(v, p.alpha2, p.res2_hi, p.res2_lo,
+                     in_pix * p.res2_ctot + p.res2_choff + cc * 32);
+  }
+  if (p.epilogue & BHSR_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  const int nvalid = p.cout_valid - cc * 32;  // >= 1 here; >= 32 means the whole slice
+  if (nchw) {
+    if (valid) {
+      const size_t plane = static_cast<size_t>(p.oh) * p.ow;
+      float* o = p.out_f32 + (static_cast<size_t>(n) * p.out_ctot + p.out_choff + cc * 32) *
+                                 plane + static_cast<size_t>(oy) * p.ow + ox;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) o[j * plane] = v[j];
+    }
+  } else if (p.epilogue & BHSR_EPI_SHUFFLE2) {
+    // nn.PixelShuffle(2) scatter (SR/HRfuse.py:24): conv channel 4c'+2i+j of pixel (y,x)
+    // becomes channel c' of pixel (2y+i, 2x+j).  This 32-channel slice holds 8 consecutive c'
+    // for each of the four sub-pixels: one 16-byte store per sub-pixel and plane.
+    if (valid) {
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        __align__(16) __half hh[8];
+        __align__(16) __half ll[8];
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) split_hi_lo(v[4 * k8 + sub], hh[k8], ll[k8]);
+        const size_t opix = (static_cast<size_t>(n) * p.oh + 2 * py + (sub >> 1)) * p.ow + 2 * px + (sub & 1);
+        const size_t off = opix * p.out_ctot + p.out_choff + cc * 8;
+        *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hh);
+        if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(ll);
+      }
+    }
+  } else {
+    // Store transpose: a lane owns one pixel (64 B of this 32-channel slice).  Written
+    // directly, every 16-byte store instruction would touch 32 different lines; staged
+    // through shared memory, a store instruction covers 8 pixels x 64 B (8 lines).
+    uint8_t* stg = s_stage + warp * (32 * 80);
+    const uint32_t pix32 = valid ? static_cast<uint32_t>(out_pix) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      __half* dst_plane = part == 0 ? p.out_hi : p.out_lo;
+      if (dst_plane == nullptr) break;  // warp-uniform
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        __align__(16) __half hh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x = v[g * 8 + j];
+          const __half hi = __float2half_rn(x);
+          hh[j] = part == 0 ? hi : __float2half_rn((x - __half2float(hi)) * 2048.f);
+        }
+        *reinterpret_cast<uint4*>(stg + lane * 80 + g * 16) = *reinterpret_cast<const uint4*>(hh);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int src = 8 * j4 + (lane >> 2);
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + src * 80 + (lane & 3) * 16);
+        const uint32_t pp = __shfl_sync(0xffffffffu, pix32, src);
+        if (pp != 0xFFFFFFFFu && (lane & 3) * 8 < nvalid) {
+          __half* o = dst_plane + static_cast<size_t>(pp) * p.out_ctot + p.out_choff + cc * 32 +
+                      (lane & 3) * 8;
+          *reinterpret_cast<uint4*>(o) = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // WMODE: how the weights reach shared memory — 0: streamed, one window row (KS taps) per ring
 // slot; 1: streamed, a whole window (KS*KS taps) per slot; 2: resident (loaded once per CTA).
 template <int N, bool EXACT, int MB, int KS, int WMODE>
@@ -176,6 +270,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef BHSR_TIMING
+  const long long t_entry = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxAStages; ++i) {
@@ -271,6 +368,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #ifdef BHSR_TIMING
     long long t_tempty = 0, t_afull = 0, t_wfull = 0, t_total = clock64(), tq = 0;
     const bool dbg = p.dbg != nullptr;
+    const long long t_loop0 = t_total;
 #else
     long long t_tempty = 0, t_afull = 0, t_wfull = 0, tq = 0;
     constexpr bool dbg = false;
@@ -359,6 +457,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 const uint32_t pbar = slot == 0 ? bar_w_next : (slot == 1 ? bar_a_next : bar_t_next);
                 const uint32_t ppar = slot == 0 ? par_w_next
                                                 : (slot == 1 ? static_cast<uint32_t>(a_ph_next) : par_t_next);
+#ifdef BHSR_TIMING
+                if (p.nomma) { if (tt < 3) okbits |= static_cast<uint32_t>(mbar_try_wait(pbar, ppar)) << tt; continue; }
+#endif
                 const uint32_t ok = issue_tap<EXACT, MB, KST, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N>(
                     a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, tt > 0 ? 1u : accumulate, pbar, ppar);
                 if (tt < 3) okbits |= ok << tt;
@@ -388,6 +489,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (dbg && lane == 0) {
       long long* o = p.dbg + blockIdx.x * 8;
       o[0] = clock64() - t_total; o[1] = t_tempty; o[2] = t_afull; o[3] = t_wfull; o[4] = tile_it;
+      o[5] = t_loop0 - t_entry;   // prologue: barrier init, TMEM alloc, PDL wait
     }
 #endif
     (void)t_tempty; (void)t_afull; (void)t_wfull; (void)tq;
@@ -397,13 +499,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     const int row = q * 32 + lane;
     uint32_t tile_it = 0;
     const bool nchw = (p.epilogue & BHSR_EPI_OUT_NCHW_F32) != 0;
+#ifdef BHSR_TIMING
+    long long t_epi_wait = 0;
+#endif
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int sn = tile / p.tiles_per_strip;
       const int s = sn % p.n_strips;
       const int n = sn / p.n_strips;
       const int as = tile_it & 1;
+#ifdef BHSR_TIMING
+      const long long tw0 = clock64();
+#endif
       mbar_wait(bar(B_TFULL + as), (tile_it >> 1) & 1);
+#ifdef BHSR_TIMING
+      t_epi_wait += clock64() - tw0;
+#endif
       tc_fence_after();
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
@@ -435,98 +546,415 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           }
-          if (cc * 32 >= p.cout_valid) continue;  // padded output channels: nothing to store (uniform)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[cc * 32 + j], s_bias[cc * 32 + j]);
-          if (p.epilogue & BHSR_EPI_LRELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
-          }
-          if (valid) {
-            if (p.epilogue & BHSR_EPI_RES1)
-              add_residual32(v, p.alpha1, p.res1_hi, p.res1_lo,
-                             in_pix * p.res1_ctot + p.res1_choff + cc * 32);
-            if (p.epilogue & BHSR_EPI_RES2)
-              add_residual32(v, p.alpha2, p.res2_hi, p.res2_lo,
-                             in_pix * p.res2_ctot + p.res2_choff + cc * 32);
-          }
-          if (p.epilogue & BHSR_EPI_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          const int nvalid = p.cout_valid - cc * 32;  // >= 1 here; >= 32 means the whole slice
-          if (nchw) {
-            if (valid) {
-              const size_t plane = static_cast<size_t>(p.oh) * p.ow;
-              float* o = p.out_f32 + (static_cast<size_t>(n) * p.out_ctot + p.out_choff + cc * 32) *
-                                         plane + static_cast<size_t>(oy) * p.ow + ox;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) o[j * plane] = v[j];
-            }
-          } else if (p.epilogue & BHSR_EPI_SHUFFLE2) {
-            // nn.PixelShuffle(2) scatter (SR/HRfuse.py:24): conv channel 4c'+2i+j of pixel (y,x)
-            // becomes channel c' of pixel (2y+i, 2x+j).  This 32-channel slice holds 8 consecutive c'
-            // for each of the four sub-pixels: one 16-byte store per sub-pixel and plane.
-            if (valid) {
-#pragma unroll
-              for (int sub = 0; sub < 4; ++sub) {
-                __align__(16) __half hh[8];
-                __align__(16) __half ll[8];
-#pragma unroll
-                for (int k8 = 0; k8 < 8; ++k8) split_hi_lo(v[4 * k8 + sub], hh[k8], ll[k8]);
-                const size_t opix = (static_cast<size_t>(n) * p.oh + 2 * py + (sub >> 1)) * p.ow + 2 * px + (sub & 1);
-                const size_t off = opix * p.out_ctot + p.out_choff + cc * 8;
-                *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hh);
-                if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(ll);
-              }
-            }
-          } else {
-            // Store transpose: a lane owns one pixel (64 B of this 32-channel slice).  Written
-            // directly, every 16-byte store instruction would touch 32 different lines; staged
-            // through shared memory, a store instruction covers 8 pixels x 64 B (8 lines).
-            uint8_t* stg = s_stage + warp * (32 * 80);
-            const uint32_t pix32 = valid ? static_cast<uint32_t>(out_pix) : 0xFFFFFFFFu;
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
-              __half* dst_plane = part == 0 ? p.out_hi : p.out_lo;
-              if (dst_plane == nullptr) break;  // warp-uniform
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                __align__(16) __half hh[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float x = v[g * 8 + j];
-                  const __half hi = __float2half_rn(x);
-                  hh[j] = part == 0 ? hi : __float2half_rn((x - __half2float(hi)) * 2048.f);
-                }
-                *reinterpret_cast<uint4*>(stg + lane * 80 + g * 16) = *reinterpret_cast<const uint4*>(hh);
-              }
-              __syncwarp();
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const int src = 8 * j4 + (lane >> 2);
-                const uint4 val = *reinterpret_cast<const uint4*>(stg + src * 80 + (lane & 3) * 16);
-                const uint32_t pp = __shfl_sync(0xffffffffu, pix32, src);
-                if (pp != 0xFFFFFFFFu && (lane & 3) * 8 < nvalid) {
-                  __half* o = dst_plane + static_cast<size_t>(pp) * p.out_ctot + p.out_choff + cc * 32 +
-                              (lane & 3) * 8;
-                  *reinterpret_cast<uint4*>(o) = val;
-                }
-              }
-              __syncwarp();
-            }
-          }
+          finish_slice32(p, v, cc, valid, n, py, px, in_pix, out_pix, oy, ox, warp, lane, nchw, s_stage,
+                         s_bias, s_scale);
         }
       }
       tc_fence_before();
       mbar_arrive(bar(B_TEMPTY + as));
     }
+#ifdef BHSR_TIMING
+    if (p.dbg != nullptr && threadIdx.x == 0) {
+      long long* o = p.dbg + blockIdx.x * 8;
+      o[6] = t_epi_wait;            // epilogue warp 0: cycles waiting for a full accumulator
+      o[7] = clock64() - t_entry;   // kernel entry -> last epilogue done
+    }
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == kWarpMma) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ======================================================================================
+// conv_dx_kernel — "dx-in-N" variant of the tap conv for the 32-output-channel 3x3 layers
+// (conv1..conv4 of every ResidualDenseBlock, SR/rrdbnet_arch.py:137-140).
+//
+// With N = 32 an M=128 MMA spends 32 of its 40 cycles re-reading the 128-row activation operand
+// from shared memory (profiles/r01_mma_microbench_tight.log) and, measured in the real kernel,
+// ~15 more cycles of fixed per-instruction cost.  Here the three dx taps of one window row share
+// ONE activation read: the weight tiles of (dy,-1), (dy,0), (dy,+1) are stacked along N
+// (N = 96; exact numerics: hi rows then lo' rows, N = 192 for the hi activations and N = 96 for
+// the lo' activations), the MMA's A operand is the halo tile shifted by dy*66 only, and
+//     D[r][g*32 + n] = sum_{dy,c} X[row r + dy*66][c] * W[dy][dx = g-1][n][c].
+// The conv output of flat pixel r is D[r-1][g=0] + D[r][g=1] + D[r+1][g=2]: the epilogue combines
+// three column groups with a one-lane shift (warp shuffles + a 2-row exchange between the four
+// warps of a TMEM lane quarter set).  Rows 0 and 127 of every 128-row block have no neighbour
+// and are recomputed by the adjacent block: blocks advance by 126 flat pixels.
+// 9 (18 exact) narrow MMAs per k-step become 3 (6) wide ones.
+//
+// Warp roles (352 threads): warps 0..3 / 4..7 = two epilogue groups (accumulator blocks
+// alternate between them; each drains its TMEM block to registers and releases it at once),
+// warp 8 = activation TMA producer, warp 9 = weight TMA producer, warp 10 = MMA issuer.
+// The packed weight blob is the same as the per-tap kernel's: a 5-D tensor map reorders
+// [tap][part][cout] to [part][dx][cout] on the way into shared memory.
+constexpr int kDxThreads = 352;
+constexpr int kDxWarpProdA = 8, kDxWarpProdW = 9, kDxWarpMma = 10;
+constexpr int kDxStageBytes = 8 * 32 * 80;          // store-transpose staging, 8 epilogue warps
+constexpr int kDxXchgFloats = 2 * 2 * 4 * 64;       // [group][parity][warp][v0 of lane 31 | v2 of lane 0]
+constexpr int kDxTailBytes = (2 * kMaxAStages + 8 + 2 * kMaxWSlots) * 8 + 16 + 2 * 64 * 4 + 64 +
+                             kDxStageBytes + kDxXchgFloats * 4;
+
+template <bool EXACT, int MB, bool WRES>
+__global__ void __launch_bounds__(kDxThreads, 1)
+conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+               const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_w, const ConvTcKernelParams p) {
+  constexpr int CH = EXACT ? 32 : 64;
+  using G = TileGeom<MB, CH>;
+  constexpr int RB = G::kRowBytes;
+  constexpr int RB16 = RB / 16;
+  constexpr int KSTEPS = CH / 16;
+  constexpr int NPART = EXACT ? 2 : 1;
+  constexpr int COLS = 96 * NPART;                 // weight rows per window row = TMEM columns per block
+  constexpr int W_SLAB = COLS * RB;                // one (chunk, dy) weight slab: 12288 B either way
+  constexpr int A_STAGE = G::kTileBytes * NPART;
+  constexpr int A_TX = G::kTileBytesRaw * NPART;
+  constexpr int NSLOT = EXACT ? 2 : 4;             // accumulator blocks in TMEM (192 / 96 columns each)
+  constexpr int S_BLK = 126;                       // valid output rows per 128-row block
+  constexpr int S_OUT = S_BLK * MB;
+  static_assert(NSLOT * COLS <= 512, "TMEM overflow");
+  constexpr uint32_t IDESC_WIDE = make_idesc_f16(COLS);
+  constexpr uint32_t IDESC_N = make_idesc_f16(96);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_base = smem_base;
+  const int NS = p.astages;
+  const uint32_t w_base = a_base + NS * A_STAGE;
+  uint8_t* tail = smem + NS * A_STAGE + p.wslots * W_SLAB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  auto bar = [&](int i) { return smem_u32(bars + i); };
+  constexpr int B_AFULL = 0, B_AEMPTY = kMaxAStages, B_TFULL = 2 * kMaxAStages,
+                B_TEMPTY = B_TFULL + 4, B_WFULL = B_TFULL + 8;
+  const int B_WEMPTY = B_WFULL + kMaxWSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_WFULL + 2 * kMaxWSlots);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_scale = s_bias + 64;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_scale + 64);
+  float* s_xchg = reinterpret_cast<float*>(s_stage + kDxStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+#ifdef BHSR_TIMING
+  const long long t_entry = clock64();
+#endif
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxAStages; ++i) {
+      mbar_init(bar(B_AFULL + i), 1);
+      mbar_init(bar(B_AEMPTY + i), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(B_TFULL + i), 1);
+      mbar_init(bar(B_TEMPTY + i), 128);
+    }
+    for (int i = 0; i < p.wslots; ++i) {
+      mbar_init(bar(B_WFULL + i), 1);
+      mbar_init(bar(B_WEMPTY + i), 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_a_hi);
+    if (EXACT) tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (threadIdx.x < 32) {
+    s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+  }
+  if (warp == kDxWarpMma) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (p.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp != kDxWarpProdW) asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+
+  const int first_tile = blockIdx.x;
+  const int tile_step = gridDim.x;
+
+  if (warp == kDxWarpProdA) {
+    // ------------------------------------------------ activation producer
+    if (lane == 0) {
+      int st = 0, ph = 1;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const int t = tile % p.tiles_per_strip;
+        const int sn = tile / p.tiles_per_strip;
+        const int s = sn % p.n_strips;
+        const int n = sn / p.n_strips;
+        // block 0 row 0 is flat output t*S_OUT - 1; its dy = -1 operand row starts one image row up
+        const int r0 = (t * S_OUT + kPitch - 1) / kPitch - 2;
+        for (int c = 0; c < p.n_chunks; ++c, st = (st + 1 == NS ? 0 : st + 1), ph ^= (st == 0)) {
+          mbar_wait(bar(B_AEMPTY + st), ph);
+          mbar_expect_tx(bar(B_AFULL + st), A_TX);
+          const uint32_t dst = a_base + st * A_STAGE;
+          tma_load_4d(dst, &tm_a_hi, bar(B_AFULL + st), p.in_choff + c * CH, s * kStrip - 1, r0, n);
+          if (EXACT)
+            tma_load_4d(dst + G::kTileBytes, &tm_a_lo, bar(B_AFULL + st), p.in_choff + c * CH,
+                        s * kStrip - 1, r0, n);
+        }
+      }
+    }
+  } else if (warp == kDxWarpProdW) {
+    // ------------------------------------------------ weight producer (one slab per (chunk, dy))
+    if (lane == 0) {
+      uint32_t it = 0;
+      const int slabs = p.n_chunks * 3;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        for (int sl = 0; sl < slabs; ++sl, ++it) {
+          const int ws = WRES ? sl : static_cast<int>(it % p.wslots);
+          if (!WRES) mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
+          mbar_expect_tx(bar(B_WFULL + ws), W_SLAB);
+          tma_load_5d(w_base + ws * W_SLAB, &tm_w, bar(B_WFULL + ws), 0, 0, 0, 0, sl);
+        }
+        if (WRES) break;
+      }
+    }
+  } else if (warp == kDxWarpMma) {
+    // ------------------------------------------------ MMA issuer
+    const uint64_t desc0 = make_kmajor_desc<RB>(0);
+    const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+    const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
+    uint32_t tile_it = 0;
+#ifdef BHSR_TIMING
+    long long t_tempty = 0, t_afull = 0, t_wfull = 0, t_total = clock64(), tq = 0;
+    const bool dbg = p.dbg != nullptr;
+    const long long t_loop0 = t_total;
+#else
+    long long t_tempty = 0, t_afull = 0, t_wfull = 0, tq = 0;
+    constexpr bool dbg = false;
+#endif
+    uint32_t ok_a = 0, ok_w = 0;
+    const int my_tiles = (p.total_tiles - first_tile + tile_step - 1) / tile_step;
+    const int n_chunks = p.n_chunks, cin = p.cin, wslots = p.wslots;
+    int st = 0, a_ph = 0;
+    int ws_r = 0, w_ph = 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+      const int t = tile % p.tiles_per_strip;
+      const int f0 = t * S_OUT;
+      const int r0 = (f0 + kPitch - 1) / kPitch - 2;
+      const int base_flat = f0 - r0 * kPitch;     // 67..132: tile-relative flat row of block 0, dy = 0
+      const bool more_tiles = tile_it + 1 < static_cast<uint32_t>(my_tiles);
+      for (int c = 0; c < n_chunks; ++c) {
+        if (!ok_a) {
+          if (dbg) tq = clock64();
+          mbar_wait(bar(B_AFULL + st), a_ph);
+          if (dbg) t_afull += clock64() - tq;
+        }
+        ok_a = 0;
+        tc_fence_after();
+        int st_next = st + 1, a_ph_next = a_ph;
+        if (st_next == NS) { st_next = 0; a_ph_next ^= 1; }
+        const uint32_t bar_a_next = bar(B_AFULL + st_next);
+        // descriptor low word of (block 0, dy = -1, k-step 0) of this stage
+        const uint32_t a_lo0 =
+            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (base_flat - kPitch) * RB16;
+        const int rem = cin - c * CH;
+        const bool last_chunk = (c + 1 == n_chunks);
+        auto issue_chunk = [&](auto ksteps_tag) {
+          constexpr int KST = decltype(ksteps_tag)::value;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {            // window row dy = g - 1
+            int ws;
+            uint32_t bar_w_next = bar_a_next, par_w_next = a_ph_next;
+            if (WRES) {
+              ws = c * 3 + g;
+              if (tile_it == 0) {
+                mbar_wait(bar(B_WFULL + ws), 0);
+                tc_fence_after();
+              }
+            } else {
+              ws = ws_r;
+              if (!ok_w) {
+                if (dbg) tq = clock64();
+                mbar_wait(bar(B_WFULL + ws), w_ph);
+                if (dbg) t_wfull += clock64() - tq;
+              }
+              ok_w = 0;
+              tc_fence_after();
+              if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }
+              bar_w_next = bar(B_WFULL + ws_r);
+              par_w_next = w_ph;
+            }
+            const uint32_t b_lo = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
+            uint32_t okbits = 0;
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint32_t blk = tile_it * MB + mb;
+              const uint32_t slot = blk % NSLOT;
+              if (c == 0 && g == 0) {              // first MMA into this accumulator block
+                if (dbg) tq = clock64();
+                mbar_wait(bar(B_TEMPTY + slot), ((blk / NSLOT) & 1) ^ 1);
+                if (dbg) t_tempty += clock64() - tq;
+                tc_fence_after();
+              }
+              const uint32_t acc = tmem_base + slot * COLS;
+              const uint32_t a_lo = a_lo0 + (g * kPitch + mb * S_BLK) * RB16;
+              // probe slot: block 0 tests the next weight slab, the last block the next activation stage
+              const bool probe_w = (mb == 0) && !WRES;
+              const uint32_t pbar = probe_w ? bar_w_next : bar_a_next;
+              const uint32_t ppar = probe_w ? par_w_next : static_cast<uint32_t>(a_ph_next);
+              if (elect_one()) {
+#ifdef BHSR_TIMING
+                if (!p.nomma)
+#endif
+                {
+                  const uint32_t ok = issue_tap<EXACT, 1, KST, 128 * RB16, (G::kTileBytes >> 4), COLS, 96>(
+                      a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, (c > 0 || g > 0) ? 1u : 0u, pbar, ppar);
+                  okbits |= ok << (probe_w ? 0 : 1);
+                }
+                if (last_chunk && g == 2) umma_commit(bar(B_TFULL + slot));
+                if (mb == MB - 1 && !WRES) umma_commit(bar(B_WEMPTY + ws));
+              }
+              __syncwarp();
+            }
+            okbits = __reduce_or_sync(0xffffffffu, okbits);
+            if (!WRES) ok_w = okbits & 1u;
+            if (g == 2 && (!last_chunk || more_tiles)) ok_a = (okbits >> 1) & 1u;
+          }
+        };
+        if (rem >= CH) issue_chunk(std::integral_constant<int, KSTEPS>{});
+        else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
+        if (elect_one()) umma_commit(bar(B_AEMPTY + st));
+        __syncwarp();
+        st = st_next;
+        a_ph = a_ph_next;
+      }
+    }
+#ifdef BHSR_TIMING
+    if (dbg && lane == 0) {
+      long long* o = p.dbg + blockIdx.x * 8;
+      o[0] = clock64() - t_total; o[1] = t_tempty; o[2] = t_afull; o[3] = t_wfull; o[4] = tile_it;
+      o[5] = t_loop0 - t_entry;
+    }
+#endif
+    (void)t_tempty; (void)t_afull; (void)t_wfull; (void)tq;
+  } else {
+    // ------------------------------------------------ epilogue (two groups of four warps)
+    const int grp = warp >> 2;
+    const int q = warp & 3;                          // TMEM lane quarter (warp id % 4)
+    const int row = q * 32 + lane;
+    uint32_t tile_it = 0;
+    uint32_t xpar = 0;
+#ifdef BHSR_TIMING
+    long long t_epi_wait = 0;
+#endif
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+      const int t = tile % p.tiles_per_strip;
+      const int sn = tile / p.tiles_per_strip;
+      const int s = sn % p.n_strips;
+      const int n = sn / p.n_strips;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const uint32_t blk = tile_it * MB + mb;
+        if (static_cast<int>(blk & 1u) != grp) continue;   // warp-uniform
+        const uint32_t slot = blk % NSLOT;
+#ifdef BHSR_TIMING
+        const long long tw0 = clock64();
+#endif
+        mbar_wait(bar(B_TFULL + slot), (blk / NSLOT) & 1);
+#ifdef BHSR_TIMING
+        t_epi_wait += clock64() - tw0;
+#endif
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * COLS;
+        // drain the three dx groups (main + 2^-11 * correction) and free the block at once
+        float v0[32], v1[32], v2[32];
+        auto drain = [&](uint32_t col, float (&dst)[32]) {
+          uint32_t raw[32];
+          tmem_ld_32x32(t_row + col, raw);
+          if (EXACT) {
+            uint32_t rawl[32];
+            tmem_ld_32x32(t_row + 96 + col, rawl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              dst[j] = fmaf(__uint_as_float(rawl[j]), 1.f / 2048.f, __uint_as_float(raw[j]));
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(raw[j]);
+          }
+        };
+        drain(0, v0);
+        drain(32, v1);
+        drain(64, v2);
+        tc_fence_before();
+        mbar_arrive(bar(B_TEMPTY + slot));
+        // out[row] = g0[row-1] + g1[row] + g2[row+1]: lane shifts inside the warp, smem across warps
+        float* xb = s_xchg + ((grp * 2 + xpar) * 4) * 64;
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(xb + q * 64 + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(xb + q * 64 + 32 + j) = make_float4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
+        }
+        if (grp == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
+        xpar ^= 1;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float up = __shfl_up_sync(0xffffffffu, v0[j], 1);
+          const float dn = __shfl_down_sync(0xffffffffu, v2[j], 1);
+          v0[j] = up;
+          v2[j] = dn;
+        }
+        if (lane == 0 && q > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xb + (q - 1) * 64 + j);
+            v0[j] = x.x; v0[j + 1] = x.y; v0[j + 2] = x.z; v0[j + 3] = x.w;
+          }
+        }
+        if (lane == 31 && q < 3) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xb + (q + 1) * 64 + 32 + j);
+            v2[j] = x.x; v2[j + 1] = x.y; v2[j + 2] = x.z; v2[j + 3] = x.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (v0[j] + v1[j]) + v2[j];
+
+        const int f = t * S_OUT - 1 + mb * S_BLK + row;
+        const int py = f / kPitch;
+        const int pc = f - py * kPitch;
+        const int px = s * kStrip + pc;
+        const bool valid = (row >= 1) && (row <= S_BLK) && (pc < kStrip) && (py < p.h) && (px < p.w);
+        const size_t in_pix = (static_cast<size_t>(n) * p.h + py) * p.w + px;
+        const int oy = py * p.out_scale + p.out_oy;
+        const int ox = px * p.out_scale + p.out_ox;
+        const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
+        finish_slice32(p, v, 0, valid, n, py, px, in_pix, out_pix, oy, ox, warp, lane, false, s_stage,
+                       s_bias, s_scale);
+      }
+    }
+#ifdef BHSR_TIMING
+    if (p.dbg != nullptr && threadIdx.x == 0) {
+      long long* o = p.dbg + blockIdx.x * 8;
+      o[6] = t_epi_wait;
+      o[7] = clock64() - t_entry;
+    }
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kDxWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -616,6 +1044,13 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
     if (slots_for(ns) >= slabs) { astages = ns; wslots = slots_for(ns); picked = true; }
   for (int ns = kMaxAStages; ns >= 2 && !picked; --ns)   // 2nd: a ring of at least 4 slabs
     if (slots_for(ns) >= 4) { astages = ns; wslots = slots_for(ns); picked = true; }
+  {
+    static const char* force_ns = getenv("BHSR_ASTAGES");  // debug knob: fixed activation ring depth
+    if (force_ns && force_ns[0] >= '2' && force_ns[0] <= '4' && slots_for(force_ns[0] - '0') >= 2) {
+      astages = force_ns[0] - '0';
+      wslots = slots_for(astages);
+    }
+  }
   if (wslots > kMaxWSlots) wslots = kMaxWSlots;
   if (wslots < 2 && wslots < slabs) return set_error(BHSR_EINVAL, "conv_tc: no room for weight ring");
   p.w_resident = slabs <= wslots ? 1 : 0;
@@ -661,6 +1096,108 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
   if (wmode == 2) return launch_kernel<N, EXACT, MB, KS, 2>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
   if (wmode == 1) return launch_kernel<N, EXACT, MB, KS, 1>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
   return launch_kernel<N, EXACT, MB, KS, 0>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+}
+
+// 5-D view of the packed weight blob [chunk][tap = dy*3+dx][part][32 couts][CH] that lands one
+// (chunk, dy) slab in shared memory as [part][dx][cout][CH] rows (see conv_dx_kernel).
+static int make_weight_map_dx(CUtensorMap* tm, const void* base, int n_chunks, int nparts, int ch) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return BHSR_ECUDA;
+  const cuuint64_t rb = (cuuint64_t)ch * 2;
+  const cuuint64_t tap_bytes = (cuuint64_t)nparts * 32 * rb;
+  cuuint64_t dims[5] = {(cuuint64_t)ch, 32, 3, (cuuint64_t)nparts, (cuuint64_t)n_chunks * 3};
+  cuuint64_t strides[4] = {rb, tap_bytes, 32 * rb, 3 * tap_bytes};
+  cuuint32_t box[5] = {(cuuint32_t)ch, 32, 3, (cuuint32_t)nparts, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(w, dx) -> %d", (int)r);
+  return 0;
+}
+
+template <bool EXACT, int MB, bool WRES>
+static int launch_dx_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
+                            const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
+  auto kern = conv_dx_kernel<EXACT, MB, WRES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BHSR_CUDA_CHECK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kDxThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  BHSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));
+  return 0;
+}
+
+// dx-in-N launch for a 32-output 3x3 layer (plain window, planes output).
+template <bool EXACT, int MB>
+static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream) {
+  constexpr int CH = EXACT ? 32 : 64;
+  using G = TileGeom<MB, CH>;
+  constexpr int NPART = EXACT ? 2 : 1;
+  constexpr int W_SLAB = 96 * NPART * G::kRowBytes;
+  constexpr int A_STAGE = G::kTileBytes * NPART;
+  constexpr int S_OUT = 126 * MB;
+  p.tiles_per_strip = (d.h * kPitch + S_OUT - 1) / S_OUT;
+  p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;
+  const int slabs = p.n_chunks * 3;
+  auto slots_for = [&](int ns) {
+    const int avail = kSmemLimit - 1024 - ns * A_STAGE - kDxTailBytes;
+    return avail < 0 ? 0 : avail / W_SLAB;
+  };
+  int astages = 2, wslots = slots_for(2);
+  bool picked = false;
+  for (int ns = kMaxAStages; ns >= 2 && !picked; --ns)   // whole layer resident, deepest ring
+    if (slots_for(ns) >= slabs) { astages = ns; wslots = slots_for(ns); picked = true; }
+  for (int ns = kMaxAStages; ns >= 2 && !picked; --ns)   // else a weight ring of >= 6 slabs (two chunks)
+    if (slots_for(ns) >= 6) { astages = ns; wslots = slots_for(ns); picked = true; }
+  {
+    static const char* force_ns = getenv("BHSR_ASTAGES");
+    if (force_ns && force_ns[0] >= '2' && force_ns[0] <= '4' && slots_for(force_ns[0] - '0') >= 3) {
+      astages = force_ns[0] - '0';
+      wslots = slots_for(astages);
+    }
+  }
+  if (wslots > kMaxWSlots) wslots = kMaxWSlots;
+  if (wslots < 3) return set_error(BHSR_EINVAL, "conv_tc(dx): no room for the weight ring");
+  p.w_resident = slabs <= wslots ? 1 : 0;
+  {
+    static const char* force = getenv("BHSR_DEBUG_FORCE_STREAM");
+    if (force && force[0] == '1') { p.w_resident = 0; if (wslots > 6) wslots = 6; }
+  }
+  if (p.w_resident) wslots = slabs;
+  p.wslots = wslots;
+  p.astages = astages;
+  const int smem_bytes = 1024 + astages * A_STAGE + wslots * W_SLAB + kDxTailBytes;
+
+  CUtensorMap tm_hi, tm_lo, tm_w;
+  int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, CH);
+  if (rc) return rc;
+  rc = make_act_map(&tm_lo, EXACT ? d.in_lo : d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, CH);
+  if (rc) return rc;
+  rc = make_weight_map_dx(&tm_w, d.w_packed, p.n_chunks, NPART, CH);
+  if (rc) return rc;
+
+  int sms = device_sm_count();
+  if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
+  int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
+  static const char* no_pdl = getenv("BHSR_NO_PDL");
+  p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
+  if (p.w_resident) return launch_dx_kernel<EXACT, MB, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  return launch_dx_kernel<EXACT, MB, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
 }
 
 }  // namespace bhsr
@@ -762,6 +1299,18 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
     if (want && want[0] == '1') {
       if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 256 * 8 * sizeof(long long));
       p.dbg = g_dbg_buf;
+    }
+    static const char* nomma = getenv("BHSR_DEBUG_NOMMA");
+    p.nomma = (nomma && nomma[0] == '1') ? 1 : 0;
+  }
+
+  // 32-output plain 3x3 layers with plane outputs: the dx-in-N kernel (BHSR_DXN=0 keeps the per-tap one)
+  {
+    static const char* dxn = getenv("BHSR_DXN");
+    const bool use_dx = !(dxn && dxn[0] == '0');
+    if (use_dx && d.cout == 32 && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2)) {
+      if (exact) return mb == 2 ? launch_dx<true, 2>(d, p, stream) : launch_dx<true, 1>(d, p, stream);
+      return mb == 2 ? launch_dx<false, 2>(d, p, stream) : launch_dx<false, 1>(d, p, stream);
     }
   }
 

@@ -65,11 +65,20 @@ def run_case(name, desc_mode):
     }
     cases["time_exact32_mb2"] = dict(nb=64, exact=True, mb=2, time=True)
     cases["time_exact64_c192_mb2"] = dict(nb=64, cout=64, cin=192, exact=True, mb=2, lrelu=False, res=1, time=True)
+    cases["time_exact32_c160_mb2"] = dict(nb=64, cin=160, exact=True, mb=2, time=True)
+    cases["time_exact32_c160"] = dict(nb=64, cin=160, exact=True, mb=1, time=True)
+    cases["time_fast32_c160_mb2"] = dict(nb=64, cin=160, mb=2, time=True)
+    cases["exact32_mb2"] = dict(exact=True, mb=2)
+    cases["exact32_c160_mb2"] = dict(cin=160, exact=True, mb=2, nb=3)
+    cases["odd_h_mb2"] = dict(nb=3, h=40, w=128, cin=128, exact=True, mb=2)
+    cases["fast32_c96_mb2"] = dict(cin=96, mb=2, nb=3)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
     cfg["max_ctas"] = 0
     cfg.update(cases[name])
+    if os.environ.get("PROBE_MAX_CTAS"):
+        cfg["max_ctas"] = int(os.environ["PROBE_MAX_CTAS"])
     def note(msg):
         print("#", msg, file=sys.stderr, flush=True)
     note("start " + name)
@@ -178,7 +187,10 @@ def run_case(name, desc_mode):
                 print(json.dumps({"case": name, "mma_warp_cycles_per_tile": {
                     "total": float((buf[:, 0] / tiles).mean()), "wait_tmem_empty": float((buf[:, 1] / tiles).mean()),
                     "wait_act": float((buf[:, 2] / tiles).mean()), "wait_weights": float((buf[:, 3] / tiles).mean()),
-                    "tiles_per_cta": float(tiles.mean())}}))
+                    "tiles_per_cta": float(tiles.mean()),
+                    "prologue_cycles": float(buf[:, 5].mean()), "epi_wait_per_tile": float((buf[:, 6] / tiles).mean()),
+                    "kernel_cycles_mean": float(buf[:, 7].mean()), "kernel_cycles_max": float(buf[:, 7].max()),
+                    "mma_loop_max": float(buf[:, 0].max())}}))
     torch.cuda.synchronize()
     err = (got - ref).abs()
     tol = 1e-5 + 1e-4 * ref.abs()  # loose here: fp16 hi/lo output quantisation is ~2^-22 relative
