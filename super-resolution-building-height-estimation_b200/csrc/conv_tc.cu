@@ -587,6 +587,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 // and are recomputed by the adjacent block: blocks advance by 126 flat pixels.
 // 9 (18 exact) narrow MMAs per k-step become 3 (6) wide ones.
 //
+// Activation supply.  Measured (profiles/r01_tma_supply_nomma_v5.log, r01_dxn_bringup_v6.log): a
+// halo-tile TMA load completes ~2400 cycles + bytes/25 after issue and a stage cannot be refilled
+// while its MMAs are pending, so a 2-deep ring of 59 KB (hi+lo) stages starves the MMA stream.
+// In exact numerics the hi and lo' planes therefore travel in SEPARATE rings and every chunk is
+// issued in two phases — all hi MMAs (N=192), then all lo' MMAs (N=96, into the correction
+// columns): each 30 KB stage is released as soon as its own phase has been issued, which doubles
+// the number of loads in flight for the same shared memory.
+//
+// Issue blocks.  A barrier test costs ~100 cycles and ends every asm issue block, so a block must
+// carry >= 4 MMAs or the tensor queue drains (measured: 2-MMA blocks of N=96 made the lo' phase
+// issue-bound, profiles/r01_dxn_v2_splitrings_slower.log): both 128-row blocks of a tile share
+// one block per (phase, window row).  Only around the accumulator hand-over (first chunk's hi
+// phase, last chunk's lo' phase) the order is block-major with per-block blocks, so block 0's
+// drain overlaps block 1's last MMAs and block 1's drain overlaps block 0's first ones.
+//
 // Warp roles (352 threads): warps 0..3 / 4..7 = two epilogue groups (accumulator blocks
 // alternate between them; each drains its TMEM block to registers and releases it at once),
 // warp 8 = activation TMA producer, warp 9 = weight TMA producer, warp 10 = MMA issuer.
@@ -596,8 +611,9 @@ constexpr int kDxThreads = 352;
 constexpr int kDxWarpProdA = 8, kDxWarpProdW = 9, kDxWarpMma = 10;
 constexpr int kDxStageBytes = 8 * 32 * 80;          // store-transpose staging, 8 epilogue warps
 constexpr int kDxXchgFloats = 2 * 2 * 4 * 64;       // [group][parity][warp][v0 of lane 31 | v2 of lane 0]
-constexpr int kDxTailBytes = (2 * kMaxAStages + 8 + 2 * kMaxWSlots) * 8 + 16 + 2 * 64 * 4 + 64 +
-                             kDxStageBytes + kDxXchgFloats * 4;
+constexpr int kDxBars = 4 * kMaxAStages + 8 + 2 * kMaxWSlots;
+constexpr int kDxTailBytes = kDxBars * 8 + 16 + 2 * 64 * 4 + 64 + kDxStageBytes + kDxXchgFloats * 4;
+constexpr int kDxBlk = 126;                         // valid output rows per 128-row block
 
 template <bool EXACT, int MB, bool WRES>
 __global__ void __launch_bounds__(kDxThreads, 1)
@@ -612,11 +628,10 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   constexpr int NPART = EXACT ? 2 : 1;
   constexpr int COLS = 96 * NPART;                 // weight rows per window row = TMEM columns per block
   constexpr int W_SLAB = COLS * RB;                // one (chunk, dy) weight slab: 12288 B either way
-  constexpr int A_STAGE = G::kTileBytes * NPART;
-  constexpr int A_TX = G::kTileBytesRaw * NPART;
+  constexpr int TILE = G::kTileBytes;              // one plane of one halo tile
+  constexpr int A_TX = G::kTileBytesRaw;
   constexpr int NSLOT = EXACT ? 2 : 4;             // accumulator blocks in TMEM (192 / 96 columns each)
-  constexpr int S_BLK = 126;                       // valid output rows per 128-row block
-  constexpr int S_OUT = S_BLK * MB;
+  constexpr int S_OUT = kDxBlk * MB;               // valid output rows per tile
   static_assert(NSLOT * COLS <= 512, "TMEM overflow");
   constexpr uint32_t IDESC_WIDE = make_idesc_f16(COLS);
   constexpr uint32_t IDESC_N = make_idesc_f16(96);
@@ -624,16 +639,18 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t a_base = smem_base;
-  const int NS = p.astages;
-  const uint32_t w_base = a_base + NS * A_STAGE;
-  uint8_t* tail = smem + NS * A_STAGE + p.wslots * W_SLAB;
+  const int NS = p.astages;                        // depth of the hi ring and of the lo ring
+  const uint32_t ah_base = smem_base;
+  const uint32_t al_base = ah_base + NS * TILE;
+  const uint32_t w_base = ah_base + NPART * NS * TILE;
+  uint8_t* tail = smem + NPART * NS * TILE + p.wslots * W_SLAB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   auto bar = [&](int i) { return smem_u32(bars + i); };
-  constexpr int B_AFULL = 0, B_AEMPTY = kMaxAStages, B_TFULL = 2 * kMaxAStages,
-                B_TEMPTY = B_TFULL + 4, B_WFULL = B_TFULL + 8;
+  constexpr int B_HFULL = 0, B_HEMPTY = kMaxAStages, B_LFULL = 2 * kMaxAStages,
+                B_LEMPTY = 3 * kMaxAStages, B_TFULL = 4 * kMaxAStages, B_TEMPTY = B_TFULL + 4,
+                B_WFULL = B_TFULL + 8;
   const int B_WEMPTY = B_WFULL + kMaxWSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_WFULL + 2 * kMaxWSlots);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kDxBars);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
   float* s_scale = s_bias + 64;
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_scale + 64);
@@ -646,10 +663,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #endif
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxAStages; ++i) {
-      mbar_init(bar(B_AFULL + i), 1);
-      mbar_init(bar(B_AEMPTY + i), 1);
-    }
+    for (int i = 0; i < 4 * kMaxAStages; ++i) mbar_init(bar(i), 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar(B_TFULL + i), 1);
       mbar_init(bar(B_TEMPTY + i), 128);
@@ -684,9 +698,9 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   const int tile_step = gridDim.x;
 
   if (warp == kDxWarpProdA) {
-    // ------------------------------------------------ activation producer
+    // ------------------------------------------------ activation producer (hi ring, lo ring)
     if (lane == 0) {
-      int st = 0, ph = 1;
+      int sh = 0, ph_h = 1, sl = 0, ph_l = 1;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const int t = tile % p.tiles_per_strip;
         const int sn = tile / p.tiles_per_strip;
@@ -694,14 +708,19 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int n = sn / p.n_strips;
         // block 0 row 0 is flat output t*S_OUT - 1; its dy = -1 operand row starts one image row up
         const int r0 = (t * S_OUT + kPitch - 1) / kPitch - 2;
-        for (int c = 0; c < p.n_chunks; ++c, st = (st + 1 == NS ? 0 : st + 1), ph ^= (st == 0)) {
-          mbar_wait(bar(B_AEMPTY + st), ph);
-          mbar_expect_tx(bar(B_AFULL + st), A_TX);
-          const uint32_t dst = a_base + st * A_STAGE;
-          tma_load_4d(dst, &tm_a_hi, bar(B_AFULL + st), p.in_choff + c * CH, s * kStrip - 1, r0, n);
-          if (EXACT)
-            tma_load_4d(dst + G::kTileBytes, &tm_a_lo, bar(B_AFULL + st), p.in_choff + c * CH,
+        for (int c = 0; c < p.n_chunks; ++c) {
+          mbar_wait(bar(B_HEMPTY + sh), ph_h);
+          mbar_expect_tx(bar(B_HFULL + sh), A_TX);
+          tma_load_4d(ah_base + sh * TILE, &tm_a_hi, bar(B_HFULL + sh), p.in_choff + c * CH,
+                      s * kStrip - 1, r0, n);
+          if (++sh == NS) { sh = 0; ph_h ^= 1; }
+          if (EXACT) {
+            mbar_wait(bar(B_LEMPTY + sl), ph_l);
+            mbar_expect_tx(bar(B_LFULL + sl), A_TX);
+            tma_load_4d(al_base + sl * TILE, &tm_a_lo, bar(B_LFULL + sl), p.in_choff + c * CH,
                         s * kStrip - 1, r0, n);
+            if (++sl == NS) { sl = 0; ph_l ^= 1; }
+          }
         }
       }
     }
@@ -734,101 +753,207 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     long long t_tempty = 0, t_afull = 0, t_wfull = 0, tq = 0;
     constexpr bool dbg = false;
 #endif
-    uint32_t ok_a = 0, ok_w = 0;
+    uint32_t ok_h = 0, ok_l = 0, ok_w = 0;   // early-probe results (ok_w: one bit per window row)
     const int my_tiles = (p.total_tiles - first_tile + tile_step - 1) / tile_step;
     const int n_chunks = p.n_chunks, cin = p.cin, wslots = p.wslots;
-    int st = 0, a_ph = 0;
+    int sh = 0, h_ph = 0, sl = 0, l_ph = 0;
     int ws_r = 0, w_ph = 0;
+    constexpr uint32_t ASTEP = kDxBlk * RB16;       // descriptor units between the two blocks
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int f0 = t * S_OUT;
       const int r0 = (f0 + kPitch - 1) / kPitch - 2;
       const int base_flat = f0 - r0 * kPitch;     // 67..132: tile-relative flat row of block 0, dy = 0
       const bool more_tiles = tile_it + 1 < static_cast<uint32_t>(my_tiles);
+      // accumulator blocks of this tile (consecutive slots) and their barrier parities
+      const uint32_t blk0 = tile_it * MB;
+      const uint32_t slot0 = blk0 % NSLOT;
+      const uint32_t acc0 = tmem_base + slot0 * COLS;
+      const uint32_t t_par = (blk0 / NSLOT) & 1;
       for (int c = 0; c < n_chunks; ++c) {
-        if (!ok_a) {
+        // ---- the three weight slabs (window rows) of this chunk
+        int wsl[3];
+        uint32_t nbar[3], npar[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          if (WRES) {
+            wsl[g] = c * 3 + g;
+            if (tile_it == 0) mbar_wait(bar(B_WFULL + wsl[g]), 0);
+          } else {
+            wsl[g] = ws_r;
+            if (!((ok_w >> g) & 1u)) {
+              if (dbg) tq = clock64();
+              mbar_wait(bar(B_WFULL + ws_r), w_ph);
+              if (dbg) t_wfull += clock64() - tq;
+            }
+            if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }
+          }
+        }
+        ok_w = 0;
+        {
+          int r = ws_r, ph = w_ph;                 // where the NEXT chunk's slabs will land
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            nbar[g] = bar(B_WFULL + (WRES ? wsl[g] : r));
+            npar[g] = WRES ? 0u : static_cast<uint32_t>(ph);
+            if (++r == wslots) { r = 0; ph ^= 1; }
+          }
+        }
+        if (!ok_h) {
           if (dbg) tq = clock64();
-          mbar_wait(bar(B_AFULL + st), a_ph);
+          mbar_wait(bar(B_HFULL + sh), h_ph);
           if (dbg) t_afull += clock64() - tq;
         }
-        ok_a = 0;
+        ok_h = 0;
         tc_fence_after();
-        int st_next = st + 1, a_ph_next = a_ph;
-        if (st_next == NS) { st_next = 0; a_ph_next ^= 1; }
-        const uint32_t bar_a_next = bar(B_AFULL + st_next);
-        // descriptor low word of (block 0, dy = -1, k-step 0) of this stage
-        const uint32_t a_lo0 =
-            desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) + (base_flat - kPitch) * RB16;
+        int sh_next = sh + 1, h_ph_next = h_ph;
+        if (sh_next == NS) { sh_next = 0; h_ph_next ^= 1; }
+        const uint32_t bar_h_next = bar(B_HFULL + sh_next);
+        const uint32_t bar_l_cur = bar(B_LFULL + sl);
+        // descriptor low words of (block 0, dy = -1, k-step 0) in the hi / lo stage
+        const uint32_t row0 = (base_flat - kPitch) * RB16;
+        const uint32_t a_h0 = desc_lo0 + (((ah_base + sh * TILE) >> 4) & 0x3FFF) + row0;
+        const uint32_t a_l0 = desc_lo0 + (((al_base + sl * TILE) >> 4) & 0x3FFF) + row0;
+        const uint32_t b0 = desc_lo0 + ((w_base >> 4) & 0x3FFF);
         const int rem = cin - c * CH;
+        const bool first_chunk = (c == 0);
         const bool last_chunk = (c + 1 == n_chunks);
         auto issue_chunk = [&](auto ksteps_tag) {
           constexpr int KST = decltype(ksteps_tag)::value;
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {            // window row dy = g - 1
-            int ws;
-            uint32_t bar_w_next = bar_a_next, par_w_next = a_ph_next;
-            if (WRES) {
-              ws = c * 3 + g;
-              if (tile_it == 0) {
-                mbar_wait(bar(B_WFULL + ws), 0);
-                tc_fence_after();
-              }
-            } else {
-              ws = ws_r;
-              if (!ok_w) {
-                if (dbg) tq = clock64();
-                mbar_wait(bar(B_WFULL + ws), w_ph);
-                if (dbg) t_wfull += clock64() - tq;
-              }
-              ok_w = 0;
-              tc_fence_after();
-              if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }
-              bar_w_next = bar(B_WFULL + ws_r);
-              par_w_next = w_ph;
-            }
-            const uint32_t b_lo = desc_lo0 + (((w_base + ws * W_SLAB) >> 4) & 0x3FFF);
-            uint32_t okbits = 0;
+          uint32_t okbits = 0;
+          // ================= phase H: hi activations x [W_hi | W_lo'] (fast: the only phase)
+          // probes: bit 0 = what follows this phase (exact: this chunk's lo stage; fast: next hi
+          // stage), bit 1 = (fast only) next chunk's weight slab of the same window row
+          const uint32_t hb1 = EXACT ? bar_l_cur : bar_h_next;
+          const uint32_t hp1 = static_cast<uint32_t>(EXACT ? l_ph : h_ph_next);
+          if (EXACT && first_chunk) {
+            // block-major around the accumulator hand-over
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
-              const uint32_t blk = tile_it * MB + mb;
-              const uint32_t slot = blk % NSLOT;
-              if (c == 0 && g == 0) {              // first MMA into this accumulator block
-                if (dbg) tq = clock64();
-                mbar_wait(bar(B_TEMPTY + slot), ((blk / NSLOT) & 1) ^ 1);
-                if (dbg) t_tempty += clock64() - tq;
-                tc_fence_after();
-              }
-              const uint32_t acc = tmem_base + slot * COLS;
-              const uint32_t a_lo = a_lo0 + (g * kPitch + mb * S_BLK) * RB16;
-              // probe slot: block 0 tests the next weight slab, the last block the next activation stage
-              const bool probe_w = (mb == 0) && !WRES;
-              const uint32_t pbar = probe_w ? bar_w_next : bar_a_next;
-              const uint32_t ppar = probe_w ? par_w_next : static_cast<uint32_t>(a_ph_next);
+              if (dbg) tq = clock64();
+              mbar_wait(bar(B_TEMPTY + slot0 + mb), t_par ^ 1);
+              if (dbg) t_tempty += clock64() - tq;
+              tc_fence_after();
               if (elect_one()) {
 #ifdef BHSR_TIMING
                 if (!p.nomma)
 #endif
-                {
-                  const uint32_t ok = issue_tap<EXACT, 1, KST, 128 * RB16, (G::kTileBytes >> 4), COLS, 96>(
-                      a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, (c > 0 || g > 0) ? 1u : 0u, pbar, ppar);
-                  okbits |= ok << (probe_w ? 0 : 1);
-                }
-                if (last_chunk && g == 2) umma_commit(bar(B_TFULL + slot));
-                if (mb == MB - 1 && !WRES) umma_commit(bar(B_WEMPTY + ws));
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+                  okbits |= issue_dx<KST, 1, 0>(a_h0 + (g * kPitch + mb * kDxBlk) * RB16,
+                                                b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0 + mb * COLS, 0,
+                                                IDESC_WIDE, g > 0 ? 1u : 0u, hb1, hp1, hb1, hp1);
               }
               __syncwarp();
             }
+          } else {
+            if (first_chunk) {                     // fast numerics: 4 slots, no hand-over pressure
+#pragma unroll
+              for (int mb = 0; mb < MB; ++mb) {
+                if (dbg) tq = clock64();
+                mbar_wait(bar(B_TEMPTY + slot0 + mb), t_par ^ 1);
+                if (dbg) t_tempty += clock64() - tq;
+              }
+              tc_fence_after();
+            }
+            if (elect_one()) {
+#ifdef BHSR_TIMING
+              if (!p.nomma)
+#endif
+#pragma unroll
+              for (int g = 0; g < 3; ++g) {
+                const uint32_t r = issue_dx<KST, MB, ASTEP>(
+                    a_h0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0, acc0 + COLS,
+                    IDESC_WIDE, (c > 0 || g > 0) ? 1u : 0u, hb1, hp1, EXACT ? hb1 : nbar[g],
+                    EXACT ? hp1 : npar[g]);
+                okbits |= (r & 1u) | ((r >> 1) << (1 + g));
+              }
+              if (!EXACT) {
+                if (last_chunk) {
+#pragma unroll
+                  for (int mb = 0; mb < MB; ++mb) umma_commit(bar(B_TFULL + slot0 + mb));
+                }
+                if (!WRES) {
+#pragma unroll
+                  for (int g = 0; g < 3; ++g) umma_commit(bar(B_WEMPTY + wsl[g]));
+                }
+              }
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit(bar(B_HEMPTY + sh));
+          okbits = __reduce_or_sync(0xffffffffu, okbits);
+          if (EXACT) {
+            ok_l = okbits & 1u;
+          } else {
+            if (!last_chunk || more_tiles) ok_h = okbits & 1u;
+            if (!WRES) ok_w = (okbits >> 1) & 7u;
+          }
+          if (EXACT) {
+            // ================= phase L: lo' activations x W_hi into the correction columns
+            // probes: bit 0 = next hi stage, bit 1 = next chunk's weight slab of the same row
+            if (!ok_l) {
+              if (dbg) tq = clock64();
+              mbar_wait(bar(B_LFULL + sl), l_ph);
+              if (dbg) t_afull += clock64() - tq;
+            }
+            ok_l = 0;
+            tc_fence_after();
+            okbits = 0;
+            if (last_chunk) {
+#pragma unroll
+              for (int mb = 0; mb < MB; ++mb) {
+                if (elect_one()) {
+#ifdef BHSR_TIMING
+                  if (!p.nomma)
+#endif
+#pragma unroll
+                  for (int g = 0; g < 3; ++g) {
+                    const uint32_t r = issue_dx<KST, 1, 0>(
+                        a_l0 + (g * kPitch + mb * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi,
+                        acc0 + mb * COLS + 96, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
+                        nbar[g], npar[g]);
+                    if (mb == MB - 1) okbits |= (r & 1u) | ((r >> 1) << (1 + g));
+                  }
+                  umma_commit(bar(B_TFULL + slot0 + mb));
+                }
+                __syncwarp();
+              }
+            } else {
+              if (elect_one()) {
+#ifdef BHSR_TIMING
+                if (!p.nomma)
+#endif
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                  const uint32_t r = issue_dx<KST, MB, ASTEP>(
+                      a_l0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0 + 96,
+                      acc0 + COLS + 96, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next), nbar[g],
+                      npar[g]);
+                  okbits |= (r & 1u) | ((r >> 1) << (1 + g));
+                }
+              }
+              __syncwarp();
+            }
+            if (elect_one()) {
+              if (!WRES) {
+#pragma unroll
+                for (int g = 0; g < 3; ++g) umma_commit(bar(B_WEMPTY + wsl[g]));
+              }
+              umma_commit(bar(B_LEMPTY + sl));
+            }
             okbits = __reduce_or_sync(0xffffffffu, okbits);
-            if (!WRES) ok_w = okbits & 1u;
-            if (g == 2 && (!last_chunk || more_tiles)) ok_a = (okbits >> 1) & 1u;
+            if (!last_chunk || more_tiles) ok_h = okbits & 1u;
+            if (!WRES) ok_w = (okbits >> 1) & 7u;
           }
         };
         if (rem >= CH) issue_chunk(std::integral_constant<int, KSTEPS>{});
         else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
-        if (elect_one()) umma_commit(bar(B_AEMPTY + st));
-        __syncwarp();
-        st = st_next;
-        a_ph = a_ph_next;
+        sh = sh_next;
+        h_ph = h_ph_next;
+        if (EXACT) {
+          if (++sl == NS) { sl = 0; l_ph ^= 1; }
+        }
       }
     }
 #ifdef BHSR_TIMING
@@ -878,12 +1003,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             tmem_ld_32x32(t_row + 96 + col, rawl);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              dst[j] = fmaf(__uint_as_float(rawl[j]), 1.f / 2048.f, __uint_as_float(raw[j]));
+            for (int jj = 0; jj < 32; ++jj)
+              dst[jj] = fmaf(__uint_as_float(rawl[jj]), 1.f / 2048.f, __uint_as_float(raw[jj]));
           } else {
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(raw[j]);
+            for (int jj = 0; jj < 32; ++jj) dst[jj] = __uint_as_float(raw[jj]);
           }
         };
         drain(0, v0);
@@ -895,46 +1020,46 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         float* xb = s_xchg + ((grp * 2 + xpar) * 4) * 64;
         if (lane == 31) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(xb + q * 64 + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+          for (int jj = 0; jj < 32; jj += 4)
+            *reinterpret_cast<float4*>(xb + q * 64 + jj) = make_float4(v0[jj], v0[jj + 1], v0[jj + 2], v0[jj + 3]);
         }
         if (lane == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(xb + q * 64 + 32 + j) = make_float4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
+          for (int jj = 0; jj < 32; jj += 4)
+            *reinterpret_cast<float4*>(xb + q * 64 + 32 + jj) = make_float4(v2[jj], v2[jj + 1], v2[jj + 2], v2[jj + 3]);
         }
         if (grp == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
         xpar ^= 1;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float up = __shfl_up_sync(0xffffffffu, v0[j], 1);
-          const float dn = __shfl_down_sync(0xffffffffu, v2[j], 1);
-          v0[j] = up;
-          v2[j] = dn;
+        for (int jj = 0; jj < 32; ++jj) {
+          const float up = __shfl_up_sync(0xffffffffu, v0[jj], 1);
+          const float dn = __shfl_down_sync(0xffffffffu, v2[jj], 1);
+          v0[jj] = up;
+          v2[jj] = dn;
         }
         if (lane == 0 && q > 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(xb + (q - 1) * 64 + j);
-            v0[j] = x.x; v0[j + 1] = x.y; v0[j + 2] = x.z; v0[j + 3] = x.w;
+          for (int jj = 0; jj < 32; jj += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xb + (q - 1) * 64 + jj);
+            v0[jj] = x.x; v0[jj + 1] = x.y; v0[jj + 2] = x.z; v0[jj + 3] = x.w;
           }
         }
         if (lane == 31 && q < 3) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(xb + (q + 1) * 64 + 32 + j);
-            v2[j] = x.x; v2[j + 1] = x.y; v2[j + 2] = x.z; v2[j + 3] = x.w;
+          for (int jj = 0; jj < 32; jj += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xb + (q + 1) * 64 + 32 + jj);
+            v2[jj] = x.x; v2[jj + 1] = x.y; v2[jj + 2] = x.z; v2[jj + 3] = x.w;
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (v0[j] + v1[j]) + v2[j];
+        for (int jj = 0; jj < 32; ++jj) v[jj] = (v0[jj] + v1[jj]) + v2[jj];
 
-        const int f = t * S_OUT - 1 + mb * S_BLK + row;
+        const int f = (t * MB + mb) * kDxBlk - 1 + row;
         const int py = f / kPitch;
         const int pc = f - py * kPitch;
         const int px = s * kStrip + pc;
-        const bool valid = (row >= 1) && (row <= S_BLK) && (pc < kStrip) && (py < p.h) && (px < p.w);
+        const bool valid = (row >= 1) && (row <= kDxBlk) && (pc < kStrip) && (py < p.h) && (px < p.w);
         const size_t in_pix = (static_cast<size_t>(n) * p.h + py) * p.w + px;
         const int oy = py * p.out_scale + p.out_oy;
         const int ox = px * p.out_scale + p.out_ox;
@@ -1148,8 +1273,8 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   using G = TileGeom<MB, CH>;
   constexpr int NPART = EXACT ? 2 : 1;
   constexpr int W_SLAB = 96 * NPART * G::kRowBytes;
-  constexpr int A_STAGE = G::kTileBytes * NPART;
-  constexpr int S_OUT = 126 * MB;
+  constexpr int A_STAGE = G::kTileBytes * NPART;   // one hi stage + one lo stage
+  constexpr int S_OUT = kDxBlk * MB;               // valid output rows per tile
   p.tiles_per_strip = (d.h * kPitch + S_OUT - 1) / S_OUT;
   p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;
   const int slabs = p.n_chunks * 3;
@@ -1307,7 +1432,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   // 32-output plain 3x3 layers with plane outputs: the dx-in-N kernel (BHSR_DXN=0 keeps the per-tap one)
   {
     static const char* dxn = getenv("BHSR_DXN");
-    const bool use_dx = !(dxn && dxn[0] == '0');
+    const bool use_dx = !(dxn && dxn[0] == '0') && !(d.desc_mode & 0x100);  // desc_mode bit 8: per-tap kernel
     if (use_dx && d.cout == 32 && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2)) {
       if (exact) return mb == 2 ? launch_dx<true, 2>(d, p, stream) : launch_dx<true, 1>(d, p, stream);
       return mb == 2 ? launch_dx<false, 2>(d, p, stream) : launch_dx<false, 1>(d, p, stream);

@@ -252,6 +252,7 @@ __device__ __forceinline__ uint32_t issue_tap(uint32_t a_lo, uint32_t b_lo, uint
   uint32_t ok;
   if constexpr (!EXACT && MB == 1 && KST == 4) BHSR_TAP_ASM(BHSR_K4(BHSR_STEP_F));
   else if constexpr (!EXACT && MB == 1 && KST == 2) BHSR_TAP_ASM(BHSR_K2(BHSR_STEP_F));
+  else if constexpr (!EXACT && MB == 1 && KST == 1) BHSR_TAP_ASM(BHSR_K1(BHSR_STEP_F));
   else if constexpr (!EXACT && MB == 2 && KST == 4) BHSR_TAP_ASM(BHSR_K4(BHSR_STEP_F) BHSR_NEXT_MB BHSR_K4(BHSR_STEP_F));
   else if constexpr (!EXACT && MB == 2 && KST == 2) BHSR_TAP_ASM(BHSR_K2(BHSR_STEP_F) BHSR_NEXT_MB BHSR_K2(BHSR_STEP_F));
   else if constexpr (EXACT && MB == 1 && KST == 2) BHSR_TAP_ASM(BHSR_K2(BHSR_STEP_E));
@@ -260,6 +261,49 @@ __device__ __forceinline__ uint32_t issue_tap(uint32_t a_lo, uint32_t b_lo, uint
   else if constexpr (EXACT && MB == 2 && KST == 1) BHSR_TAP_ASM(BHSR_K1(BHSR_STEP_E) BHSR_NEXT_MB BHSR_K1(BHSR_STEP_E));
   else static_assert(KST < 0, "unsupported issue_tap variant");
   return ok;
+}
+
+// ---------------------------------------------------------------- dx-in-N issue block
+// KST k-steps for NB (1 or 2) 128-row blocks that share one weight slab, as ONE asm block with two
+// non-blocking mbarrier tests whose results are materialised at the bottom (see issue_tap).
+//   a_lo / b_lo: descriptor low words of (block 0, k-step 0);  d0 / d1: TMEM accumulators;
+//   ASTEP16: descriptor units between the two blocks' first rows.
+#define BHSR_DX_PRE                                                                    \
+  "{\n.reg .pred pacc, ptrue, pw1, pw2;\n.reg .b32 alo, blo;\n.reg .b64 da, db;\n"     \
+  "setp.ne.b32 pacc, %8, 0;\nsetp.eq.b32 ptrue, 0, 0;\n"                               \
+  "mbarrier.try_wait.parity.shared::cta.b64 pw1, [%9], %10;\n"                         \
+  "mbarrier.try_wait.parity.shared::cta.b64 pw2, [%11], %12;\n"                        \
+  "mov.b32 alo, %2;\nmov.b32 blo, %3;\n"
+#define BHSR_DX_STEP(D, ACC)                                                           \
+  "mov.b64 da, {alo, %4};\nmov.b64 db, {blo, %4};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %7, " ACC ";\n"                 \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_DX_NEXT "add.u32 alo, alo, %13;\nsub.u32 blo, blo, %14;\n"
+#define BHSR_DX_POST "selp.u32 %0, 1, 0, pw1;\nselp.u32 %1, 1, 0, pw2;\n}\n"
+#define BHSR_DX_B1(D) BHSR_DX_STEP(D, "pacc")
+#define BHSR_DX_B2(D) BHSR_DX_STEP(D, "pacc") BHSR_DX_STEP(D, "ptrue")
+#define BHSR_DX_B4(D) BHSR_DX_STEP(D, "pacc") BHSR_DX_STEP(D, "ptrue") BHSR_DX_STEP(D, "ptrue") BHSR_DX_STEP(D, "ptrue")
+#define BHSR_DX_ASM(BODY)                                                              \
+  asm volatile(BHSR_DX_PRE BODY BHSR_DX_POST                                           \
+               : "=r"(ok1), "=r"(ok2)                                                  \
+               : "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(d0), "r"(d1), "r"(idesc), "r"(acc_first), \
+                 "r"(bar1), "r"(par1), "r"(bar2), "r"(par2), "n"(ASTEP16 - 2 * KST), "n"(2 * KST)  \
+               : "memory")
+
+// returns bit 0 = first barrier test passed, bit 1 = second
+template <int KST, int NB, int ASTEP16>
+__device__ __forceinline__ uint32_t issue_dx(uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t d0,
+                                             uint32_t d1, uint32_t idesc, uint32_t acc_first,
+                                             uint32_t bar1, uint32_t par1, uint32_t bar2, uint32_t par2) {
+  uint32_t ok1, ok2;
+  if constexpr (KST == 4 && NB == 2) BHSR_DX_ASM(BHSR_DX_B4("%5") BHSR_DX_NEXT BHSR_DX_B4("%6"));
+  else if constexpr (KST == 2 && NB == 2) BHSR_DX_ASM(BHSR_DX_B2("%5") BHSR_DX_NEXT BHSR_DX_B2("%6"));
+  else if constexpr (KST == 1 && NB == 2) BHSR_DX_ASM(BHSR_DX_B1("%5") BHSR_DX_NEXT BHSR_DX_B1("%6"));
+  else if constexpr (KST == 4 && NB == 1) BHSR_DX_ASM(BHSR_DX_B4("%5"));
+  else if constexpr (KST == 2 && NB == 1) BHSR_DX_ASM(BHSR_DX_B2("%5"));
+  else if constexpr (KST == 1 && NB == 1) BHSR_DX_ASM(BHSR_DX_B1("%5"));
+  else static_assert(KST < 0, "unsupported issue_dx variant");
+  return ok1 | (ok2 << 1);
 }
 
 }  // namespace bhsr

@@ -173,7 +173,7 @@ class _RRDBNetBase(nn.Module):
 
     def _engine_init(self):
         self.numerics = _default_numerics()
-        self.mblocks = 0
+        self.mblocks = int(os.environ.get("BHSR_MBLOCKS", "0"))  # 0 = auto (2)
         self._packed = None       # (key, packed, biases)
         self._workspace = {}      # (device, nb, h, w, feature) -> uint8 tensor
 

@@ -68,6 +68,42 @@ def test_conv_tc_vs_oracle(dev, numerics, rtol, atol, cin, cout, h, w, nb):
     assert float(out_hi[..., :64].abs().max()) == 0.0 and float(out_hi[..., 64 + cout:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("numerics,rtol,atol", [("exact", 1e-3, 1e-4), ("fast", 2e-2, 2e-2)])
+@pytest.mark.parametrize("cin,h,w,nb,mb,max_ctas", [(64, 64, 64, 3, 2, 0), (64, 64, 64, 3, 1, 0), (160, 64, 64, 2, 2, 5),
+                                                     (96, 23, 130, 2, 2, 3), (128, 2, 64, 1, 1, 0), (32, 64, 64, 1, 2, 1)])
+def test_conv_dx_kernel_vs_per_tap_and_oracle(dev, numerics, rtol, atol, cin, h, w, nb, mb, max_ctas):
+    """The dx-in-N kernel (three dx taps stacked along N, lane-shift combine; conv_tc.cu) against the
+    per-tap kernel (desc_mode bit 8) and the oracle, for both block pairings, ragged block ranges
+    (max_ctas), several strips, images shorter than one block, and the residual/ReLU/scale epilogue."""
+    from bhsr import ops
+    from bhsr._lib import NUMERICS
+    rng = np.random.RandomState(cin + h + w + mb)
+    x = (rng.rand(nb, cin, h, w) * 2 - 0.5).astype(np.float32)
+    wt = (rng.standard_normal((32, cin, 3, 3)) * (0.5 / np.sqrt(cin * 9))).astype(np.float32)
+    b = (rng.standard_normal(32) * 0.1).astype(np.float32)
+    sc = (rng.rand(32) + 0.5).astype(np.float32)
+    r1 = rng.standard_normal((nb, 32, h, w)).astype(np.float32)
+    conv = R.conv2d(x, wt, None, padding=1, acc_dtype=np.float64)
+    ref = np.maximum((conv * sc[None, :, None, None] + b[None, :, None, None]) * 0.5 + r1, 0.0)
+    num = NUMERICS[numerics]
+    ctot = 192
+    hi, lo = _planes(x, ctot, dev)
+    rhi, rlo = _planes(r1, 32, dev)
+    wp = ops.pack_conv_weights(cuda(wt, dev), num)
+    outs = []
+    for mode in (0, 0x100):
+        out_hi = torch.zeros((nb, h, w, 64), dtype=torch.float16, device=dev)
+        out_lo = torch.zeros_like(out_hi)
+        ops.conv_tc(hi, lo, 0, cin, wp, 32, cuda(b, dev), ops.PLAIN_TAPS, out_hi, out_lo, out_choff=32,
+                    scale=cuda(sc, dev), res1=(rhi, rlo, 0), alpha1=0.5, relu=True, numerics=num,
+                    mblocks=mb, max_ctas=max_ctas, desc_mode=mode)
+        assert float(out_hi[..., :32].abs().max()) == 0.0
+        outs.append(ops.planes_to_nchw(out_hi, out_lo, 32, 32).cpu().numpy())
+    assert_close(outs[0], ref, rtol, atol, f"dx kernel {cin}->32 {numerics} mb{mb}")
+    assert_close(outs[1], ref, rtol, atol, f"per-tap kernel {cin}->32 {numerics} mb{mb}")
+    assert_close(outs[0], outs[1], rtol, atol, "dx vs per-tap")
+
+
 def test_conv_tc_residual_epilogues(dev):
     """conv5 of rdb3: (conv*0.2 + x)*0.2 + rrdb_in  (rrdbnet_arch.py:143,167)."""
     from bhsr import ops

@@ -72,6 +72,11 @@ def run_case(name, desc_mode):
     cases["exact32_c160_mb2"] = dict(cin=160, exact=True, mb=2, nb=3)
     cases["odd_h_mb2"] = dict(nb=3, h=40, w=128, cin=128, exact=True, mb=2)
     cases["fast32_c96_mb2"] = dict(cin=96, mb=2, nb=3)
+    cases["time_exact32_mb2_nb16"] = dict(nb=16, exact=True, mb=2, time=True)
+    cases["time_exact32_c160_mb2_nb16"] = dict(nb=16, cin=160, exact=True, mb=2, time=True)
+    cases["time_exact32_mb2_nb32"] = dict(nb=32, exact=True, mb=2, time=True)
+    cases["time_exact32_mb2_ct64"] = dict(nb=64, exact=True, mb=2, ctot=64, time=True)
+    cases["time_exact64_c192_mb2_nb16"] = dict(nb=16, cout=64, cin=192, exact=True, mb=2, lrelu=False, res=1, time=True)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
