@@ -1100,10 +1100,19 @@ static int make_act_map(CUtensorMap* tm, const void* base, int nb, int h, int w,
                            (cuuint64_t)h * w * ctot * 2};
   cuuint32_t box[4] = {(cuuint32_t)ch, (cuuint32_t)kPitch, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  // L2 promotion of the activation loads.  A chunk is 64-128 B of every pixel's ctot*2-byte record:
+  // promoting each access to 256 B drags neighbouring channels through DRAM that this layer never
+  // reads (measured: DRAM reads 1.5-1.7x the unique bytes); 128 B measured best (r01_l2promo_v7.log).
+  static const int promo = [] {
+    const char* e = getenv("BHSR_L2PROMO");
+    return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : -1;
+  }();
+  CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (promo >= 0) l2p = static_cast<CUtensorMapL2promotion>(promo);  // 0 none, 1 64B, 2 128B, 3 256B
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(act) -> %d", (int)r);
   return 0;
 }

@@ -206,6 +206,8 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
 
 
 // ---------------------------------------------------------------- fused issue block
+// (The probe is mbarrier.test_wait: try_wait may suspend the issuing thread for a
+// system-dependent time when the phase is not complete yet, which stalls the MMA stream.)
 // All MMAs of ONE filter tap (MB m-blocks x KST k-steps, x2 in exact numerics) as a single asm
 // block that ALSO starts a non-blocking mbarrier test at its top and materialises the test's
 // result at its bottom.  A barrier test has ~100 cycles of latency even when the phase is long
@@ -219,7 +221,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
 #define BHSR_TAP_PRE                                                                   \
   "{\n.reg .pred pacc, ptrue, pw;\n.reg .b32 alo, blo, d, dn, al2;\n.reg .b64 da, db, dl;\n" \
   "setp.ne.b32 pacc, %7, 0;\nsetp.eq.b32 ptrue, 0, 0;\n"                               \
-  "mbarrier.try_wait.parity.shared::cta.b64 pw, [%8], %9;\n"                          \
+  "mbarrier.test_wait.parity.shared::cta.b64 pw, [%8], %9;\n"                           \
   "mov.b32 alo, %1;\nmov.b32 blo, %2;\nmov.b32 d, %4;\n"
 #define BHSR_TAP_POST "selp.u32 %0, 1, 0, pw;\n}\n"
 #define BHSR_STEP_F(ACC)                                                               \
@@ -271,8 +273,8 @@ __device__ __forceinline__ uint32_t issue_tap(uint32_t a_lo, uint32_t b_lo, uint
 #define BHSR_DX_PRE                                                                    \
   "{\n.reg .pred pacc, ptrue, pw1, pw2;\n.reg .b32 alo, blo;\n.reg .b64 da, db;\n"     \
   "setp.ne.b32 pacc, %8, 0;\nsetp.eq.b32 ptrue, 0, 0;\n"                               \
-  "mbarrier.try_wait.parity.shared::cta.b64 pw1, [%9], %10;\n"                         \
-  "mbarrier.try_wait.parity.shared::cta.b64 pw2, [%11], %12;\n"                        \
+  "mbarrier.test_wait.parity.shared::cta.b64 pw1, [%9], %10;\n"                         \
+  "mbarrier.test_wait.parity.shared::cta.b64 pw2, [%11], %12;\n"                        \
   "mov.b32 alo, %2;\nmov.b32 blo, %3;\n"
 #define BHSR_DX_STEP(D, ACC)                                                           \
   "mov.b64 da, {alo, %4};\nmov.b64 db, {blo, %4};\n"                                   \

@@ -77,6 +77,11 @@ def run_case(name, desc_mode):
     cases["time_exact32_mb2_nb32"] = dict(nb=32, exact=True, mb=2, time=True)
     cases["time_exact32_mb2_ct64"] = dict(nb=64, exact=True, mb=2, ctot=64, time=True)
     cases["time_exact64_c192_mb2_nb16"] = dict(nb=16, cout=64, cin=192, exact=True, mb=2, lrelu=False, res=1, time=True)
+    cases["time_fast32_ct64"] = dict(nb=64, mb=2, ctot=64, time=True)
+    cases["time_exact32_c32_ct32"] = dict(nb=64, cin=32, ctot=32, exact=True, mb=2, time=True)
+    cases["time_exact32_c32_ct192"] = dict(nb=64, cin=32, ctot=192, exact=True, mb=2, time=True)
+    cases["time_fast64_ct64"] = dict(nb=64, cout=64, cin=64, ctot=64, mb=2, lrelu=False, time=True)
+    cases["time_fast64_ct192"] = dict(nb=64, cout=64, cin=64, ctot=192, mb=2, lrelu=False, time=True)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
