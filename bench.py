@@ -121,6 +121,63 @@ def synth_state_torch(num_block):
     return rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=num_block, num_grow_ch=32)
 
 
+# ---------------------------------------------------------------------------------- per-kernel leg
+def _ncu_traffic():
+    """dram bytes per launch of the RDB conv kernels from the committed `ncu --set full` capture
+    (profiles/r01_ncu_kernels.json, written by tools/make_profile_summary.py)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return json.load(f)
+
+
+def layer_kernels_live(dev, B, numerics):
+    """The five conv shapes of one ResidualDenseBlock at batch B, each timed in isolation with CUDA
+    events on the launching stream (50 launches after 5 warm-ups): algorithmic FLOPs / duration."""
+    import torch
+    from bhsr import ops
+    from bhsr._lib import NUMERICS
+    num = NUMERICS[numerics]
+    traffic = _ncu_traffic().get(numerics, {})
+    g = torch.Generator(device="cpu").manual_seed(7)
+    hi = (torch.randn((B, 64, 64, 192), generator=g) * 0.5).to(torch.float16).to(dev)
+    lo = (torch.randn((B, 64, 64, 192), generator=g) * 0.5).to(torch.float16).to(dev)
+    out_hi = torch.zeros_like(hi)
+    out_lo = torch.zeros_like(hi)
+    res = []
+    for c in range(5):
+        cin, cout = 64 + 32 * c, (32 if c < 4 else 64)
+        w = torch.randn((cout, cin, 3, 3), generator=g).to(dev) * 0.01
+        b = torch.zeros(cout, device=dev)
+        wp = ops.pack_conv_weights(w, num)
+        kw = dict(lrelu=True) if c < 4 else dict(res1=(hi, lo, 0), alpha1=0.2)
+
+        def call():
+            ops.conv_tc(hi, lo, 0, cin, wp, cout, b, ops.PLAIN_TAPS, out_hi, out_lo,
+                        out_choff=(cin if c < 4 else 0), numerics=num, **kw)
+        for _ in range(5):
+            call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 50
+        e0.record()
+        for _ in range(n):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / n * 1e3
+        gflop = 2.0 * B * 64 * 64 * cout * cin * 9 / 1e9
+        name = f"rdb.conv{c + 1}"
+        t = traffic.get(name, {})
+        res.append({"layer": name, "kernel": ("conv_dx_kernel" if c < 4 else "conv_tc_kernel") + f"<{numerics}>",
+                    "shape": f"{cin}->{cout} 3x3 @64x64 x{B}", "us": us, "gflop": gflop,
+                    "tflops": gflop / (us * 1e-6) / 1e3,
+                    "launches_per_step": 69, "traffic_bytes": t.get("dram_bytes"),
+                    "traffic_source": t.get("source")})
+    return res
+
+
 # ---------------------------------------------------------------------------------- reference arm
 def cpu_reference_run(args, steps, warmup, tiles_per_step):
     """The reference's CPU path for the same workload: oracle/ref_torch.py (the stock
@@ -279,6 +336,7 @@ def main():
         except Exception as e:  # pinned 1 GiB may be refused on a small host
             extras["e2e_full_output_d2h"] = {"error": str(e)[:100]}
 
+    kernels = layer_kernels_live(dev, B, args.numerics) if rank == 0 else []
     peak, peak_src = measured_peaks()
     tiles = B * world
     value = tiles * K / ms * 1e3
@@ -300,12 +358,27 @@ def main():
                 "note": "nn.Module.forward_feature on pinned host tiles; D2H = per-tile checksum of the feature "
                         "map (in the reference pipeline the 1.07 GB feature map stays on the GPU for the head)"},
         "gpu_launches": launches_per_step * K,
-        "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peak, "traffic": None,
-                     "peak_source": peak_src,
-                     "note": "algorithmic conv FLOPs (146.630 GFLOP/tile, counted once) / step time, per GPU; "
-                             f"numerics={args.numerics}"},
         "clocks": clocks,
+    }
+    # roofline of the dominant kernel (the RDB conv5 instance: ~40 % of the step) from its live
+    # CUDA-event duration; the whole-step figure (all 357 launches) sits beside it
+    dom = next((k for k in kernels if k["layer"] == "rdb.conv5"), None)
+    line["roofline"] = {
+        "bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_source": peak_src,
+        "kernel": dom["kernel"] if dom else None,
+        "achieved": dom["tflops"] if dom else achieved_tflops,
+        "frac": (dom["tflops"] if dom else achieved_tflops) / peak,
+        "traffic": dom["traffic_bytes"] if dom else None,
+        "traffic_source": dom["traffic_source"] if dom else None,
+        "algorithmic_gflop_per_launch": dom["gflop"] if dom else None,
+        "us_per_launch": dom["us"] if dom else None,
+        "step": {"achieved": achieved_tflops, "frac": achieved_tflops / peak,
+                 "note": "algorithmic conv FLOPs of forward_feature (146.630 GFLOP/tile, counted once whatever the "
+                         "split-precision passes) / step time, per GPU"},
+        "kernels": kernels,
+        "note": f"numerics={args.numerics}; per-kernel durations: CUDA events around 50 back-to-back launches of the "
+                "layer shape at this batch on torch's current stream (the stream the library launches on), inputs "
+                "200 MB > L2; traffic = dram__bytes_read+write per launch from the committed ncu capture",
     }
     line.update(extras)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

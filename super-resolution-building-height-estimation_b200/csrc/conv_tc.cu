@@ -74,6 +74,9 @@ struct ConvTcKernelParams {
   int pdl;           // launched with programmatic stream serialization
   int desc_mode;
   int nomma;         // BHSR_TIMING builds only: skip the MMAs (measures the TMA supply rate alone)
+  // dx kernel: the tiles of an incomplete last round are dealt as single 128-row blocks so that
+  // twice as many SMs share them (item index split_round, CTAs [0, split_items)); -1 = off
+  int split_round, split_items, split_tile0;
   long long* dbg;  // optional [grid][8] cycle counters of the MMA warp (BHSR_DEBUG_TIMING)
 };
 
@@ -615,6 +618,19 @@ constexpr int kDxBars = 4 * kMaxAStages + 8 + 2 * kMaxWSlots;
 constexpr int kDxTailBytes = kDxBars * 8 + 16 + 2 * 64 * 4 + 64 + kDxStageBytes + kDxXchgFloats * 4;
 constexpr int kDxBlk = 126;                         // valid output rows per 128-row block
 
+// Work item `it` of this CTA: a whole tile (sel = -1) or, in the split last round, one block of it.
+__device__ __forceinline__ bool dx_item(const ConvTcKernelParams& p, int it, int& tile, int& sel) {
+  sel = -1;
+  if (p.split_round >= 0 && it >= p.split_round) {
+    if (it > p.split_round || static_cast<int>(blockIdx.x) >= p.split_items) return false;
+    tile = p.split_tile0 + (blockIdx.x >> 1);
+    sel = blockIdx.x & 1;
+    return true;
+  }
+  tile = blockIdx.x + it * gridDim.x;
+  return tile < p.total_tiles;
+}
+
 template <bool EXACT, int MB, bool WRES>
 __global__ void __launch_bounds__(kDxThreads, 1)
 conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
@@ -694,14 +710,13 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (warp != kDxWarpProdW) asm volatile("griddepcontrol.wait;" ::: "memory");
   }
 
-  const int first_tile = blockIdx.x;
-  const int tile_step = gridDim.x;
+  int tile, sel;
 
   if (warp == kDxWarpProdA) {
     // ------------------------------------------------ activation producer (hi ring, lo ring)
     if (lane == 0) {
       int sh = 0, ph_h = 1, sl = 0, ph_l = 1;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      for (int it = 0; dx_item(p, it, tile, sel); ++it) {
         const int t = tile % p.tiles_per_strip;
         const int sn = tile / p.tiles_per_strip;
         const int s = sn % p.n_strips;
@@ -729,7 +744,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (lane == 0) {
       uint32_t it = 0;
       const int slabs = p.n_chunks * 3;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      for (int item = 0; dx_item(p, item, tile, sel); ++item) {
         for (int sl = 0; sl < slabs; ++sl, ++it) {
           const int ws = WRES ? sl : static_cast<int>(it % p.wslots);
           if (!WRES) mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
@@ -754,17 +769,24 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     constexpr bool dbg = false;
 #endif
     uint32_t ok_h = 0, ok_l = 0, ok_w = 0;   // early-probe results (ok_w: one bit per window row)
-    const int my_tiles = (p.total_tiles - first_tile + tile_step - 1) / tile_step;
     const int n_chunks = p.n_chunks, cin = p.cin, wslots = p.wslots;
     int sh = 0, h_ph = 0, sl = 0, l_ph = 0;
     int ws_r = 0, w_ph = 0;
     constexpr uint32_t ASTEP = kDxBlk * RB16;       // descriptor units between the two blocks
-    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+    for (; dx_item(p, static_cast<int>(tile_it), tile, sel); ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int f0 = t * S_OUT;
       const int r0 = (f0 + kPitch - 1) / kPitch - 2;
       const int base_flat = f0 - r0 * kPitch;     // 67..132: tile-relative flat row of block 0, dy = 0
-      const bool more_tiles = tile_it + 1 < static_cast<uint32_t>(my_tiles);
+      bool more_tiles;
+      {
+        int t2, s2;
+        more_tiles = dx_item(p, static_cast<int>(tile_it) + 1, t2, s2);
+      }
+      // blocks of the tile this item covers: both, or only block `sel` (split last round)
+      const int mb_lo = sel < 0 ? 0 : sel;
+      const int mb_hi = sel < 0 ? MB : sel + 1;
+      const bool pair = (MB == 2) && sel < 0;
       // accumulator blocks of this tile (consecutive slots) and their barrier parities
       const uint32_t blk0 = tile_it * MB;
       const uint32_t slot0 = blk0 % NSLOT;
@@ -830,6 +852,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             // block-major around the accumulator hand-over
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
+              if (mb < mb_lo || mb >= mb_hi) continue;
               if (dbg) tq = clock64();
               mbar_wait(bar(B_TEMPTY + slot0 + mb), t_par ^ 1);
               if (dbg) t_tempty += clock64() - tq;
@@ -850,6 +873,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             if (first_chunk) {                     // fast numerics: 4 slots, no hand-over pressure
 #pragma unroll
               for (int mb = 0; mb < MB; ++mb) {
+                if (mb < mb_lo || mb >= mb_hi) continue;
                 if (dbg) tq = clock64();
                 mbar_wait(bar(B_TEMPTY + slot0 + mb), t_par ^ 1);
                 if (dbg) t_tempty += clock64() - tq;
@@ -862,16 +886,24 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #endif
 #pragma unroll
               for (int g = 0; g < 3; ++g) {
-                const uint32_t r = issue_dx<KST, MB, ASTEP>(
-                    a_h0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0, acc0 + COLS,
-                    IDESC_WIDE, (c > 0 || g > 0) ? 1u : 0u, hb1, hp1, EXACT ? hb1 : nbar[g],
-                    EXACT ? hp1 : npar[g]);
+                uint32_t r;
+                if (pair || MB == 1)
+                  r = issue_dx<KST, MB, ASTEP>(
+                      a_h0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0, acc0 + COLS,
+                      IDESC_WIDE, (c > 0 || g > 0) ? 1u : 0u, hb1, hp1, EXACT ? hb1 : nbar[g],
+                      EXACT ? hp1 : npar[g]);
+                else
+                  r = issue_dx<KST, 1, 0>(
+                      a_h0 + (g * kPitch + mb_lo * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi,
+                      acc0 + mb_lo * COLS, 0, IDESC_WIDE, (c > 0 || g > 0) ? 1u : 0u, hb1, hp1,
+                      EXACT ? hb1 : nbar[g], EXACT ? hp1 : npar[g]);
                 okbits |= (r & 1u) | ((r >> 1) << (1 + g));
               }
               if (!EXACT) {
                 if (last_chunk) {
 #pragma unroll
-                  for (int mb = 0; mb < MB; ++mb) umma_commit(bar(B_TFULL + slot0 + mb));
+                  for (int mb = 0; mb < MB; ++mb)
+                    if (mb >= mb_lo && mb < mb_hi) umma_commit(bar(B_TFULL + slot0 + mb));
                 }
                 if (!WRES) {
 #pragma unroll
@@ -903,6 +935,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             if (last_chunk) {
 #pragma unroll
               for (int mb = 0; mb < MB; ++mb) {
+                if (mb < mb_lo || mb >= mb_hi) continue;
                 if (elect_one()) {
 #ifdef BHSR_TIMING
                   if (!p.nomma)
@@ -913,7 +946,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                         a_l0 + (g * kPitch + mb * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi,
                         acc0 + mb * COLS + 96, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
                         nbar[g], npar[g]);
-                    if (mb == MB - 1) okbits |= (r & 1u) | ((r >> 1) << (1 + g));
+                    if (mb == mb_hi - 1) okbits |= (r & 1u) | ((r >> 1) << (1 + g));
                   }
                   umma_commit(bar(B_TFULL + slot0 + mb));
                 }
@@ -926,10 +959,17 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #endif
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                  const uint32_t r = issue_dx<KST, MB, ASTEP>(
-                      a_l0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0 + 96,
-                      acc0 + COLS + 96, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next), nbar[g],
-                      npar[g]);
+                  uint32_t r;
+                  if (pair || MB == 1)
+                    r = issue_dx<KST, MB, ASTEP>(
+                        a_l0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0 + 96,
+                        acc0 + COLS + 96, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next), nbar[g],
+                        npar[g]);
+                  else
+                    r = issue_dx<KST, 1, 0>(
+                        a_l0 + (g * kPitch + mb_lo * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi,
+                        acc0 + mb_lo * COLS + 96, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
+                        nbar[g], npar[g]);
                   okbits |= (r & 1u) | ((r >> 1) << (1 + g));
                 }
               }
@@ -974,13 +1014,14 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #ifdef BHSR_TIMING
     long long t_epi_wait = 0;
 #endif
-    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+    for (; dx_item(p, static_cast<int>(tile_it), tile, sel); ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int sn = tile / p.tiles_per_strip;
       const int s = sn % p.n_strips;
       const int n = sn / p.n_strips;
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
+        if (sel >= 0 && mb != sel) continue;             // split last round: one block of the tile
         const uint32_t blk = tile_it * MB + mb;
         if (static_cast<int>(blk & 1u) != grp) continue;   // warp-uniform
         const uint32_t slot = blk % NSLOT;
@@ -1328,6 +1369,17 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
+  // an incomplete last round that at most half the CTAs would work on is dealt block by block
+  p.split_round = -1; p.split_items = 0; p.split_tile0 = 0;
+  {
+    static const char* nosplit = getenv("BHSR_NO_SPLIT");
+    const int rounds = p.total_tiles / grid, rem = p.total_tiles % grid;
+    if (MB == 2 && rounds >= 1 && rem > 0 && 2 * rem <= grid && !(nosplit && nosplit[0] == '1')) {
+      p.split_round = rounds;
+      p.split_items = 2 * rem;
+      p.split_tile0 = rounds * grid;
+    }
+  }
   static const char* no_pdl = getenv("BHSR_NO_PDL");
   p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   if (p.w_resident) return launch_dx_kernel<EXACT, MB, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
@@ -1398,6 +1450,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   BHSR_REQUIRE(mb == 1 || mb == 2, "conv_tc: mblocks must be 1 or 2");
 
   ConvTcKernelParams p{};
+  p.split_round = -1;
   p.nb = d.nb; p.h = d.h; p.w = d.w;
   p.n_strips = (d.w + kStrip - 1) / kStrip;
   const int mt = 128 * mb;

@@ -38,6 +38,8 @@ def ncu_raw(rep):
     rows = list(csv.reader(txt.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     want = ["Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
             "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__m_xbar2l1tex_read_bytes.sum",
             "sm__cycles_elapsed.avg.per_second", "launch__registers_per_thread", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
@@ -67,15 +69,42 @@ def main():
         lines += ["", f"First RDB (conv1..conv5, us): {', '.join(first)}; conv_hr (last launch): {seq[-1][1]:.1f} us.", ""]
         rep = os.path.join(OUT, f"prof_rdb_{mode}.ncu-rep")
         if os.path.exists(rep):
-            lines += [f"### `ncu --set full` capture of 5 consecutive trunk convs ({mode})", "",
-                      "| kernel | us | tensor pipe active % | DRAM read MB | DRAM write MB | L2->SM MB | SM GHz | regs |", "|---|---|---|---|---|---|---|---|"]
-            for k in ncu_raw(rep):
+            lines += [f"### `ncu --set full` capture of 10 consecutive trunk convs ({mode})", "",
+                      "| layer | kernel | us | tensor pipe active % | smem tensor-read wavefronts % | smem bank writes % | DRAM read MB | DRAM write MB | L2->SM MB | L2 hit % | SM GHz | regs |",
+                      "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+            caps = ncu_raw(rep)
+            names = [re.sub(r"\(CUtensor.*", "", k.get("Kernel Name", ("", ""))[0]).replace("void bhsr::", "").replace("void ", "") for k in caps]
+            # conv5 is the only 64-output instance of the per-tap kernel inside the trunk: layers follow in order
+            i5 = next((i for i, n in enumerate(names) if n.startswith("conv_tc_kernel<64")), None)
+            layer_of = {}
+            if i5 is not None:
+                for i in range(len(caps)):
+                    layer_of[i] = "rdb.conv%d" % ((i - i5 - 1) % 5 + 1)
+            kjson = {}
+            for i, k in enumerate(caps):
                 g = lambda w: k.get(w, ("", ""))[0]
-                name = re.sub(r"\(CUtensor.*", "", g("Kernel Name")).replace("void bhsr::", "").replace("void ", "")
-                lines.append(f"| `{name}` | {g('gpu__time_duration.sum')} | {g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')} | "
-                             f"{g('dram__bytes_read.sum')} | {g('dram__bytes_write.sum')} | {g('l1tex__m_xbar2l1tex_read_bytes.sum')} | "
+                lay = layer_of.get(i, "?")
+                lines.append(f"| {lay} | `{names[i]}` | {g('gpu__time_duration.sum')} | {g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')} | "
+                             f"{g('l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed')} | {g('l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed')} | "
+                             f"{g('dram__bytes_read.sum')} | {g('dram__bytes_write.sum')} | {g('l1tex__m_xbar2l1tex_read_bytes.sum')} | {g('lts__t_sector_hit_rate.pct')} | "
                              f"{g('sm__cycles_elapsed.avg.per_second')} | {g('launch__registers_per_thread')} |")
+                try:
+                    unit_r = k.get("dram__bytes_read.sum", ("", ""))[1]
+                    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(unit_r, 1e6)
+                    dram = (float(g("dram__bytes_read.sum").replace(",", "")) + float(g("dram__bytes_write.sum").replace(",", ""))) * scale
+                    if lay != "?" and lay not in kjson:
+                        kjson[lay] = {"dram_bytes": dram, "us_under_ncu": float(g("gpu__time_duration.sum").replace(",", "")),
+                                      "tensor_pipe_active_pct": float(g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")),
+                                      "source": f"profiles/r01_summary.md (ncu --set full, {mode}, cold L2 per replay)"}
+                except ValueError:
+                    pass
             lines.append("")
+            allk = {}
+            kpath = os.path.join(PROF, "r01_ncu_kernels.json")
+            if os.path.exists(kpath):
+                allk = json.load(open(kpath))
+            allk[mode] = kjson
+            json.dump(allk, open(kpath, "w"), indent=1)
     for name in sorted(os.listdir(PROF)):
         if name.startswith("r01_bench") and name.endswith(".json"):
             try:

@@ -82,6 +82,10 @@ def run_case(name, desc_mode):
     cases["time_exact32_c32_ct192"] = dict(nb=64, cin=32, ctot=192, exact=True, mb=2, time=True)
     cases["time_fast64_ct64"] = dict(nb=64, cout=64, cin=64, ctot=64, mb=2, lrelu=False, time=True)
     cases["time_fast64_ct192"] = dict(nb=64, cout=64, cin=64, ctot=192, mb=2, lrelu=False, time=True)
+    cases["time_exact32_c96"] = dict(nb=64, cin=96, exact=True, mb=1, time=True)
+    cases["time_exact32_c96_mb2"] = dict(nb=64, cin=96, exact=True, mb=2, time=True)
+    cases["time_exact32_c128"] = dict(nb=64, cin=128, exact=True, mb=1, time=True)
+    cases["time_exact32_c128_mb2"] = dict(nb=64, cin=128, exact=True, mb=2, time=True)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
