@@ -74,7 +74,7 @@ struct ConvTcKernelParams {
   int pdl;           // launched with programmatic stream serialization
   int desc_mode;
   int nomma;         // BHSR_TIMING builds only: skip the MMAs (measures the TMA supply rate alone)
-  // dx kernel: the tiles of an incomplete last round are dealt as single 128-row blocks so that
+  // the tiles of an incomplete last round are dealt as single 128-row blocks so that
   // twice as many SMs share them (item index split_round, CTAs [0, split_items)); -1 = off
   int split_round, split_items, split_tile0;
   long long* dbg;  // optional [grid][8] cycle counters of the MMA warp (BHSR_DEBUG_TIMING)
@@ -223,6 +223,19 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
   }
 }
 
+// Work item `it` of this CTA: a whole tile (sel = -1) or, in the split last round, one block of it.
+__device__ __forceinline__ bool dx_item(const ConvTcKernelParams& p, int it, int& tile, int& sel) {
+  sel = -1;
+  if (p.split_round >= 0 && it >= p.split_round) {
+    if (it > p.split_round || static_cast<int>(blockIdx.x) >= p.split_items) return false;
+    tile = p.split_tile0 + (blockIdx.x >> 1);
+    sel = blockIdx.x & 1;
+    return true;
+  }
+  tile = blockIdx.x + it * gridDim.x;
+  return tile < p.total_tiles;
+}
+
 // WMODE: how the weights reach shared memory — 0: streamed, one window row (KS taps) per ring
 // slot; 1: streamed, a whole window (KS*KS taps) per slot; 2: resident (loaded once per CTA).
 template <int N, bool EXACT, int MB, int KS, int WMODE>
@@ -315,15 +328,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (warp != kWarpProdW) asm volatile("griddepcontrol.wait;" ::: "memory");
   }
 
-  const int first_tile = blockIdx.x;
-  const int tile_step = gridDim.x;
+  int tile, sel;   // work item: a tile, or (split last round) block `sel` of a tile
 
   if (warp == kWarpProdA) {
     // ------------------------------------------------ activation producer
     if (lane == 0) {
       uint32_t it = 0;
       int st = 0, ph = 1;  // empty barriers start "free": wait on the opposite parity
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      for (int item = 0; dx_item(p, item, tile, sel); ++item) {
         const int t = tile % p.tiles_per_strip;
         const int sn = tile / p.tiles_per_strip;
         const int s = sn % p.n_strips;
@@ -345,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (lane == 0) {
       uint32_t it = 0;
       const int slabs = p.n_chunks * NG;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      for (int item = 0; dx_item(p, item, tile, sel); ++item) {
         for (int sl = 0; sl < slabs; ++sl, ++it) {
           const int ws = WRES ? sl : static_cast<int>(it % p.wslots);
           if (!WRES) mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
@@ -382,12 +394,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     // (see issue_tap in ptx.cuh) and only a test that came back "not yet" falls through to the
     // blocking wait.
     uint32_t ok_t = 0, ok_a = 0, ok_w = 0;
-    const int my_tiles = (p.total_tiles - first_tile + tile_step - 1) / tile_step;
     const int n_chunks = p.n_chunks, cin = p.cin, shift0 = p.shift0, wslots = p.wslots;
     // ring positions are advanced incrementally (no integer division on the issue path)
     int st = 0, a_ph = 0;   // activation stage / phase parity
     int ws_r = 0, w_ph = 0; // weight slot / phase parity (streaming mode)
-    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+    for (; dx_item(p, static_cast<int>(tile_it), tile, sel); ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int flat_mod = (t * MT) % kPitch;
       const int as = tile_it & 1;
@@ -399,7 +410,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       ok_t = 0;
       tc_fence_after();
       const uint32_t acc = tmem_base + as * ACC_COLS;
-      const bool more_tiles = tile_it + 1 < static_cast<uint32_t>(my_tiles);
+      bool more_tiles;
+      {
+        int t2, s2;
+        more_tiles = dx_item(p, static_cast<int>(tile_it) + 1, t2, s2);
+      }
       const uint32_t bar_t_next = bar(B_TEMPTY + ((tile_it + 1) & 1));
       const uint32_t par_t_next = (((tile_it + 1) >> 1) & 1) ^ 1;
       uint32_t accumulate = 0;
@@ -463,8 +478,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #ifdef BHSR_TIMING
                 if (p.nomma) { if (tt < 3) okbits |= static_cast<uint32_t>(mbar_try_wait(pbar, ppar)) << tt; continue; }
 #endif
-                const uint32_t ok = issue_tap<EXACT, MB, KST, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N>(
-                    a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, tt > 0 ? 1u : accumulate, pbar, ppar);
+                uint32_t ok;
+                if (MB == 1 || sel < 0)
+                  ok = issue_tap<EXACT, MB, KST, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N>(
+                      a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, tt > 0 ? 1u : accumulate, pbar, ppar);
+                else  // split last round: only m-block `sel` of the tile
+                  ok = issue_tap<EXACT, 1, KST, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N>(
+                      a_lo + sel * 128 * RB16, b_lo, desc_hi, acc + sel * ROWS_B, IDESC_WIDE, IDESC_N,
+                      tt > 0 ? 1u : accumulate, pbar, ppar);
                 if (tt < 3) okbits |= ok << tt;
               }
               if (!WRES) umma_commit(bar(B_WEMPTY + ws));
@@ -505,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #ifdef BHSR_TIMING
     long long t_epi_wait = 0;
 #endif
-    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_it) {
+    for (; dx_item(p, static_cast<int>(tile_it), tile, sel); ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int sn = tile / p.tiles_per_strip;
       const int s = sn % p.n_strips;
@@ -521,6 +542,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       tc_fence_after();
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
+        if (sel >= 0 && mb != sel) continue;             // split last round: one m-block of the tile
         const int f = t * MT + mb * 128 + row;
         const int py = f / kPitch;
         const int pc = f - py * kPitch;
@@ -617,19 +639,6 @@ constexpr int kDxXchgFloats = 2 * 2 * 4 * 64;       // [group][parity][warp][v0 
 constexpr int kDxBars = 4 * kMaxAStages + 8 + 2 * kMaxWSlots;
 constexpr int kDxTailBytes = kDxBars * 8 + 16 + 2 * 64 * 4 + 64 + kDxStageBytes + kDxXchgFloats * 4;
 constexpr int kDxBlk = 126;                         // valid output rows per 128-row block
-
-// Work item `it` of this CTA: a whole tile (sel = -1) or, in the split last round, one block of it.
-__device__ __forceinline__ bool dx_item(const ConvTcKernelParams& p, int it, int& tile, int& sel) {
-  sel = -1;
-  if (p.split_round >= 0 && it >= p.split_round) {
-    if (it > p.split_round || static_cast<int>(blockIdx.x) >= p.split_items) return false;
-    tile = p.split_tile0 + (blockIdx.x >> 1);
-    sel = blockIdx.x & 1;
-    return true;
-  }
-  tile = blockIdx.x + it * gridDim.x;
-  return tile < p.total_tiles;
-}
 
 template <bool EXACT, int MB, bool WRES>
 __global__ void __launch_bounds__(kDxThreads, 1)
@@ -1132,6 +1141,24 @@ static long long* g_dbg_buf = nullptr;
 static constexpr int kStageBytes = 4 * 32 * 80;  // epilogue store-transpose staging
 static constexpr int kTailBytes = (2 * kMaxAStages + 4 + 2 * kMaxWSlots) * 8 + 16 + 2 * 64 * 4 + 64 + kStageBytes;
 
+// An incomplete last round that at most half the CTAs would work on is dealt block by block
+// (B = 64: 1088 tiles on 148 SMs = 7 rounds + 52 tiles -> 104 half-tiles; 8 rounds become 7.5).
+// A half-tile still loads the whole halo tile, so this only pays where the MMA stream, not the
+// activation supply, bounds the layer: exact numerics with >= 128 input channels (measured,
+// profiles/r01_split_last_round_v10.log: conv5 +3 %, conv4 +2 %; conv1 -5 %, fast numerics -11 %).
+static void set_split(ConvTcKernelParams& p, int grid, int mb, bool exact) {
+  p.split_round = -1; p.split_items = 0; p.split_tile0 = 0;
+  static const char* nosplit = getenv("BHSR_NO_SPLIT");
+  static const char* allsplit = getenv("BHSR_SPLIT_ALL");
+  const bool pays = (exact && p.cin >= 128) || (allsplit && allsplit[0] == '1');
+  const int rounds = p.total_tiles / grid, rem = p.total_tiles % grid;
+  if (mb == 2 && pays && rounds >= 1 && rem > 0 && 2 * rem <= grid && !(nosplit && nosplit[0] == '1')) {
+    p.split_round = rounds;
+    p.split_items = 2 * rem;
+    p.split_tile0 = rounds * grid;
+  }
+}
+
 static int make_act_map(CUtensorMap* tm, const void* base, int nb, int h, int w, int ctot,
                         int box_rows, int ch) {
   EncodeTiledFn enc = get_encode_tiled();
@@ -1266,6 +1293,7 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
   if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
+  set_split(p, grid, MB, EXACT);
   static const char* no_pdl = getenv("BHSR_NO_PDL");
   p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   if (wmode == 2) return launch_kernel<N, EXACT, MB, KS, 2>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
@@ -1369,17 +1397,7 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
-  // an incomplete last round that at most half the CTAs would work on is dealt block by block
-  p.split_round = -1; p.split_items = 0; p.split_tile0 = 0;
-  {
-    static const char* nosplit = getenv("BHSR_NO_SPLIT");
-    const int rounds = p.total_tiles / grid, rem = p.total_tiles % grid;
-    if (MB == 2 && rounds >= 1 && rem > 0 && 2 * rem <= grid && !(nosplit && nosplit[0] == '1')) {
-      p.split_round = rounds;
-      p.split_items = 2 * rem;
-      p.split_tile0 = rounds * grid;
-    }
-  }
+  set_split(p, grid, MB, EXACT);
   static const char* no_pdl = getenv("BHSR_NO_PDL");
   p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   if (p.w_resident) return launch_dx_kernel<EXACT, MB, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);

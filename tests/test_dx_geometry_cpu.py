@@ -1,0 +1,93 @@
+"""Host-side restatement of the index arithmetic of the dx-in-N kernel (conv_tc.cu: conv_dx_kernel,
+dx_item, set_split) checked exhaustively on CPU: every output pixel of an image is produced by
+exactly one (tile, block, row), every shared-memory row an MMA touches lies inside the halo tile
+TMA delivered, and the split last round deals every tile exactly once."""
+import itertools
+
+import pytest
+
+PITCH, STRIP, BLK = 66, 64, 126          # kPitch, kStrip, kDxBlk
+
+
+def tile_rows(mb):                       # TileGeom<MB, CH>::kRows
+    return 5 if mb == 1 else 7
+
+
+def tile_geometry(t, mb):
+    """(r0, base_flat) of tile t: first image row of the TMA box, tile-relative flat row of
+    block 0 / dy = 0 (conv_dx_kernel, MMA warp)."""
+    f0 = t * BLK * mb
+    r0 = (f0 + PITCH - 1) // PITCH - 2
+    return f0, r0, f0 - r0 * PITCH
+
+
+@pytest.mark.parametrize("h,mb", [(64, 2), (64, 1), (40, 2), (7, 1), (2, 2), (256, 2), (23, 1)])
+def test_every_pixel_once_and_operands_inside_the_halo_tile(h, mb):
+    s_out = BLK * mb
+    tiles = (h * PITCH + s_out - 1) // s_out
+    seen = {}
+    for t in range(tiles):
+        f0, r0, base = tile_geometry(t, mb)
+        assert 67 <= base <= 132
+        for b in range(mb):
+            # operand rows of the three window rows: smem flat = base + 126 b + dy*66 + r, r in [0,128)
+            lo = base + BLK * b - PITCH
+            hi = base + BLK * b + PITCH + 127
+            assert lo >= 1 and hi < tile_rows(mb) * PITCH, (t, b, lo, hi)
+            for r in range(1, BLK + 1):              # rows 0 and 127 belong to the neighbours
+                f = f0 - 1 + BLK * b + r
+                py, pc = divmod(f, PITCH)
+                if pc < STRIP and py < h:
+                    assert (py, pc) not in seen
+                    seen[(py, pc)] = (t, b, r)
+                    # the A row of tap (dy, dx) is image pixel (py+dy, pc+dx): smem column pc+dx+1
+                    for dy, dx in itertools.product((-1, 0, 1), repeat=2):
+                        a_row = base + BLK * b + dy * PITCH + (r + dx)      # block row r+dx, shift dy
+                        srow, scol = divmod(a_row, PITCH)
+                        assert (srow + r0, scol - 1) == (py + dy, pc + dx)
+    assert len(seen) == h * STRIP
+
+
+def dx_item(it, cta, grid, total, split_round, split_items, split_tile0):
+    """conv_tc.cu: dx_item."""
+    if split_round >= 0 and it >= split_round:
+        if it > split_round or cta >= split_items:
+            return None
+        return split_tile0 + (cta >> 1), cta & 1
+    tile = cta + it * grid
+    return (tile, -1) if tile < total else None
+
+
+def set_split(total, grid, mb, pays=True):
+    """conv_tc.cu: set_split."""
+    rounds, rem = divmod(total, grid)
+    if mb == 2 and pays and rounds >= 1 and rem > 0 and 2 * rem <= grid:
+        return rounds, 2 * rem, rounds * grid
+    return -1, 0, 0
+
+
+@pytest.mark.parametrize("total,grid", [(1088, 148), (51, 40), (34, 24), (34, 5), (148, 148), (149, 148), (200, 148),
+                                         (10, 148), (296, 148), (1000, 7)])
+def test_split_last_round_deals_every_block_once(total, grid):
+    grid = min(grid, total)
+    sr, si, st0 = set_split(total, grid, 2)
+    work = {}
+    most = 0
+    for cta in range(grid):
+        it, blocks = 0, 0
+        while True:
+            item = dx_item(it, cta, grid, total, sr, si, st0)
+            if item is None:
+                break
+            tile, sel = item
+            for b in ((0, 1) if sel < 0 else (sel,)):
+                assert (tile, b) not in work
+                work[(tile, b)] = cta
+                blocks += 1
+            if sel >= 0:      # a half-tile is always the CTA's last item (accumulator parities rely on it)
+                assert dx_item(it + 1, cta, grid, total, sr, si, st0) is None
+            it += 1
+        most = max(most, blocks)
+    assert len(work) == 2 * total
+    if sr >= 0:               # the split saves half a round
+        assert most == 2 * (total // grid) + 1

@@ -71,7 +71,7 @@ def test_conv_tc_vs_oracle(dev, numerics, rtol, atol, cin, cout, h, w, nb):
 @pytest.mark.parametrize("numerics,rtol,atol", [("exact", 1e-3, 1e-4), ("fast", 2e-2, 2e-2)])
 @pytest.mark.parametrize("cin,h,w,nb,mb,max_ctas", [(64, 64, 64, 3, 2, 0), (64, 64, 64, 3, 1, 0), (160, 64, 64, 2, 2, 5),
                                                      (96, 23, 130, 2, 2, 3), (128, 2, 64, 1, 1, 0), (32, 64, 64, 1, 2, 1),
-                                                     (64, 64, 64, 3, 2, 40), (96, 64, 64, 2, 2, 24)])
+                                                     (128, 64, 64, 3, 2, 40), (160, 64, 64, 2, 2, 24)])
 def test_conv_dx_kernel_vs_per_tap_and_oracle(dev, numerics, rtol, atol, cin, h, w, nb, mb, max_ctas):
     """The dx-in-N kernel (three dx taps stacked along N, lane-shift combine; conv_tc.cu) against the
     per-tap kernel (desc_mode bit 8) and the oracle, for both block pairings, few CTAs (max_ctas;
