@@ -596,6 +596,283 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 }
 
 // ======================================================================================
+// conv_pair_kernel — the 64-output exact-numerics 3x3 conv (conv5 of every RDB, conv_body) on CTA
+// PAIRS (`tcgen05.mma.cta_group::2`, M = 256 across two SMs).
+//
+// The per-tap kernel is shared-memory-bandwidth bound on this layer: 14.3 KB of
+// operand reads per MMA pair plus the TMA writes of activations and streamed weights all go
+// through one 128 B/clk port.  In a pair each CTA keeps its own tile (activation rings,
+// accumulators, epilogue — image 2m+rank, same tile index, so one A descriptor serves both) but
+// only HALF of every weight tile: the N = 128 hi-activation MMA takes W_hi from the even CTA and
+// W_lo' from the odd one, the N = 64 lo'-activation MMA takes W_hi rows 0-31 / 32-63.  Weight
+// bytes per SM (TMA writes and MMA reads) drop by 25 % / 50 %.
+// Protocol: the even CTA (leader) issues every MMA; all "full" barriers live in the leader and
+// receive the TMA bytes of both CTAs (`cp.async.bulk.tensor...cta_group::2`); `tcgen05.commit
+// ...multicast::cluster` releases stages / publishes accumulators in both CTAs; the odd CTA's
+// epilogue threads arrive on the leader's accumulator-free barrier through the cluster window.
+constexpr int kPairWTap = 96 * 64;                 // per CTA and tap: 64 rows (X) + 32 rows (Y) of 64 B
+constexpr int kPairWSlab = 3 * kPairWTap;          // one window row (3 taps)
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+                 const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_w, const ConvTcKernelParams p) {
+  constexpr int N = 64, MB = 2, KS = 3, CH = 32;
+  using G = TileGeom<MB, CH>;
+  constexpr int RB = G::kRowBytes;                 // 64
+  constexpr int RB16 = RB / 16;
+  constexpr int ROWS_B = 2 * N;                    // TMEM columns per m-block (main | correction)
+  constexpr int A_STAGE = G::kTileBytes * 2;
+  constexpr int A_TX = G::kTileBytesRaw * 2;
+  constexpr int ACC_COLS = MB * ROWS_B;
+  constexpr int MT = 128 * MB;
+  constexpr uint32_t IDESC_WIDE = make_idesc_f16(ROWS_B, 256);
+  constexpr uint32_t IDESC_N = make_idesc_f16(N, 256);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_base = smem_base;
+  const int NS = p.astages;
+  const uint32_t w_base = a_base + NS * A_STAGE;
+  uint8_t* tail = smem + NS * A_STAGE + p.wslots * kPairWSlab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  auto bar = [&](int i) { return smem_u32(bars + i); };
+  constexpr int B_AFULL = 0, B_AEMPTY = kMaxAStages, B_TFULL = 2 * kMaxAStages,
+                B_TEMPTY = B_TFULL + 2, B_WFULL = B_TFULL + 4;
+  const int B_WEMPTY = B_WFULL + kMaxWSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_WFULL + 2 * kMaxWSlots);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_scale = s_bias + 64;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_scale + 64);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxAStages; ++i) {
+      mbar_init(bar(B_AFULL + i), 1);     // leader: one expect_tx arrive, bytes of both CTAs
+      mbar_init(bar(B_AEMPTY + i), 1);    // multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(B_TFULL + i), 1);     // multicast commit
+      mbar_init(bar(B_TEMPTY + i), 256);  // leader: the epilogue threads of both CTAs
+    }
+    for (int i = 0; i < p.wslots; ++i) {
+      mbar_init(bar(B_WFULL + i), 1);
+      mbar_init(bar(B_WEMPTY + i), 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (threadIdx.x < N) {
+    s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+  }
+  if (warp == kWarpMma) {
+    tmem_alloc2(smem_u32(tmem_slot), 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                     // both CTAs' barriers exist before anything is signalled
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_clusters = gridDim.x >> 1;
+  const int cl = blockIdx.x >> 1;
+  // work item `it` of this pair: a whole pair-tile (sel = -1) or, in the split last round, one
+  // m-block of it (cf. dx_item)
+  auto item = [&](int it, int& q, int& sel) {
+    sel = -1;
+    if (p.split_round >= 0 && it >= p.split_round) {
+      if (it > p.split_round || cl >= p.split_items) return false;
+      q = p.split_tile0 + (cl >> 1);
+      sel = cl & 1;
+      return true;
+    }
+    q = cl + it * n_clusters;
+    return q < p.total_tiles;
+  };
+  int q, sel;
+  // pair-tile q -> (image pair, strip, tile); this CTA takes image 2m + rank
+  auto decode = [&](int q, int& t, int& s, int& n) {
+    t = q % p.tiles_per_strip;
+    const int sn = q / p.tiles_per_strip;
+    s = sn % p.n_strips;
+    n = 2 * (sn / p.n_strips) + static_cast<int>(rank);
+  };
+
+  if (warp == kWarpProdA) {
+    // ------------------------------------------------ activation producer (both CTAs)
+    if (lane == 0) {
+      int st = 0, ph = 1;
+      for (int it = 0; item(it, q, sel); ++it) {
+        int t, s, n;
+        decode(q, t, s, n);
+        const int r0 = (t * MT) / kPitch - 1;
+        for (int c = 0; c < p.n_chunks; ++c, st = (st + 1 == NS ? 0 : st + 1), ph ^= (st == 0)) {
+          mbar_wait_cluster(bar(B_AEMPTY + st), ph);
+          if (leader) mbar_expect_tx(bar(B_AFULL + st), 2 * A_TX);
+          const uint32_t dst = a_base + st * A_STAGE;
+          tma_load_4d_2sm(dst, &tm_a_hi, bar(B_AFULL + st), p.in_choff + c * CH, s * kStrip - 1, r0, n);
+          tma_load_4d_2sm(dst + G::kTileBytes, &tm_a_lo, bar(B_AFULL + st), p.in_choff + c * CH,
+                          s * kStrip - 1, r0, n);
+        }
+      }
+    }
+  } else if (warp == kWarpProdW) {
+    // ------------------------------------------------ weight producer (both CTAs, half the rows each)
+    // packed rows of tap T: [T*128, +64) = W_hi, [T*128+64, +64) = W_lo'.  This CTA: X = its 64-row
+    // part of the wide operand (two 32-row boxes), Y = W_hi rows [rank*32, +32) for the narrow one.
+    if (lane == 0) {
+      uint32_t it = 0;
+      const int slabs = p.n_chunks * 3;
+      for (int wi = 0; item(wi, q, sel); ++wi) {
+        for (int sl = 0; sl < slabs; ++sl, ++it) {
+          const int ws = static_cast<int>(it % p.wslots);
+          mbar_wait_cluster(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
+          if (leader) mbar_expect_tx(bar(B_WFULL + ws), 2 * kPairWSlab);
+#pragma unroll
+          for (int tt = 0; tt < 3; ++tt) {
+            const int row0 = (sl * 3 + tt) * 128;
+            const uint32_t dst = w_base + ws * kPairWSlab + tt * kPairWTap;
+            tma_load_2d_2sm(dst, &tm_w, bar(B_WFULL + ws), 0, row0 + static_cast<int>(rank) * 64);
+            tma_load_2d_2sm(dst + 2048, &tm_w, bar(B_WFULL + ws), 0, row0 + static_cast<int>(rank) * 64 + 32);
+            tma_load_2d_2sm(dst + 4096, &tm_w, bar(B_WFULL + ws), 0, row0 + static_cast<int>(rank) * 32);
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      const uint64_t desc0 = make_kmajor_desc<RB>(0);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
+      uint32_t tile_it = 0;
+      uint32_t ok_a = 0, ok_w = 0;
+      const int n_chunks = p.n_chunks, shift0 = p.shift0, wslots = p.wslots;
+      int st = 0, a_ph = 0;
+      int ws_r = 0, w_ph = 0;
+      for (; item(static_cast<int>(tile_it), q, sel); ++tile_it) {
+        const int t = q % p.tiles_per_strip;
+        const int flat_mod = (t * MT) % kPitch;
+        const int as = tile_it & 1;
+        mbar_wait_cluster(bar(B_TEMPTY + as), ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * ACC_COLS;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+          if (!ok_a) mbar_wait_cluster(bar(B_AFULL + st), a_ph);
+          ok_a = 0;
+          tc_fence_after();
+          int st_next = st + 1, a_ph_next = a_ph;
+          if (st_next == NS) { st_next = 0; a_ph_next ^= 1; }
+          const uint32_t bar_a_next = bar(B_AFULL + st_next);
+          const uint32_t a_lo0 = desc_lo0 + (((a_base + st * A_STAGE) >> 4) & 0x3FFF) +
+                                 (flat_mod + kPitch + 1 + shift0) * RB16;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const int ws = ws_r;
+            if (!ok_w) mbar_wait_cluster(bar(B_WFULL + ws), w_ph);
+            ok_w = 0;
+            tc_fence_after();
+            if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }
+            const uint32_t bar_w_next = bar(B_WFULL + ws_r);
+            const uint32_t par_w_next = w_ph;
+            const uint32_t b_lo0 = desc_lo0 + (((w_base + ws * kPairWSlab) >> 4) & 0x3FFF);
+            uint32_t okbits = 0;
+            if (elect_one()) {
+#pragma unroll
+              for (int tt = 0; tt < 3; ++tt) {
+                const uint32_t a_lo = a_lo0 + (g * kPitch + tt) * RB16;
+                const uint32_t b_lo = b_lo0 + tt * (kPairWTap >> 4);
+                const uint32_t pbar = tt == 0 ? bar_w_next : bar_a_next;
+                const uint32_t ppar = tt == 0 ? par_w_next : static_cast<uint32_t>(a_ph_next);
+                uint32_t ok;
+                if (sel < 0)
+                  ok = issue_tap_pair<2, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N, (4096 >> 4)>(
+                      a_lo, b_lo, desc_hi, acc, IDESC_WIDE, IDESC_N, tt > 0 ? 1u : accumulate, pbar, ppar);
+                else
+                  ok = issue_tap_pair<1, 128 * RB16, (G::kTileBytes >> 4), ROWS_B, N, (4096 >> 4)>(
+                      a_lo + sel * 128 * RB16, b_lo, desc_hi, acc + sel * ROWS_B, IDESC_WIDE, IDESC_N,
+                      tt > 0 ? 1u : accumulate, pbar, ppar);
+                if (tt < 2) okbits |= ok << tt;
+              }
+              umma_commit2(bar(B_WEMPTY + ws));
+            }
+            okbits = __reduce_or_sync(0xffffffffu, okbits);
+            ok_w = okbits & 1u;
+            if (g == 2) ok_a = (okbits >> 1) & 1u;
+            accumulate = 1;
+          }
+          if (elect_one()) umma_commit2(bar(B_AEMPTY + st));
+          __syncwarp();
+          st = st_next;
+          a_ph = a_ph_next;
+        }
+        if (elect_one()) umma_commit2(bar(B_TFULL + as));
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 0..3, both CTAs)
+    const int qd = warp;
+    const int row = qd * 32 + lane;
+    uint32_t tile_it = 0;
+    for (; item(static_cast<int>(tile_it), q, sel); ++tile_it) {
+      int t, s, n;
+      decode(q, t, s, n);
+      const int as = tile_it & 1;
+      mbar_wait_cluster(bar(B_TFULL + as), (tile_it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        if (sel >= 0 && mb != sel) continue;             // split last round: one m-block of the tile
+        const int f = t * MT + mb * 128 + row;
+        const int py = f / kPitch;
+        const int pc = f - py * kPitch;
+        const int px = s * kStrip + pc;
+        const bool valid = (pc < kStrip) && (py < p.h) && (px < p.w) && (n < p.nb);
+        const size_t in_pix = (static_cast<size_t>(n) * p.h + py) * p.w + px;
+        const int oy = py * p.out_scale + p.out_oy;
+        const int ox = px * p.out_scale + p.out_ox;
+        const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + as * ACC_COLS + mb * ROWS_B;
+#pragma unroll
+        for (int cc = 0; cc < N / 32; ++cc) {
+          uint32_t raw[32], rawl[32];
+          float v[32];
+          tmem_ld_32x32(t_row + cc * 32, raw);
+          tmem_ld_32x32(t_row + N + cc * 32, rawl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaf(__uint_as_float(rawl[j]), 1.f / 2048.f, __uint_as_float(raw[j]));
+          finish_slice32(p, v, cc, valid, n, py, px, in_pix, out_pix, oy, ox, warp, lane,
+                         (p.epilogue & BHSR_EPI_OUT_NCHW_F32) != 0, s_stage, s_bias, s_scale);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_leader(bar(B_TEMPTY + as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                     // the leader's shared memory / barriers outlive every remote arrive
+  if (warp == kWarpMma) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// ======================================================================================
 // conv_dx_kernel — "dx-in-N" variant of the tap conv for the 32-output-channel 3x3 layers
 // (conv1..conv4 of every ResidualDenseBlock, SR/rrdbnet_arch.py:137-140).
 //
@@ -1404,6 +1681,62 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   return launch_dx_kernel<EXACT, MB, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
 }
 
+// CTA-pair launch for the 64-output exact 3x3 layers (even batch, plane or NCHW output).
+static int launch_pair(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream, bool* launched) {
+  using G = TileGeom<2, 32>;
+  constexpr int A_STAGE = G::kTileBytes * 2;
+  *launched = false;
+  const int astages = 2;
+  int wslots = (kSmemLimit - 1024 - astages * A_STAGE - kTailBytes) / kPairWSlab;
+  if (wslots > kMaxWSlots) wslots = kMaxWSlots;
+  if (wslots < 4) return 0;
+  auto kern = conv_pair_kernel;
+  static int max_clusters = -1;
+  const int smem_bytes = 1024 + astages * A_STAGE + wslots * kPairWSlab + kTailBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BHSR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    int sms = device_sm_count();
+    cfg.gridDim = dim3(sms > 1 ? sms / 2 * 2 : 2);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    max_clusters = n;
+  }
+  if (max_clusters < 8) return 0;          // pairs cannot be co-scheduled here: use the per-tap kernel
+  p.tiles_per_strip = (d.h * kPitch + 255) / 256;
+  p.total_tiles = (d.nb / 2) * p.n_strips * p.tiles_per_strip;   // pair-tiles
+  p.wslots = wslots;
+  p.astages = astages;
+  p.w_resident = 0;
+  p.pdl = 0;
+  CUtensorMap tm_hi, tm_lo, tm_w;
+  int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, 32);
+  if (rc) return rc;
+  rc = make_act_map(&tm_lo, d.in_lo, d.nb, d.h, d.w, d.in_ctot, G::kRows, 32);
+  if (rc) return rc;
+  rc = make_weight_map(&tm_w, d.w_packed, p.n_chunks * 9 * 128, 32, 32);
+  if (rc) return rc;
+  int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
+  if (d.max_ctas > 1 && clusters > d.max_ctas / 2) clusters = d.max_ctas / 2;
+  set_split(p, clusters, 2, true);         // in units of pair-tiles and clusters
+  cfg.gridDim = dim3(2 * clusters);
+  BHSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));
+  *launched = true;
+  return 0;
+}
+
 }  // namespace bhsr
 
 using namespace bhsr;
@@ -1516,6 +1849,20 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
     if (use_dx && d.cout == 32 && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2)) {
       if (exact) return mb == 2 ? launch_dx<true, 2>(d, p, stream) : launch_dx<true, 1>(d, p, stream);
       return mb == 2 ? launch_dx<false, 2>(d, p, stream) : launch_dx<false, 1>(d, p, stream);
+    }
+  }
+
+  // 64-output exact 3x3 layers on an even batch: CTA pairs (BHSR_PAIR=0 or desc_mode bit 9 keep the per-tap kernel)
+  {
+    static const char* pr = getenv("BHSR_PAIR");
+    const bool use_pair = !(pr && pr[0] == '0') && !(d.desc_mode & 0x200);
+    if (use_pair && exact && d.cout == 64 && ks == 3 && mb == 2 && d.nb % 2 == 0 && d.cin % 32 == 0 &&
+        !(d.epilogue & BHSR_EPI_SHUFFLE2)) {
+      bool launched = false;
+      int rc = launch_pair(d, p, stream, &launched);
+      if (rc || launched) return rc;
+      p.tiles_per_strip = (d.h * kPitch + mt - 1) / mt;            // fall back: restore the per-tap tiling
+      p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;
     }
   }
 

@@ -200,8 +200,8 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t start) {
   return d;
 }
 // Instruction descriptor, kind::f16: fp16 A/B (K-major), fp32 D, M=128, N given.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
-  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 
@@ -306,6 +306,120 @@ __device__ __forceinline__ uint32_t issue_dx(uint32_t a_lo, uint32_t b_lo, uint3
   else if constexpr (KST == 1 && NB == 1) BHSR_DX_ASM(BHSR_DX_B1("%5"));
   else static_assert(KST < 0, "unsupported issue_dx variant");
   return ok1 | (ok2 << 1);
+}
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// PTX forms follow CUTLASS (cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp, cutlass/arch/barrier.h).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the pair's even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive (once every prior tcgen05 op of this thread completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// TMA tile loads into THIS CTA's shared memory that report their bytes to the pair leader's barrier
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                                int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the pair leader's barrier from either CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("bhsr: cluster mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  }
+}
+
+// One filter tap of the exact-numerics pair kernel: for each of the two m-blocks and KST k-steps a
+// wide MMA (hi activations x [W_hi | W_lo'], the two halves of N living in the two CTAs) and a
+// narrow one (lo' activations x W_hi into the correction columns), M = 256 across the CTA pair.
+#define BHSR_P_PRE                                                                     \
+  "{\n.reg .pred pacc, ptrue, pw;\n.reg .b32 alo, blo, bn, d, dn, al2;\n.reg .b64 da, db, dl;\n" \
+  "setp.ne.b32 pacc, %7, 0;\nsetp.eq.b32 ptrue, 0, 0;\n"                               \
+  "mbarrier.test_wait.parity.shared::cta.b64 pw, [%8], %9;\n"                          \
+  "mov.b32 alo, %1;\nmov.b32 blo, %2;\nmov.b32 d, %4;\n"
+#define BHSR_P_STEP(ACC)                                                               \
+  "mov.b64 da, {alo, %3};\nmov.b64 db, {blo, %3};\n"                                   \
+  "tcgen05.mma.cta_group::2.kind::f16 [d], da, db, %5, " ACC ";\n"                     \
+  "add.u32 al2, alo, %11;\nmov.b64 dl, {al2, %3};\nadd.u32 dn, d, %13;\n"              \
+  "add.u32 bn, blo, %15;\nmov.b64 db, {bn, %3};\n"                                     \
+  "tcgen05.mma.cta_group::2.kind::f16 [dn], dl, db, %6, ptrue;\n"                      \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_P_NEXT "add.u32 alo, alo, %10;\nsub.u32 blo, blo, %14;\nadd.u32 d, d, %12;\n"
+#define BHSR_P_POST "selp.u32 %0, 1, 0, pw;\n}\n"
+// KST = 2, NB m-blocks (2, or 1 in the split last round); BY16 = descriptor units from a tap's wide
+// operand to its narrow operand
+template <int NB, int MBS16, int LO16, int ROWS, int NN, int BY16>
+__device__ __forceinline__ uint32_t issue_tap_pair(uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t d_acc,
+                                                   uint32_t idesc_wide, uint32_t idesc_n, uint32_t acc_first,
+                                                   uint32_t probe_bar, uint32_t probe_parity) {
+  uint32_t ok;
+  constexpr int KST = 2;
+  if constexpr (NB == 2)
+    asm volatile(BHSR_P_PRE BHSR_P_STEP("pacc") BHSR_P_STEP("ptrue") BHSR_P_NEXT BHSR_P_STEP("pacc")
+                     BHSR_P_STEP("ptrue") BHSR_P_POST
+                 : "=r"(ok)
+                 : "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(d_acc), "r"(idesc_wide), "r"(idesc_n), "r"(acc_first),
+                   "r"(probe_bar), "r"(probe_parity), "n"(MBS16 - 2 * KST), "n"(LO16), "n"(ROWS), "n"(NN),
+                   "n"(2 * KST), "n"(BY16)
+                 : "memory");
+  else
+    asm volatile(BHSR_P_PRE BHSR_P_STEP("pacc") BHSR_P_STEP("ptrue") BHSR_P_POST
+                 : "=r"(ok)
+                 : "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(d_acc), "r"(idesc_wide), "r"(idesc_n), "r"(acc_first),
+                   "r"(probe_bar), "r"(probe_parity), "n"(MBS16 - 2 * KST), "n"(LO16), "n"(ROWS), "n"(NN),
+                   "n"(2 * KST), "n"(BY16)
+                 : "memory");
+  return ok;
 }
 
 }  // namespace bhsr

@@ -106,6 +106,44 @@ def test_conv_dx_kernel_vs_per_tap_and_oracle(dev, numerics, rtol, atol, cin, h,
     assert_close(outs[0], outs[1], rtol, atol, "dx vs per-tap")
 
 
+@pytest.mark.parametrize("cin,nb,h,w,max_ctas,nchw", [(192, 6, 64, 64, 80, False), (64, 2, 40, 130, 0, False),
+                                                       (192, 4, 64, 64, 6, False), (64, 2, 128, 128, 0, True)])
+def test_conv_pair_kernel_vs_per_tap_and_oracle(dev, cin, nb, h, w, max_ctas, nchw):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2, each CTA holds half of every weight tile;
+    conv_tc.cu: conv_pair_kernel) against the per-tap kernel (desc_mode bit 9) and the oracle: a split
+    last round (80 CTAs), several strips / ragged height, few clusters, and the fp32 NCHW output."""
+    from bhsr import ops
+    from bhsr._lib import NUMERICS_EXACT
+    rng = np.random.RandomState(cin + nb + h)
+    x = (rng.rand(nb, cin, h, w) * 2 - 0.5).astype(np.float32)
+    wt = (rng.standard_normal((64, cin, 3, 3)) * (0.5 / np.sqrt(cin * 9))).astype(np.float32)
+    b = (rng.standard_normal(64) * 0.1).astype(np.float32)
+    r1 = rng.standard_normal((nb, 64, h, w)).astype(np.float32)
+    conv = R.conv2d(x, wt, b, padding=1, acc_dtype=np.float64)
+    ref = conv if nchw else conv * 0.2 + r1
+    hi, lo = _planes(x, 192, dev)
+    rhi, rlo = _planes(r1, 64, dev)
+    wp = ops.pack_conv_weights(cuda(wt, dev), NUMERICS_EXACT)
+    outs = []
+    for mode in (0, 0x200):
+        if nchw:
+            out = torch.zeros((nb, 64, h, w), device=dev)
+            ops.conv_tc(hi, lo, 0, cin, wp, 64, cuda(b, dev), ops.PLAIN_TAPS, None, None, out_f32=out,
+                        numerics=NUMERICS_EXACT, mblocks=2, max_ctas=max_ctas, desc_mode=mode)
+            outs.append(out.cpu().numpy())
+        else:
+            out_hi = torch.zeros((nb, h, w, 64), dtype=torch.float16, device=dev)
+            out_lo = torch.zeros_like(out_hi)
+            ops.conv_tc(hi, lo, 0, cin, wp, 64, cuda(b, dev), ops.PLAIN_TAPS, out_hi, out_lo, out_choff=0,
+                        res1=(rhi, rlo, 0), alpha1=0.2, numerics=NUMERICS_EXACT, mblocks=2, max_ctas=max_ctas,
+                        desc_mode=mode)
+            outs.append(ops.planes_to_nchw(out_hi, out_lo, 64, 0).cpu().numpy())
+    assert_close(outs[0], ref, what=f"pair kernel {cin}->64")
+    assert_close(outs[1], ref, what=f"per-tap kernel {cin}->64")
+    # same products in the same order: the two kernels agree to rounding of the last accumulation
+    assert_close(outs[0], outs[1], 1e-5, 1e-6, "pair vs per-tap")
+
+
 def test_conv_tc_residual_epilogues(dev):
     """conv5 of rdb3: (conv*0.2 + x)*0.2 + rrdb_in  (rrdbnet_arch.py:143,167)."""
     from bhsr import ops
