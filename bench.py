@@ -170,7 +170,8 @@ def layer_kernels_live(dev, B, numerics):
         gflop = 2.0 * B * 64 * 64 * cout * cin * 9 / 1e9
         name = f"rdb.conv{c + 1}"
         t = traffic.get(name, {})
-        res.append({"layer": name, "kernel": ("conv_dx_kernel" if c < 4 else "conv_tc_kernel") + f"<{numerics}>",
+        kname = "conv_dx_kernel" if c < 4 else ("conv_pair_kernel" if numerics == "exact" and B % 2 == 0 else "conv_tc_kernel")
+        res.append({"layer": name, "kernel": kname + f"<{numerics}>",
                     "shape": f"{cin}->{cout} 3x3 @64x64 x{B}", "us": us, "gflop": gflop,
                     "tflops": gflop / (us * 1e-6) / 1e3,
                     "launches_per_step": 69, "traffic_bytes": t.get("dram_bytes"),
@@ -360,7 +361,7 @@ def main():
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
     }
-    # roofline of the dominant kernel (the RDB conv5 instance: ~40 % of the step) from its live
+    # roofline of the dominant kernel (the RDB conv5 instance, CTA-pair kernel: ~38 % of the step) from its live
     # CUDA-event duration; the whole-step figure (all 357 launches) sits beside it
     dom = next((k for k in kernels if k["layer"] == "rdb.conv5"), None)
     line["roofline"] = {

@@ -94,7 +94,8 @@ typedef struct BhsrConvTcDesc {
   int32_t max_ctas;         /* 0 = one CTA per SM */
   int32_t desc_mode;        /* 0 = default; bit 8 (0x100) forces the per-tap kernel for 32-output layers
                              * (default: the dx-in-N kernel); bit 9 (0x200) forces the single-CTA per-tap
-                             * kernel for 64-output exact layers (default: CTA pairs), see conv_tc.cu */
+                             * kernel for 64-output exact layers (default: CTA pairs); bit 10 (0x400) opts the
+                             * 32-output exact layers into CTA pairs too (measured: no gain), see conv_tc.cu */
 } BhsrConvTcDesc;
 
 int bhsr_conv_tc(const BhsrConvTcDesc* desc, void* stream);

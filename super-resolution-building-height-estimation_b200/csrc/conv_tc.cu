@@ -224,16 +224,21 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
 }
 
 // Work item `it` of this CTA: a whole tile (sel = -1) or, in the split last round, one block of it.
-__device__ __forceinline__ bool dx_item(const ConvTcKernelParams& p, int it, int& tile, int& sel) {
+__device__ __forceinline__ bool dx_item_at(const ConvTcKernelParams& p, int it, int idx, int cnt, int& tile,
+                                           int& sel) {
   sel = -1;
   if (p.split_round >= 0 && it >= p.split_round) {
-    if (it > p.split_round || static_cast<int>(blockIdx.x) >= p.split_items) return false;
-    tile = p.split_tile0 + (blockIdx.x >> 1);
-    sel = blockIdx.x & 1;
+    if (it > p.split_round || idx >= p.split_items) return false;
+    tile = p.split_tile0 + (idx >> 1);
+    sel = idx & 1;
     return true;
   }
-  tile = blockIdx.x + it * gridDim.x;
+  tile = idx + it * cnt;
   return tile < p.total_tiles;
+}
+// ... for one CTA per work stream (idx = CTA, cnt = grid); CTA pairs pass their cluster index
+__device__ __forceinline__ bool dx_item(const ConvTcKernelParams& p, int it, int& tile, int& sel) {
+  return dx_item_at(p, it, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), tile, sel);
 }
 
 // WMODE: how the weights reach shared memory — 0: streamed, one window row (KS taps) per ring
@@ -917,7 +922,7 @@ constexpr int kDxBars = 4 * kMaxAStages + 8 + 2 * kMaxWSlots;
 constexpr int kDxTailBytes = kDxBars * 8 + 16 + 2 * 64 * 4 + 64 + kDxStageBytes + kDxXchgFloats * 4;
 constexpr int kDxBlk = 126;                         // valid output rows per 128-row block
 
-template <bool EXACT, int MB, bool WRES>
+template <bool EXACT, int MB, bool WRES, bool PAIR>
 __global__ void __launch_bounds__(kDxThreads, 1)
 conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo,
@@ -929,14 +934,19 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   constexpr int KSTEPS = CH / 16;
   constexpr int NPART = EXACT ? 2 : 1;
   constexpr int COLS = 96 * NPART;                 // weight rows per window row = TMEM columns per block
-  constexpr int W_SLAB = COLS * RB;                // one (chunk, dy) weight slab: 12288 B either way
+  // one (chunk, dy) weight slab: 12288 B; in a CTA pair this CTA keeps 144 of the 192 rows:
+  // X = its half of the wide operand (96 rows: W_hi in the even CTA, W_lo' in the odd one, couts in
+  // halves of 16: row = half*48 + dx*16 + cout%16), Y = W_hi half `rank` (48 rows) for the lo' phase
+  static_assert(!PAIR || (EXACT && MB == 2), "CTA pairs: exact numerics, two blocks per tile");
+  constexpr int W_SLAB = PAIR ? 144 * RB : COLS * RB;
+  constexpr uint32_t W_Y16 = PAIR ? ((96 * RB) >> 4) : 0;   // descriptor units from X to Y
   constexpr int TILE = G::kTileBytes;              // one plane of one halo tile
   constexpr int A_TX = G::kTileBytesRaw;
   constexpr int NSLOT = EXACT ? 2 : 4;             // accumulator blocks in TMEM (192 / 96 columns each)
   constexpr int S_OUT = kDxBlk * MB;               // valid output rows per tile
   static_assert(NSLOT * COLS <= 512, "TMEM overflow");
-  constexpr uint32_t IDESC_WIDE = make_idesc_f16(COLS);
-  constexpr uint32_t IDESC_N = make_idesc_f16(96);
+  constexpr uint32_t IDESC_WIDE = make_idesc_f16(COLS, PAIR ? 256 : 128);
+  constexpr uint32_t IDESC_N = make_idesc_f16(96, PAIR ? 256 : 128);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -960,6 +970,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pairs (see conv_pair_kernel): the even CTA issues the M = 256 MMAs and owns every "full"
+  // and accumulator-free barrier; this CTA works on image 2m + rank of pair-tile q
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cta_idx = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int cta_cnt = PAIR ? (gridDim.x >> 1) : gridDim.x;
 #ifdef BHSR_TIMING
   const long long t_entry = clock64();
 #endif
@@ -968,7 +984,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     for (int i = 0; i < 4 * kMaxAStages; ++i) mbar_init(bar(i), 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar(B_TFULL + i), 1);
-      mbar_init(bar(B_TEMPTY + i), 128);
+      mbar_init(bar(B_TEMPTY + i), PAIR ? 256 : 128);
     }
     for (int i = 0; i < p.wslots; ++i) {
       mbar_init(bar(B_WFULL + i), 1);
@@ -984,11 +1000,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
   }
   if (warp == kDxWarpMma) {
-    tmem_alloc(smem_u32(tmem_slot), 512);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc2(smem_u32(tmem_slot), 512); tmem_relinquish2(); }
+    else { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();           // both CTAs' barriers exist before anything is signalled
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (p.pdl) {
@@ -997,29 +1014,41 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   }
 
   int tile, sel;
+  auto item = [&](int it, int& tl, int& sl_) { return dx_item_at(p, it, cta_idx, cta_cnt, tl, sl_); };
+  auto wait_local = [&](uint32_t b_, uint32_t par_) {   // barriers signalled from the other CTA too
+    if (PAIR) mbar_wait_cluster(b_, par_); else mbar_wait(b_, par_);
+  };
 
   if (warp == kDxWarpProdA) {
     // ------------------------------------------------ activation producer (hi ring, lo ring)
     if (lane == 0) {
       int sh = 0, ph_h = 1, sl = 0, ph_l = 1;
-      for (int it = 0; dx_item(p, it, tile, sel); ++it) {
+      for (int it = 0; item(it, tile, sel); ++it) {
         const int t = tile % p.tiles_per_strip;
         const int sn = tile / p.tiles_per_strip;
         const int s = sn % p.n_strips;
-        const int n = sn / p.n_strips;
+        const int n = PAIR ? 2 * (sn / p.n_strips) + static_cast<int>(rank) : sn / p.n_strips;
         // block 0 row 0 is flat output t*S_OUT - 1; its dy = -1 operand row starts one image row up
         const int r0 = (t * S_OUT + kPitch - 1) / kPitch - 2;
         for (int c = 0; c < p.n_chunks; ++c) {
-          mbar_wait(bar(B_HEMPTY + sh), ph_h);
-          mbar_expect_tx(bar(B_HFULL + sh), A_TX);
-          tma_load_4d(ah_base + sh * TILE, &tm_a_hi, bar(B_HFULL + sh), p.in_choff + c * CH,
-                      s * kStrip - 1, r0, n);
+          wait_local(bar(B_HEMPTY + sh), ph_h);
+          if (leader) mbar_expect_tx(bar(B_HFULL + sh), PAIR ? 2 * A_TX : A_TX);
+          if (PAIR)
+            tma_load_4d_2sm(ah_base + sh * TILE, &tm_a_hi, bar(B_HFULL + sh), p.in_choff + c * CH,
+                            s * kStrip - 1, r0, n);
+          else
+            tma_load_4d(ah_base + sh * TILE, &tm_a_hi, bar(B_HFULL + sh), p.in_choff + c * CH,
+                        s * kStrip - 1, r0, n);
           if (++sh == NS) { sh = 0; ph_h ^= 1; }
           if (EXACT) {
-            mbar_wait(bar(B_LEMPTY + sl), ph_l);
-            mbar_expect_tx(bar(B_LFULL + sl), A_TX);
-            tma_load_4d(al_base + sl * TILE, &tm_a_lo, bar(B_LFULL + sl), p.in_choff + c * CH,
-                        s * kStrip - 1, r0, n);
+            wait_local(bar(B_LEMPTY + sl), ph_l);
+            if (leader) mbar_expect_tx(bar(B_LFULL + sl), PAIR ? 2 * A_TX : A_TX);
+            if (PAIR)
+              tma_load_4d_2sm(al_base + sl * TILE, &tm_a_lo, bar(B_LFULL + sl), p.in_choff + c * CH,
+                              s * kStrip - 1, r0, n);
+            else
+              tma_load_4d(al_base + sl * TILE, &tm_a_lo, bar(B_LFULL + sl), p.in_choff + c * CH,
+                          s * kStrip - 1, r0, n);
             if (++sl == NS) { sl = 0; ph_l ^= 1; }
           }
         }
@@ -1030,18 +1059,27 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (lane == 0) {
       uint32_t it = 0;
       const int slabs = p.n_chunks * 3;
-      for (int item = 0; dx_item(p, item, tile, sel); ++item) {
+      for (int wi = 0; item(wi, tile, sel); ++wi) {
         for (int sl = 0; sl < slabs; ++sl, ++it) {
           const int ws = WRES ? sl : static_cast<int>(it % p.wslots);
-          if (!WRES) mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
-          mbar_expect_tx(bar(B_WFULL + ws), W_SLAB);
-          tma_load_5d(w_base + ws * W_SLAB, &tm_w, bar(B_WFULL + ws), 0, 0, 0, 0, sl);
+          if (!WRES) wait_local(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
+          if (leader) mbar_expect_tx(bar(B_WFULL + ws), PAIR ? 2 * W_SLAB : W_SLAB);
+          if (PAIR) {
+            // tm_w boxes are {CH, 16 couts, 3 dx, 1 part}: 48 rows each
+            const uint32_t dst = w_base + ws * W_SLAB;
+            const int r = static_cast<int>(rank);
+            tma_load_5d_2sm(dst, &tm_w, bar(B_WFULL + ws), 0, 0, 0, r, sl);                 // X, couts 0-15
+            tma_load_5d_2sm(dst + 48 * RB, &tm_w, bar(B_WFULL + ws), 0, 16, 0, r, sl);      // X, couts 16-31
+            tma_load_5d_2sm(dst + 96 * RB, &tm_w, bar(B_WFULL + ws), 0, 16 * r, 0, 0, sl);  // Y = W_hi half r
+          } else {
+            tma_load_5d(w_base + ws * W_SLAB, &tm_w, bar(B_WFULL + ws), 0, 0, 0, 0, sl);
+          }
         }
         if (WRES) break;
       }
     }
-  } else if (warp == kDxWarpMma) {
-    // ------------------------------------------------ MMA issuer
+  } else if (warp == kDxWarpMma && (!PAIR || leader)) {
+    // ------------------------------------------------ MMA issuer (pairs: the even CTA only)
     const uint64_t desc0 = make_kmajor_desc<RB>(0);
     const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
     const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
@@ -1055,11 +1093,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     constexpr bool dbg = false;
 #endif
     uint32_t ok_h = 0, ok_l = 0, ok_w = 0;   // early-probe results (ok_w: one bit per window row)
+    auto commit_ = [&](uint32_t b_) { if (PAIR) umma_commit2(b_); else umma_commit(b_); };
     const int n_chunks = p.n_chunks, cin = p.cin, wslots = p.wslots;
     int sh = 0, h_ph = 0, sl = 0, l_ph = 0;
     int ws_r = 0, w_ph = 0;
     constexpr uint32_t ASTEP = kDxBlk * RB16;       // descriptor units between the two blocks
-    for (; dx_item(p, static_cast<int>(tile_it), tile, sel); ++tile_it) {
+    for (; item(static_cast<int>(tile_it), tile, sel); ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int f0 = t * S_OUT;
       const int r0 = (f0 + kPitch - 1) / kPitch - 2;
@@ -1067,7 +1106,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       bool more_tiles;
       {
         int t2, s2;
-        more_tiles = dx_item(p, static_cast<int>(tile_it) + 1, t2, s2);
+        more_tiles = item(static_cast<int>(tile_it) + 1, t2, s2);
       }
       // blocks of the tile this item covers: both, or only block `sel` (split last round)
       const int mb_lo = sel < 0 ? 0 : sel;
@@ -1086,12 +1125,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         for (int g = 0; g < 3; ++g) {
           if (WRES) {
             wsl[g] = c * 3 + g;
-            if (tile_it == 0) mbar_wait(bar(B_WFULL + wsl[g]), 0);
+            if (tile_it == 0) wait_local(bar(B_WFULL + wsl[g]), 0);
           } else {
             wsl[g] = ws_r;
             if (!((ok_w >> g) & 1u)) {
               if (dbg) tq = clock64();
-              mbar_wait(bar(B_WFULL + ws_r), w_ph);
+              wait_local(bar(B_WFULL + ws_r), w_ph);
               if (dbg) t_wfull += clock64() - tq;
             }
             if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }
@@ -1109,7 +1148,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         }
         if (!ok_h) {
           if (dbg) tq = clock64();
-          mbar_wait(bar(B_HFULL + sh), h_ph);
+          wait_local(bar(B_HFULL + sh), h_ph);
           if (dbg) t_afull += clock64() - tq;
         }
         ok_h = 0;
@@ -1140,7 +1179,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             for (int mb = 0; mb < MB; ++mb) {
               if (mb < mb_lo || mb >= mb_hi) continue;
               if (dbg) tq = clock64();
-              mbar_wait(bar(B_TEMPTY + slot0 + mb), t_par ^ 1);
+              wait_local(bar(B_TEMPTY + slot0 + mb), t_par ^ 1);
               if (dbg) t_tempty += clock64() - tq;
               tc_fence_after();
               if (elect_one()) {
@@ -1149,7 +1188,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #endif
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
-                  okbits |= issue_dx<KST, 1, 0>(a_h0 + (g * kPitch + mb * kDxBlk) * RB16,
+                  okbits |= issue_dx<KST, 1, 0, PAIR>(a_h0 + (g * kPitch + mb * kDxBlk) * RB16,
                                                 b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0 + mb * COLS, 0,
                                                 IDESC_WIDE, g > 0 ? 1u : 0u, hb1, hp1, hb1, hp1);
               }
@@ -1161,7 +1200,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
               for (int mb = 0; mb < MB; ++mb) {
                 if (mb < mb_lo || mb >= mb_hi) continue;
                 if (dbg) tq = clock64();
-                mbar_wait(bar(B_TEMPTY + slot0 + mb), t_par ^ 1);
+                wait_local(bar(B_TEMPTY + slot0 + mb), t_par ^ 1);
                 if (dbg) t_tempty += clock64() - tq;
               }
               tc_fence_after();
@@ -1174,12 +1213,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
               for (int g = 0; g < 3; ++g) {
                 uint32_t r;
                 if (pair || MB == 1)
-                  r = issue_dx<KST, MB, ASTEP>(
+                  r = issue_dx<KST, MB, ASTEP, PAIR>(
                       a_h0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0, acc0 + COLS,
                       IDESC_WIDE, (c > 0 || g > 0) ? 1u : 0u, hb1, hp1, EXACT ? hb1 : nbar[g],
                       EXACT ? hp1 : npar[g]);
                 else
-                  r = issue_dx<KST, 1, 0>(
+                  r = issue_dx<KST, 1, 0, PAIR>(
                       a_h0 + (g * kPitch + mb_lo * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi,
                       acc0 + mb_lo * COLS, 0, IDESC_WIDE, (c > 0 || g > 0) ? 1u : 0u, hb1, hp1,
                       EXACT ? hb1 : nbar[g], EXACT ? hp1 : npar[g]);
@@ -1189,17 +1228,17 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 if (last_chunk) {
 #pragma unroll
                   for (int mb = 0; mb < MB; ++mb)
-                    if (mb >= mb_lo && mb < mb_hi) umma_commit(bar(B_TFULL + slot0 + mb));
+                    if (mb >= mb_lo && mb < mb_hi) commit_(bar(B_TFULL + slot0 + mb));
                 }
                 if (!WRES) {
 #pragma unroll
-                  for (int g = 0; g < 3; ++g) umma_commit(bar(B_WEMPTY + wsl[g]));
+                  for (int g = 0; g < 3; ++g) commit_(bar(B_WEMPTY + wsl[g]));
                 }
               }
             }
             __syncwarp();
           }
-          if (elect_one()) umma_commit(bar(B_HEMPTY + sh));
+          if (elect_one()) commit_(bar(B_HEMPTY + sh));
           okbits = __reduce_or_sync(0xffffffffu, okbits);
           if (EXACT) {
             ok_l = okbits & 1u;
@@ -1212,7 +1251,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             // probes: bit 0 = next hi stage, bit 1 = next chunk's weight slab of the same row
             if (!ok_l) {
               if (dbg) tq = clock64();
-              mbar_wait(bar(B_LFULL + sl), l_ph);
+              wait_local(bar(B_LFULL + sl), l_ph);
               if (dbg) t_afull += clock64() - tq;
             }
             ok_l = 0;
@@ -1228,13 +1267,13 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #endif
 #pragma unroll
                   for (int g = 0; g < 3; ++g) {
-                    const uint32_t r = issue_dx<KST, 1, 0>(
-                        a_l0 + (g * kPitch + mb * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi,
+                    const uint32_t r = issue_dx<KST, 1, 0, PAIR>(
+                        a_l0 + (g * kPitch + mb * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4) + W_Y16, desc_hi,
                         acc0 + mb * COLS + 96, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
                         nbar[g], npar[g]);
                     if (mb == mb_hi - 1) okbits |= (r & 1u) | ((r >> 1) << (1 + g));
                   }
-                  umma_commit(bar(B_TFULL + slot0 + mb));
+                  commit_(bar(B_TFULL + slot0 + mb));
                 }
                 __syncwarp();
               }
@@ -1247,13 +1286,13 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 for (int g = 0; g < 3; ++g) {
                   uint32_t r;
                   if (pair || MB == 1)
-                    r = issue_dx<KST, MB, ASTEP>(
-                        a_l0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, acc0 + 96,
+                    r = issue_dx<KST, MB, ASTEP, PAIR>(
+                        a_l0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4) + W_Y16, desc_hi, acc0 + 96,
                         acc0 + COLS + 96, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next), nbar[g],
                         npar[g]);
                   else
-                    r = issue_dx<KST, 1, 0>(
-                        a_l0 + (g * kPitch + mb_lo * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi,
+                    r = issue_dx<KST, 1, 0, PAIR>(
+                        a_l0 + (g * kPitch + mb_lo * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4) + W_Y16, desc_hi,
                         acc0 + mb_lo * COLS + 96, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
                         nbar[g], npar[g]);
                   okbits |= (r & 1u) | ((r >> 1) << (1 + g));
@@ -1264,9 +1303,9 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             if (elect_one()) {
               if (!WRES) {
 #pragma unroll
-                for (int g = 0; g < 3; ++g) umma_commit(bar(B_WEMPTY + wsl[g]));
+                for (int g = 0; g < 3; ++g) commit_(bar(B_WEMPTY + wsl[g]));
               }
-              umma_commit(bar(B_LEMPTY + sl));
+              commit_(bar(B_LEMPTY + sl));
             }
             okbits = __reduce_or_sync(0xffffffffu, okbits);
             if (!last_chunk || more_tiles) ok_h = okbits & 1u;
@@ -1300,11 +1339,11 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #ifdef BHSR_TIMING
     long long t_epi_wait = 0;
 #endif
-    for (; dx_item(p, static_cast<int>(tile_it), tile, sel); ++tile_it) {
+    for (; item(static_cast<int>(tile_it), tile, sel); ++tile_it) {
       const int t = tile % p.tiles_per_strip;
       const int sn = tile / p.tiles_per_strip;
       const int s = sn % p.n_strips;
-      const int n = sn / p.n_strips;
+      const int n = PAIR ? 2 * (sn / p.n_strips) + static_cast<int>(rank) : sn / p.n_strips;
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
         if (sel >= 0 && mb != sel) continue;             // split last round: one block of the tile
@@ -1314,7 +1353,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #ifdef BHSR_TIMING
         const long long tw0 = clock64();
 #endif
-        mbar_wait(bar(B_TFULL + slot), (blk / NSLOT) & 1);
+        wait_local(bar(B_TFULL + slot), (blk / NSLOT) & 1);
 #ifdef BHSR_TIMING
         t_epi_wait += clock64() - tw0;
 #endif
@@ -1323,6 +1362,22 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         // drain the three dx groups (main + 2^-11 * correction) and free the block at once
         float v0[32], v1[32], v2[32];
         auto drain = [&](uint32_t col, float (&dst)[32]) {
+          if (PAIR) {
+            // pair column order: couts in halves of 16 -> column (cout/16)*48 + dx*16 + cout%16
+            const uint32_t cg = (col >> 5) * 16;
+            uint32_t m0[16], m1[16], c0[16], c1[16];
+            tmem_ld_32x16(t_row + cg, m0);
+            tmem_ld_32x16(t_row + 48 + cg, m1);
+            tmem_ld_32x16(t_row + 96 + cg, c0);
+            tmem_ld_32x16(t_row + 144 + cg, c1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              dst[jj] = fmaf(__uint_as_float(c0[jj]), 1.f / 2048.f, __uint_as_float(m0[jj]));
+              dst[16 + jj] = fmaf(__uint_as_float(c1[jj]), 1.f / 2048.f, __uint_as_float(m1[jj]));
+            }
+            return;
+          }
           uint32_t raw[32];
           tmem_ld_32x32(t_row + col, raw);
           if (EXACT) {
@@ -1342,7 +1397,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         drain(32, v1);
         drain(64, v2);
         tc_fence_before();
-        mbar_arrive(bar(B_TEMPTY + slot));
+        if (PAIR) mbar_arrive_leader(bar(B_TEMPTY + slot)); else mbar_arrive(bar(B_TEMPTY + slot));
         // out[row] = g0[row-1] + g1[row] + g2[row+1]: lane shifts inside the warp, smem across warps
         float* xb = s_xchg + ((grp * 2 + xpar) * 4) * 64;
         if (lane == 31) {
@@ -1406,9 +1461,10 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();           // the leader's barriers outlive every remote arrive
   if (warp == kDxWarpMma) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1580,14 +1636,15 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
 
 // 5-D view of the packed weight blob [chunk][tap = dy*3+dx][part][32 couts][CH] that lands one
 // (chunk, dy) slab in shared memory as [part][dx][cout][CH] rows (see conv_dx_kernel).
-static int make_weight_map_dx(CUtensorMap* tm, const void* base, int n_chunks, int nparts, int ch) {
+static int make_weight_map_dx(CUtensorMap* tm, const void* base, int n_chunks, int nparts, int ch,
+                              int box_couts = 32, int box_parts = -1) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return BHSR_ECUDA;
   const cuuint64_t rb = (cuuint64_t)ch * 2;
   const cuuint64_t tap_bytes = (cuuint64_t)nparts * 32 * rb;
   cuuint64_t dims[5] = {(cuuint64_t)ch, 32, 3, (cuuint64_t)nparts, (cuuint64_t)n_chunks * 3};
   cuuint64_t strides[4] = {rb, tap_bytes, 32 * rb, 3 * tap_bytes};
-  cuuint32_t box[5] = {(cuuint32_t)ch, 32, 3, (cuuint32_t)nparts, 1};
+  cuuint32_t box[5] = {(cuuint32_t)ch, (cuuint32_t)box_couts, 3, (cuuint32_t)(box_parts < 0 ? nparts : box_parts), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1600,7 +1657,7 @@ static int make_weight_map_dx(CUtensorMap* tm, const void* base, int n_chunks, i
 template <bool EXACT, int MB, bool WRES>
 static int launch_dx_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
                             const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
-  auto kern = conv_dx_kernel<EXACT, MB, WRES>;
+  auto kern = conv_dx_kernel<EXACT, MB, WRES, false>;
   static bool attr_set = false;
   if (!attr_set) {
     BHSR_CUDA_CHECK(
@@ -1737,6 +1794,71 @@ static int launch_pair(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStrea
   return 0;
 }
 
+// dx-in-N launch on CTA pairs (exact numerics, two blocks per tile, even batch).
+static int launch_dx_pair(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream, bool* launched) {
+  using G = TileGeom<2, 32>;
+  constexpr int W_SLAB = 144 * G::kRowBytes;       // this CTA's 144 of the 192 rows of a (chunk, dy) slab
+  constexpr int A_STAGE = G::kTileBytes * 2;
+  constexpr int S_OUT = kDxBlk * 2;
+  *launched = false;
+  const int slabs = p.n_chunks * 3;
+  const int astages = 2;
+  int wslots = (kSmemLimit - 1024 - astages * A_STAGE - kDxTailBytes) / W_SLAB;
+  if (wslots > kMaxWSlots) wslots = kMaxWSlots;
+  if (wslots < 6) return 0;
+  const bool resident = slabs <= wslots;
+  if (resident) wslots = slabs;
+  const int smem_bytes = 1024 + astages * A_STAGE + wslots * W_SLAB + kDxTailBytes;
+  auto kern_r = conv_dx_kernel<true, 2, true, true>;
+  auto kern_s = conv_dx_kernel<true, 2, false, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BHSR_CUDA_CHECK(cudaFuncSetAttribute(kern_r, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    BHSR_CUDA_CHECK(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kDxThreads);
+  cfg.dynamicSmemBytes = kSmemLimit;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    int sms = device_sm_count();
+    cfg.gridDim = dim3(sms > 1 ? sms / 2 * 2 : 2);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern_s, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    max_clusters = n;
+  }
+  if (max_clusters < 8) return 0;
+  cfg.dynamicSmemBytes = smem_bytes;
+  p.tiles_per_strip = (d.h * kPitch + S_OUT - 1) / S_OUT;
+  p.total_tiles = (d.nb / 2) * p.n_strips * p.tiles_per_strip;   // pair-tiles
+  p.wslots = wslots;
+  p.astages = astages;
+  p.w_resident = resident ? 1 : 0;
+  p.pdl = 0;
+  CUtensorMap tm_hi, tm_lo, tm_w;
+  int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, 32);
+  if (rc) return rc;
+  rc = make_act_map(&tm_lo, d.in_lo, d.nb, d.h, d.w, d.in_ctot, G::kRows, 32);
+  if (rc) return rc;
+  rc = make_weight_map_dx(&tm_w, d.w_packed, p.n_chunks, 2, 32, /*box_couts=*/16, /*box_parts=*/1);
+  if (rc) return rc;
+  int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
+  if (d.max_ctas > 1 && clusters > d.max_ctas / 2) clusters = d.max_ctas / 2;
+  set_split(p, clusters, 2, true);
+  cfg.gridDim = dim3(2 * clusters);
+  if (resident) BHSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern_r, tm_hi, tm_lo, tm_w, p));
+  else BHSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern_s, tm_hi, tm_lo, tm_w, p));
+  *launched = true;
+  return 0;
+}
+
 }  // namespace bhsr
 
 using namespace bhsr;
@@ -1847,6 +1969,17 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
     static const char* dxn = getenv("BHSR_DXN");
     const bool use_dx = !(dxn && dxn[0] == '0') && !(d.desc_mode & 0x100);  // desc_mode bit 8: per-tap kernel
     if (use_dx && d.cout == 32 && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2)) {
+      if (exact && mb == 2 && d.nb % 2 == 0 && d.cin % 32 == 0) {
+        // CTA pairs for the dx kernel are correct but not faster (these layers are bound by their OWN
+        // activation supply, and the leader waits for the slower of two loads:
+        // profiles/r01_dx_pair_not_faster_v12.log) -> opt-in: BHSR_DX_PAIR=1 or desc_mode bit 10
+        static const char* pr = getenv("BHSR_DX_PAIR");
+        if (((pr && pr[0] == '1') || (d.desc_mode & 0x400)) && !(d.desc_mode & 0x200)) {
+          bool launched = false;
+          int rc = launch_dx_pair(d, p, stream, &launched);
+          if (rc || launched) return rc;
+        }
+      }
       if (exact) return mb == 2 ? launch_dx<true, 2>(d, p, stream) : launch_dx<true, 1>(d, p, stream);
       return mb == 2 ? launch_dx<false, 2>(d, p, stream) : launch_dx<false, 1>(d, p, stream);
     }

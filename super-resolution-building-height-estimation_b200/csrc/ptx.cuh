@@ -276,15 +276,16 @@ __device__ __forceinline__ uint32_t issue_tap(uint32_t a_lo, uint32_t b_lo, uint
   "mbarrier.test_wait.parity.shared::cta.b64 pw1, [%9], %10;\n"                         \
   "mbarrier.test_wait.parity.shared::cta.b64 pw2, [%11], %12;\n"                        \
   "mov.b32 alo, %2;\nmov.b32 blo, %3;\n"
-#define BHSR_DX_STEP(D, ACC)                                                           \
+#define BHSR_DX_STEP(GRP, D, ACC)                                                      \
   "mov.b64 da, {alo, %4};\nmov.b64 db, {blo, %4};\n"                                   \
-  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %7, " ACC ";\n"                 \
+  "tcgen05.mma.cta_group::" GRP ".kind::f16 [" D "], da, db, %7, " ACC ";\n"           \
   "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
 #define BHSR_DX_NEXT "add.u32 alo, alo, %13;\nsub.u32 blo, blo, %14;\n"
 #define BHSR_DX_POST "selp.u32 %0, 1, 0, pw1;\nselp.u32 %1, 1, 0, pw2;\n}\n"
-#define BHSR_DX_B1(D) BHSR_DX_STEP(D, "pacc")
-#define BHSR_DX_B2(D) BHSR_DX_STEP(D, "pacc") BHSR_DX_STEP(D, "ptrue")
-#define BHSR_DX_B4(D) BHSR_DX_STEP(D, "pacc") BHSR_DX_STEP(D, "ptrue") BHSR_DX_STEP(D, "ptrue") BHSR_DX_STEP(D, "ptrue")
+#define BHSR_DX_B1(GRP, D) BHSR_DX_STEP(GRP, D, "pacc")
+#define BHSR_DX_B2(GRP, D) BHSR_DX_STEP(GRP, D, "pacc") BHSR_DX_STEP(GRP, D, "ptrue")
+#define BHSR_DX_B4(GRP, D) \
+  BHSR_DX_STEP(GRP, D, "pacc") BHSR_DX_STEP(GRP, D, "ptrue") BHSR_DX_STEP(GRP, D, "ptrue") BHSR_DX_STEP(GRP, D, "ptrue")
 #define BHSR_DX_ASM(BODY)                                                              \
   asm volatile(BHSR_DX_PRE BODY BHSR_DX_POST                                           \
                : "=r"(ok1), "=r"(ok2)                                                  \
@@ -292,19 +293,27 @@ __device__ __forceinline__ uint32_t issue_tap(uint32_t a_lo, uint32_t b_lo, uint
                  "r"(bar1), "r"(par1), "r"(bar2), "r"(par2), "n"(ASTEP16 - 2 * KST), "n"(2 * KST)  \
                : "memory")
 
-// returns bit 0 = first barrier test passed, bit 1 = second
-template <int KST, int NB, int ASTEP16>
+// returns bit 0 = first barrier test passed, bit 1 = second.  PAIR: cta_group::2 (M = 256 over a CTA pair)
+template <int KST, int NB, int ASTEP16, bool PAIR = false>
 __device__ __forceinline__ uint32_t issue_dx(uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t d0,
                                              uint32_t d1, uint32_t idesc, uint32_t acc_first,
                                              uint32_t bar1, uint32_t par1, uint32_t bar2, uint32_t par2) {
   uint32_t ok1, ok2;
-  if constexpr (KST == 4 && NB == 2) BHSR_DX_ASM(BHSR_DX_B4("%5") BHSR_DX_NEXT BHSR_DX_B4("%6"));
-  else if constexpr (KST == 2 && NB == 2) BHSR_DX_ASM(BHSR_DX_B2("%5") BHSR_DX_NEXT BHSR_DX_B2("%6"));
-  else if constexpr (KST == 1 && NB == 2) BHSR_DX_ASM(BHSR_DX_B1("%5") BHSR_DX_NEXT BHSR_DX_B1("%6"));
-  else if constexpr (KST == 4 && NB == 1) BHSR_DX_ASM(BHSR_DX_B4("%5"));
-  else if constexpr (KST == 2 && NB == 1) BHSR_DX_ASM(BHSR_DX_B2("%5"));
-  else if constexpr (KST == 1 && NB == 1) BHSR_DX_ASM(BHSR_DX_B1("%5"));
-  else static_assert(KST < 0, "unsupported issue_dx variant");
+  if constexpr (!PAIR) {
+    if constexpr (KST == 4 && NB == 2) BHSR_DX_ASM(BHSR_DX_B4("1", "%5") BHSR_DX_NEXT BHSR_DX_B4("1", "%6"));
+    else if constexpr (KST == 2 && NB == 2) BHSR_DX_ASM(BHSR_DX_B2("1", "%5") BHSR_DX_NEXT BHSR_DX_B2("1", "%6"));
+    else if constexpr (KST == 1 && NB == 2) BHSR_DX_ASM(BHSR_DX_B1("1", "%5") BHSR_DX_NEXT BHSR_DX_B1("1", "%6"));
+    else if constexpr (KST == 4 && NB == 1) BHSR_DX_ASM(BHSR_DX_B4("1", "%5"));
+    else if constexpr (KST == 2 && NB == 1) BHSR_DX_ASM(BHSR_DX_B2("1", "%5"));
+    else if constexpr (KST == 1 && NB == 1) BHSR_DX_ASM(BHSR_DX_B1("1", "%5"));
+    else static_assert(KST < 0, "unsupported issue_dx variant");
+  } else {
+    if constexpr (KST == 2 && NB == 2) BHSR_DX_ASM(BHSR_DX_B2("2", "%5") BHSR_DX_NEXT BHSR_DX_B2("2", "%6"));
+    else if constexpr (KST == 1 && NB == 2) BHSR_DX_ASM(BHSR_DX_B1("2", "%5") BHSR_DX_NEXT BHSR_DX_B1("2", "%6"));
+    else if constexpr (KST == 2 && NB == 1) BHSR_DX_ASM(BHSR_DX_B2("2", "%5"));
+    else if constexpr (KST == 1 && NB == 1) BHSR_DX_ASM(BHSR_DX_B1("2", "%5"));
+    else static_assert(KST < 0, "unsupported issue_dx pair variant");
+  }
   return ok1 | (ok2 << 1);
 }
 
@@ -343,6 +352,14 @@ __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap*
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
       "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                                int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0,

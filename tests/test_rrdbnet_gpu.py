@@ -93,7 +93,8 @@ def test_conv_dx_kernel_vs_per_tap_and_oracle(dev, numerics, rtol, atol, cin, h,
     rhi, rlo = _planes(r1, 32, dev)
     wp = ops.pack_conv_weights(cuda(wt, dev), num)
     outs = []
-    for mode in (0, 0x100):
+    modes = (0, 0x100) + ((0x400,) if (numerics == "exact" and mb == 2 and nb % 2 == 0) else ())
+    for mode in modes:   # 0x400: the dx kernel on CTA pairs (opt-in variant, kept validated)
         out_hi = torch.zeros((nb, h, w, 64), dtype=torch.float16, device=dev)
         out_lo = torch.zeros_like(out_hi)
         ops.conv_tc(hi, lo, 0, cin, wp, 32, cuda(b, dev), ops.PLAIN_TAPS, out_hi, out_lo, out_choff=32,
@@ -104,6 +105,9 @@ def test_conv_dx_kernel_vs_per_tap_and_oracle(dev, numerics, rtol, atol, cin, h,
     assert_close(outs[0], ref, rtol, atol, f"dx kernel {cin}->32 {numerics} mb{mb}")
     assert_close(outs[1], ref, rtol, atol, f"per-tap kernel {cin}->32 {numerics} mb{mb}")
     assert_close(outs[0], outs[1], rtol, atol, "dx vs per-tap")
+    if len(outs) > 2:
+        assert_close(outs[2], ref, rtol, atol, f"dx kernel on CTA pairs {cin}->32")
+        assert_close(outs[2], outs[0], 1e-5, 1e-6, "dx pair vs dx single")
 
 
 @pytest.mark.parametrize("cin,nb,h,w,max_ctas,nchw", [(192, 6, 64, 64, 80, False), (64, 2, 40, 130, 0, False),

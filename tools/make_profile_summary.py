@@ -74,8 +74,8 @@ def main():
                       "|---|---|---|---|---|---|---|---|---|---|---|---|"]
             caps = ncu_raw(rep)
             names = [re.sub(r"\(CUtensor.*", "", k.get("Kernel Name", ("", ""))[0]).replace("void bhsr::", "").replace("void ", "") for k in caps]
-            # conv5 is the only 64-output instance of the per-tap kernel inside the trunk: layers follow in order
-            i5 = next((i for i, n in enumerate(names) if n.startswith("conv_tc_kernel<64")), None)
+            # conv5 is the only 64-output conv inside the trunk (CTA-pair kernel): layers follow in order
+            i5 = next((i for i, n in enumerate(names) if n.startswith("conv_pair_kernel") or n.startswith("conv_tc_kernel<64")), None)
             layer_of = {}
             if i5 is not None:
                 for i in range(len(caps)):

@@ -88,6 +88,9 @@ def run_case(name, desc_mode):
     cases["time_exact32_c128_mb2"] = dict(nb=64, cin=128, exact=True, mb=2, time=True)
     cases["exact64_c192_mb2"] = dict(cout=64, cin=192, exact=True, mb=2, lrelu=False, res=2)
     cases["exact64_c64_mb2_nb6"] = dict(nb=6, cout=64, cin=64, exact=True, mb=2, lrelu=False, res=1, max_ctas=4)
+    cases["exact32_c160_mb2_nb4"] = dict(cin=160, exact=True, mb=2, nb=4)
+    cases["exact32_c160_mb2_nb6s"] = dict(cin=160, exact=True, mb=2, nb=6, max_ctas=80)
+    cases["exact32_c96_w130_nb2"] = dict(cin=96, exact=True, mb=2, nb=2, h=23, w=130)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
