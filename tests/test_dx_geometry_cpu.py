@@ -91,3 +91,52 @@ def test_split_last_round_deals_every_block_once(total, grid):
     assert len(work) == 2 * total
     if sr >= 0:               # the split saves half a round
         assert most == 2 * (total // grid) + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# CTA pairs: which packed weight rows each CTA of a pair loads, where they sit in its shared memory,
+# and which accumulator column they produce (conv_tc.cu: conv_pair_kernel / conv_dx_kernel<PAIR>).
+# `tcgen05.mma.cta_group::2` takes the first N/2 rows of B from the even CTA and the rest from the
+# odd one, both at the SAME shared-memory offset.
+
+def pair_tap_layout(rank):
+    """conv_pair_kernel weight producer: smem rows of one tap in CTA `rank` -> packed rows (tap-relative;
+    packed rows 0-63 = W_hi, 64-127 = W_lo')."""
+    x = [rank * 64 + r for r in range(64)]          # two 32-row boxes at +0 and +2048 B
+    y = [rank * 32 + r for r in range(32)]          # one box at +4096 B
+    return x, y
+
+
+def test_conv5_pair_weight_split_reproduces_the_single_cta_columns():
+    x0, y0 = pair_tap_layout(0)
+    x1, y1 = pair_tap_layout(1)
+    wide = x0 + x1              # B rows of the N=128 MMA in column order
+    narrow = y0 + y1            # B rows of the N=64 MMA (written at column offset 64)
+    # single-CTA kernel: columns 0-63 = W_hi couts, 64-127 = W_lo' couts; narrow = W_hi into 64-127
+    assert wide == list(range(128))
+    assert narrow == list(range(64))
+
+
+def dx_pair_slab_layout(rank):
+    """conv_dx_kernel<PAIR> weight producer: smem rows of one (chunk, dy) slab in CTA `rank` as
+    (part, dx, cout) triples; boxes are {CH, 16 couts, 3 dx, 1 part} = 48 rows each."""
+    def box(part, half):
+        return [(part, dx, half * 16 + c) for dx in range(3) for c in range(16)]
+    x = box(rank, 0) + box(rank, 1)                 # X: this CTA's 96 rows of the wide operand
+    y = box(0, rank)                                # Y: W_hi half `rank` for the lo' phase
+    return x, y
+
+
+def test_dx_pair_columns_match_the_epilogue_mapping():
+    x0, y0 = dx_pair_slab_layout(0)
+    x1, y1 = dx_pair_slab_layout(1)
+    wide = x0 + x1              # N = 192: columns 0-95 main (W_hi), 96-191 correction (W_lo')
+    narrow = y0 + y1            # N = 96, accumulated at column offset 96
+    for part in range(2):
+        for dx in range(3):
+            for cout in range(32):
+                col = (cout // 16) * 48 + dx * 16 + cout % 16      # epilogue `drain` (PAIR branch)
+                assert wide[part * 96 + col] == (part, dx, cout)
+                if part == 0:
+                    assert narrow[col] == (0, dx, cout)             # lo' x W_hi lands on the same channel
+    assert len(wide) == 192 and len(set(wide)) == 192 and len(narrow) == 96
