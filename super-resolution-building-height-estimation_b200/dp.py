@@ -10,6 +10,10 @@
   forward, three weighted losses, backward, all-reduce, optimiser step.  No per-step host sync.
 * `predict_shard` — predict_realesanet_feature_globe.py:167-177 for the tiles of one rank:
   features, head, clamp/round to uint16 (height*10) and softmax*255 (uint16), sharded rank::world.
+* `adjust_learning_rate`, `build_training_state`, `save_checkpoint`, `load_checkpoint` — the
+  epoch-level bookkeeping of train.py (66-80, 150-179, 198-212): step LR schedule (with the
+  reference's "every group is rescaled" behaviour), Adam + log-variance parameter group, the
+  `checkpoint.tar` schema and resume.
 """
 from __future__ import annotations
 
@@ -173,3 +177,69 @@ def synthetic_labels(nb: int, device, stats: Optional[torch.Tensor] = None, seed
     h_aggre = aggregate_torch(h.unsqueeze(1), 0.25).reshape(nb, 64, 64)
     w_aggre = aggregate_torch(weight.unsqueeze(1), 0.25).reshape(nb, 64, 64)
     return h, h_aggre, build, weight, w_aggre
+
+
+# ------------------------------------------------------------------ training-loop bookkeeping (row N1)
+def adjust_learning_rate(init_lr: float, epoch: int, optimizer) -> float:
+    """train.py:66-80 — step schedule on the 1-based epoch: x1 up to epoch 10, x0.1 up to 20, x0.01
+    after.  The reference means to skip the loss-weight group but tests `'lossweight' in
+    param_group`, which looks for a KEY of that name and is always False, so every group (the
+    log-var group too) is rescaled; that behaviour is kept."""
+    lr = init_lr if epoch <= 10 else (0.1 * init_lr if epoch <= 20 else 0.01 * init_lr)
+    for group in optimizer.param_groups:
+        if ('lossweight' in group) and (group.get('name') == 'lossweight'):
+            continue
+        group['lr'] = lr
+    return lr
+
+
+def build_training_state(net: nn.Module, init_lr: float = 1e-3, isaggre: bool = True,
+                         log_vars: Sequence[float] = (0.0, 0.0, 0.0), device="cuda"):
+    """Adam(weight_decay=1e-4) over the head + the uncertainty-weighted criteria whose log-variances
+    form a second parameter group `{'lr': 1e-3, 'name': 'lossweight'}` (train.py:170-179; the group
+    inherits weight_decay=1e-4 exactly as in the reference)."""
+    optimizer = torch.optim.Adam(net.parameters(), lr=init_lr, weight_decay=1e-4)
+    criterion: List[nn.Module] = [MSE_adapt_weight(log_vars[0], device=device)]
+    if isaggre:
+        criterion.append(MSE_adapt_weight(log_vars[1], device=device))
+    criterion.append(CE_DICE_adapt_weight(log_vars[2], device=device))
+    optimizer.add_param_group({'params': [c.log_var for c in criterion], 'lr': 0.001, 'name': 'lossweight'})
+    return optimizer, criterion
+
+
+def save_checkpoint(logdir: str, epoch: int, net: nn.Module, log_vars, best_acc: float, val_rmse: float,
+                    isaggre: bool = True) -> Tuple[float, bool]:
+    """train.py:198-212 — `checkpoint.tar` every epoch with the reference's schema
+    {'epoch','state_dict','log_vars','best_acc'} (optimizer state is NOT saved), a copy to
+    `model_best.tar` when `val_rmse < best_acc`, and to `checkpoint{epoch}.tar` every 5 epochs.
+    Returns (new best_acc, is_best).  With the reference's initial best_acc = 0 (train.py:108)
+    `is_best` never becomes true; callers wanting a best model start from +inf."""
+    import os
+    import shutil
+    os.makedirs(logdir, exist_ok=True)
+    path = os.path.join(logdir, 'checkpoint.tar')
+    is_best = val_rmse < best_acc
+    best_acc = min(val_rmse, best_acc)
+    module = net.module if hasattr(net, "module") else net
+    torch.save({'epoch': epoch, 'state_dict': module.state_dict(),
+                'log_vars': [float(v) for v in log_vars] if isaggre else 1.0, 'best_acc': best_acc}, path)
+    if is_best:
+        shutil.copy(path, os.path.join(logdir, 'model_best.tar'))
+    if epoch % 5 == 0:
+        shutil.copy(path, os.path.join(logdir, f'checkpoint{epoch}.tar'))
+    return best_acc, is_best
+
+
+def load_checkpoint(logdir: str, net: nn.Module, map_location=None):
+    """train.py:150-168 — resume from `logdir/checkpoint.tar` if present: returns
+    (start_epoch, best_acc, log_vars) and loads the head's state_dict; (0, None, [0,0,0]) otherwise."""
+    import os
+    path = os.path.join(logdir, 'checkpoint.tar')
+    if not os.path.isfile(path):
+        return 0, None, [0.0, 0.0, 0.0]
+    ckpt = torch.load(path, map_location=map_location)
+    net.load_state_dict(ckpt['state_dict'])
+    log_vars = ckpt['log_vars']
+    if not isinstance(log_vars, (list, tuple)):
+        log_vars = [0.0, 0.0, 0.0]
+    return int(ckpt['epoch']), ckpt['best_acc'], list(log_vars)

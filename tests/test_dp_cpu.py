@@ -91,3 +91,38 @@ def test_bucket_guards_against_detached_grads():
     torch.optim.SGD(lin.parameters(), lr=0.1).zero_grad(set_to_none=True)
     with pytest.raises(RuntimeError):
         b.zero_()
+
+
+def test_lr_schedule_rescales_every_group_like_the_reference():
+    """train.py:66-80: 1e-3 -> 1e-4 after epoch 10 -> 1e-5 after epoch 20, and (reference quirk) the
+    'lossweight' group is rescaled too."""
+    import torch
+    from bhsr import dp
+    net = torch.nn.Linear(4, 2)
+    opt, crit = dp.build_training_state(net, init_lr=1e-3, isaggre=True, device="cpu")
+    assert len(crit) == 3 and len(opt.param_groups) == 2
+    assert opt.param_groups[1]['name'] == 'lossweight' and opt.param_groups[1]['weight_decay'] == 1e-4
+    seen = {e: dp.adjust_learning_rate(1e-3, e, opt) for e in (1, 10, 11, 20, 21, 30)}
+    assert seen == {1: 1e-3, 10: 1e-3, 11: 1e-4, 20: 1e-4, 21: 1e-5, 30: 1e-5}
+    assert [g['lr'] for g in opt.param_groups] == [1e-5, 1e-5]
+
+
+def test_checkpoint_schema_and_resume(tmp_path):
+    """train.py:150-168, 198-212: checkpoint.tar keys, 5-epoch copies, best-model rule, resume."""
+    import os
+    import torch
+    from bhsr import dp
+    net = torch.nn.Linear(4, 2)
+    best = 0.0                                   # the reference's initial value: never "best"
+    best, is_best = dp.save_checkpoint(str(tmp_path), 4, net, [0.1, 0.2, 0.3], best, val_rmse=7.0)
+    assert not is_best and best == 0.0 and not os.path.exists(tmp_path / "model_best.tar")
+    best, is_best = dp.save_checkpoint(str(tmp_path), 5, net, [0.1, 0.2, 0.3], float("inf"), val_rmse=7.0)
+    assert is_best and best == 7.0
+    assert os.path.exists(tmp_path / "model_best.tar") and os.path.exists(tmp_path / "checkpoint5.tar")
+    ckpt = torch.load(tmp_path / "checkpoint.tar")
+    assert sorted(ckpt) == ['best_acc', 'epoch', 'log_vars', 'state_dict'] and ckpt['epoch'] == 5
+    other = torch.nn.Linear(4, 2)
+    epoch, best_acc, log_vars = dp.load_checkpoint(str(tmp_path), other)
+    assert (epoch, best_acc) == (5, 7.0) and log_vars == pytest.approx([0.1, 0.2, 0.3])
+    assert torch.equal(other.weight, net.weight)
+    assert dp.load_checkpoint(str(tmp_path / "missing"), other) == (0, None, [0.0, 0.0, 0.0])
