@@ -14,6 +14,9 @@
   epoch-level bookkeeping of train.py (66-80, 150-179, 198-212): step LR schedule (with the
   reference's "every group is rescaled" behaviour), Adam + log-variance parameter group, the
   `checkpoint.tar` schema and resume.
+* `grid_positions`, `CityMosaic` — the host side of the city sweep (BH_loader.py:908-929,
+  predict_realesanet_feature_globe.py:157-204): grid-cell windows from the geotransform, uint16
+  overlap-add mosaics with visit counts, per-rank partial rasters merged by summation.
 """
 from __future__ import annotations
 
@@ -243,3 +246,60 @@ def load_checkpoint(logdir: str, net: nn.Module, map_location=None):
     if not isinstance(log_vars, (list, tuple)):
         log_vars = [0.0, 0.0, 0.0]
     return int(ckpt['epoch']), ckpt['best_acc'], list(log_vars)
+
+
+# ------------------------------------------------------------------ city mosaics (row N2)
+def grid_positions(bounds: Iterable[Sequence[float]], transform: Sequence[float]) -> List[Tuple[int, int, int, int]]:
+    """BH_loader.py:908-929 (`generateindex`) without the shapefile I/O: each grid cell given as
+    (minX, minY, maxX, maxY) in map units becomes (xoff, yoff, xcount, ycount) in LR pixels of the
+    raster with GDAL geotransform `transform` (Python's round-half-to-even, like the reference)."""
+    x0, y0 = transform[0], transform[3]
+    pw, ph = transform[1], -transform[5]
+    pos = []
+    for minx, miny, maxx, maxy in bounds:
+        pos.append((round((minx - x0) / pw), round((y0 - maxy) / ph),
+                    round((maxx - minx) / pw), round((maxy - miny) / ph)))
+    return pos
+
+
+class CityMosaic:
+    """Host-side accumulation of per-tile predictions into city rasters,
+    predict_realesanet_feature_globe.py:157-159, 179-185, 195-204: uint16 height*10 sums, uint16
+    per-class softmax*255 sums, uint8 visit counts, all at 4x the LR grid; `finalize` returns the
+    arg-max class map (uint8) and the visit-normalised height (uint16, only where visited).
+    Integer widths and wrap-around are the reference's (numpy `+=` on uint16 / uint8)."""
+
+    def __init__(self, lr_height: int, lr_width: int, chans_build: int, upscale: int = 4):
+        import numpy as np
+        self.np = np
+        self.upscale = upscale
+        h, w = lr_height * upscale, lr_width * upscale
+        self.height = np.zeros((h, w), dtype=np.uint16)
+        self.build = np.zeros((chans_build, h, w), dtype=np.uint16)
+        self.weight = np.zeros((h, w), dtype=np.uint8)
+
+    def add(self, ypred, build, positions) -> None:
+        """ypred [n,1,H,W], build [n,K,H,W]: the integer-valued outputs of `predict_shard` (any
+        integer dtype / tensor); positions: n x (xoff, yoff, xcount, ycount) in LR pixels."""
+        np = self.np
+        yp = np.asarray(ypred.cpu() if hasattr(ypred, "cpu") else ypred).astype(np.uint16)
+        bp = np.asarray(build.cpu() if hasattr(build, "cpu") else build).astype(np.uint16)
+        for i, pos in enumerate(positions):
+            xoff, yoff, xcount, ycount = (int(v) * self.upscale for v in pos)
+            self.height[yoff:yoff + ycount, xoff:xoff + xcount] += yp[i, 0, :ycount, :xcount]
+            self.build[:, yoff:yoff + ycount, xoff:xoff + xcount] += bp[i, :, :ycount, :xcount]
+            self.weight[yoff:yoff + ycount, xoff:xoff + xcount] += 1
+
+    def merge(self, other: "CityMosaic") -> None:
+        """Sum the partial rasters of another rank (sharded sweep: every tile is in exactly one)."""
+        self.height += other.height
+        self.build += other.build
+        self.weight += other.weight
+
+    def finalize(self):
+        np = self.np
+        build = np.argmax(self.build, axis=0).astype(np.uint8)
+        height = self.height.copy()
+        mask = self.weight > 0
+        height[mask] = np.round(height[mask] / self.weight[mask]).astype(np.uint16)
+        return build, height

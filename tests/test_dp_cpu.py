@@ -126,3 +126,37 @@ def test_checkpoint_schema_and_resume(tmp_path):
     assert (epoch, best_acc) == (5, 7.0) and log_vars == pytest.approx([0.1, 0.2, 0.3])
     assert torch.equal(other.weight, net.weight)
     assert dp.load_checkpoint(str(tmp_path / "missing"), other) == (0, None, [0.0, 0.0, 0.0])
+
+
+def test_grid_positions_and_city_mosaic_match_the_reference_arithmetic():
+    """BH_loader.py:908-929 and predict_realesanet_feature_globe.py:157-204 restated directly."""
+    from bhsr import dp
+    transform = (500000.0, 10.0, 0.0, 4100000.0, 0.0, -10.0)        # 10 m Sentinel-2 grid
+    bounds = [(500000.0, 4099360.0, 500640.0, 4100000.0),           # 64x64 cell at the origin
+              (500320.0, 4099040.0, 500960.0, 4099680.0),           # overlaps the first one
+              (500645.0, 4099365.0, 501285.0, 4100005.0)]           # off-grid: rounding
+    pos = dp.grid_positions(bounds, transform)
+    assert pos[0] == (0, 0, 64, 64) and pos[1] == (32, 32, 64, 64)
+    assert pos[2] == (round(64.5), round(-0.5), 64, 64) == (64, 0, 64, 64)   # half-to-even, as Python's round
+    rng = np.random.RandomState(3)
+    n, k = 2, 7
+    yp = rng.randint(0, 900, size=(n, 1, 256, 256))
+    bp = rng.randint(0, 256, size=(n, k, 256, 256))
+    m = dp.CityMosaic(128, 128, k)
+    m.add(torch.from_numpy(yp).to(torch.int32), torch.from_numpy(bp).to(torch.int32), pos[:2])
+    # direct restatement
+    h = np.zeros((512, 512), np.uint16); b = np.zeros((k, 512, 512), np.uint16); w = np.zeros((512, 512), np.uint8)
+    for i, (xo, yo, xc, yc) in enumerate(np.array(pos[:2]) * 4):
+        h[yo:yo + yc, xo:xo + xc] += yp[i, 0, :yc, :xc].astype(np.uint16)
+        b[:, yo:yo + yc, xo:xo + xc] += bp[i, :, :yc, :xc].astype(np.uint16)
+        w[yo:yo + yc, xo:xo + xc] += 1
+    build, height = m.finalize()
+    assert np.array_equal(build, np.argmax(b, axis=0).astype(np.uint8))
+    ref_h = h.copy(); mask = w > 0
+    ref_h[mask] = np.round(h[mask] / w[mask]).astype(np.uint16)
+    assert np.array_equal(height, ref_h) and int(w.max()) == 2 and height[-1, -1] == 0
+    # two ranks, one tile each, merged == one rank with both
+    a, c = dp.CityMosaic(128, 128, k), dp.CityMosaic(128, 128, k)
+    a.add(yp[:1], bp[:1], pos[:1]); c.add(yp[1:], bp[1:], pos[1:2]); a.merge(c)
+    b2, h2 = a.finalize()
+    assert np.array_equal(b2, build) and np.array_equal(h2, height)
