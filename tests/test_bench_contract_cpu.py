@@ -27,3 +27,28 @@ def test_main_arm_fails_loudly_without_cuda():
         return
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], cwd=ROOT, capture_output=True, timeout=300)
     assert p.returncode != 0 and b"CUDA" in (p.stderr + p.stdout)
+
+
+def test_committed_gpu_bench_line_carries_the_whole_contract():
+    """The last bench line measured on a B200 (profiles/r01_bench_final.json) has every key the
+    driver reads, and its derived numbers are self-consistent."""
+    path = os.path.join(ROOT, "profiles", "r01_bench_final.json")
+    line = json.loads([ln for ln in open(path) if ln.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in line, k
+    assert line["unit"] == "tiles/s" and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert line["steps"] >= 1 and line["warmup"] >= 3 and line["gpu_launches"] == 356 * line["steps"]
+    b = line["config"]["batch_per_gpu"]
+    assert abs(line["value"] - b * line["n_gpus"] / line["ms_per_step"] * 1e3) < 1e-6 * line["value"]
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] == b * 6 * 64 * 64 * 4 and e2e["d2h_bytes_per_step"] > 0 and e2e["value"] > 0
+    r = line["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] > 0
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert abs(r["step"]["achieved"] - 146.630 * b / line["ms_per_step"]) < 1e-6 * r["step"]["achieved"]
+    assert {k["layer"] for k in r["kernels"]} == {f"rdb.conv{i}" for i in range(1, 6)}
+    c = line["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
