@@ -17,6 +17,8 @@
 * `grid_positions`, `CityMosaic` — the host side of the city sweep (BH_loader.py:908-929,
   predict_realesanet_feature_globe.py:157-204): grid-cell windows from the geotransform, uint16
   overlap-add mosaics with visit counts, per-rank partial rasters merged by summation.
+* `hierweight`, `make_labels` — the loader's label side on the device (BH_loader.py:30-61, 327-392):
+  level weights from the height histogram, height-level LUT, per-pixel weights, 4x4 aggregates.
 """
 from __future__ import annotations
 
@@ -156,6 +158,41 @@ def predict_shard(net_g, net, tiles: torch.Tensor) -> Tuple[torch.Tensor, torch.
     ypred = torch.round(ypred.clamp_min(0) * 10).to(torch.int32)
     build = torch.round(torch.softmax(build_pred, dim=1) * 255).to(torch.int32)
     return ypred, build
+
+
+def hierweight(stats, hir: Sequence[int], mode: str = "sqrt") -> torch.Tensor:
+    """Class weights over the height levels `hir` from a 256-bin height histogram, BH_loader.py:30-61:
+    inverse square-root frequency (`hierweight`, the one train.py uses), inverse frequency
+    (`hierweight_simple`) or all ones (`hierweight_equal`), normalised so the weights sum to the
+    number of levels.  Known answer for the shipped globe statistics: BH_loader.py:1116-1124."""
+    st = torch.as_tensor(stats, dtype=torch.float64)
+    st = st / st.sum()
+    n = len(hir) - 1
+    if mode == "equal":
+        return torch.ones(n, dtype=torch.float64)
+    freq = torch.stack([st[hir[i]:hir[i + 1]].sum() for i in range(n)])
+    w = 1.0 / torch.sqrt(freq) if mode == "sqrt" else 1.0 / freq
+    w = w / w.sum()
+    return w * (n / w.sum())
+
+
+def make_labels(height: torch.Tensor, level_weights: torch.Tensor,
+                hir: Sequence[int] = (0, 3, 12, 21, 30, 60, 90, 256), scale: float = 0.25):
+    """The loader's label pipeline on the tensor's own device (BH_loader.py:327-329, 373-392):
+    uint8-valued heights [B,256,256] -> height-level classes through the `hir` LUT, per-pixel loss
+    weights, and the 4x4-aggregated height / weight maps [B,64,64] (`aggregate_torch`)."""
+    from .aggregate import aggregate_torch
+    dev = height.device
+    lut = torch.zeros(256, dtype=torch.long)
+    for i in range(len(hir) - 1):
+        lut[hir[i]:hir[i + 1]] = i
+    build = lut.to(dev)[height.long().clamp_(0, 255)]
+    weight = level_weights.to(dev, torch.float32)[build]
+    nb = height.shape[0]
+    side = int(round(height.shape[-1] * scale))
+    h_aggre = aggregate_torch(height.float().unsqueeze(1), scale).reshape(nb, side, side)
+    w_aggre = aggregate_torch(weight.unsqueeze(1), scale).reshape(nb, side, side)
+    return build, weight, h_aggre, w_aggre
 
 
 def synthetic_labels(nb: int, device, stats: Optional[torch.Tensor] = None, seed: int = 0,

@@ -160,3 +160,22 @@ def test_grid_positions_and_city_mosaic_match_the_reference_arithmetic():
     a.add(yp[:1], bp[:1], pos[:1]); c.add(yp[1:], bp[1:], pos[1:2]); a.merge(c)
     b2, h2 = a.finalize()
     assert np.array_equal(b2, build) and np.array_equal(h2, height)
+
+
+def test_hierweight_known_answer_and_label_pipeline():
+    """BH_loader.py:1116-1124: the shipped globe histogram gives the published level weights; the
+    label pipeline maps heights to levels / weights / 4x4 aggregates like the loader (:327-392)."""
+    from bhsr import dp
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    w = dp.hierweight(golden["bh_stats_globe"], (0, 3, 12, 21, 30, 60, 90, 255))
+    np.testing.assert_allclose(w.numpy(), golden["hierweight_kat"], rtol=0, atol=5e-9)
+    assert dp.hierweight(golden["bh_stats_globe"], (0, 3, 12, 21, 30, 60, 90, 255), "equal").tolist() == [1.0] * 7
+    ws = dp.hierweight(golden["bh_stats_globe"], (0, 3, 12, 21, 30, 60, 90, 255), "simple")
+    assert abs(float(ws.sum()) - 7.0) < 1e-9 and bool((ws[1:] >= ws[:-1]).all())   # rarer levels weigh more
+    h = torch.tensor([[0, 2, 3, 11], [12, 29, 30, 59], [60, 89, 90, 255], [0, 0, 0, 0]], dtype=torch.float32)
+    h = h.repeat_interleave(4, 0).repeat_interleave(4, 1).unsqueeze(0)              # [1,16,16], 4x4 blocks
+    build, weight, h_aggre, w_aggre = dp.make_labels(h, w, scale=0.25)
+    assert build[0, ::4, ::4].tolist() == [[0, 0, 1, 1], [2, 3, 4, 4], [5, 5, 6, 6], [0, 0, 0, 0]]
+    np.testing.assert_allclose(weight[0, ::4, ::4].numpy(), w.float()[build[0, ::4, ::4]].numpy())
+    np.testing.assert_allclose(h_aggre[0].numpy(), h[0, ::4, ::4].numpy(), atol=1e-5)   # constant blocks
+    np.testing.assert_allclose(w_aggre[0].numpy(), weight[0, ::4, ::4].numpy(), atol=1e-6)
