@@ -20,13 +20,16 @@
 // a second accumulator that the epilogue scales by 2^-11.  hi*hi and hi*lo' share the A
 // operand, so they are one MMA with the two weight tiles stacked along N (N -> 2N).
 //
-// Warp roles (224 threads, 1 CTA per SM, persistent over tiles):
-//   warps 0..3    : epilogue (TMEM -> registers -> bias/LeakyReLU/residual -> global)
-//   warp 4 lane 0 : TMA producer for activation halo tiles   (ring of 2-4 stages)
-//   warp 5 lane 0 : TMA producer for weight tiles (ring of per-window-row slabs; when the
-//                   whole layer fits the ring the weights are loaded once and stay resident)
-//   warp 6        : tcgen05.mma issuer (elected lane); also owns the TMEM allocation
-// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Three kernels implement it (this file holds their host side: tensor maps, shared-memory plans,
+// kernel selection and the C ABI):
+//   conv_tap.cuh  conv_tc_kernel    per-tap MMAs, N = 32/64 (x2 in exact numerics); warp roles: warps
+//                                   0..3 epilogue, 4 activation TMA producer, 5 weight TMA producer,
+//                                   6 MMA issuer + TMEM owner; two accumulator stages in TMEM
+//                 conv_pair_kernel  the same for 64-output exact layers on CTA pairs (cta_group::2,
+//                                   M = 256, each CTA holds half of every weight tile)
+//   conv_dx.cuh   conv_dx_kernel    32-output layers: the three dx taps stacked along N, lane-shift
+//                                   combine in the epilogue (optionally on CTA pairs)
+//   conv_common.cuh                 parameters, tile geometry, the shared epilogue, work-item walk
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
