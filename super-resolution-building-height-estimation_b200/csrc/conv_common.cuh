@@ -47,7 +47,9 @@ struct ConvTcKernelParams {
   int astages;       // activation ring depth (2..kMaxAStages)
   int pdl;           // launched with programmatic stream serialization
   int desc_mode;
-  int nomma;         // BHSR_TIMING builds only: skip the MMAs (measures the TMA supply rate alone)
+  int nomma;         // BHSR_TIMING builds only: 1 = skip the MMAs (measures the TMA supply rate alone);
+                     // 2 = skip the activation reloads after the first fill of each ring stage
+                     // (dx kernel: measures the MMA stream without TMA traffic; results are garbage)
   // the tiles of an incomplete last round are dealt as single 128-row blocks so that
   // twice as many SMs share them (item index split_round, CTAs [0, split_items)); -1 = off
   int split_round, split_items, split_tile0;

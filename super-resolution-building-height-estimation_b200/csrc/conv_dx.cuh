@@ -159,6 +159,19 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         // block 0 row 0 is flat output t*S_OUT - 1; its dy = -1 operand row starts one image row up
         const int r0 = (t * S_OUT + kPitch - 1) / kPitch - 2;
         for (int c = 0; c < p.n_chunks; ++c) {
+#ifdef BHSR_TIMING
+          if (!PAIR && p.nomma == 2 && (it > 0 || c >= NS)) {   // stale tiles: no TMA traffic at all
+            mbar_wait(bar(B_HEMPTY + sh), ph_h);
+            mbar_arrive(bar(B_HFULL + sh));
+            if (++sh == NS) { sh = 0; ph_h ^= 1; }
+            if (EXACT) {
+              mbar_wait(bar(B_LEMPTY + sl), ph_l);
+              mbar_arrive(bar(B_LFULL + sl));
+              if (++sl == NS) { sl = 0; ph_l ^= 1; }
+            }
+            continue;
+          }
+#endif
           wait_local(bar(B_HEMPTY + sh), ph_h);
           if (leader) mbar_expect_tx(bar(B_HFULL + sh), PAIR ? 2 * A_TX : A_TX);
           if (PAIR)
@@ -312,7 +325,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
               tc_fence_after();
               if (elect_one()) {
 #ifdef BHSR_TIMING
-                if (!p.nomma)
+                if (p.nomma != 1)
 #endif
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
@@ -335,7 +348,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             }
             if (elect_one()) {
 #ifdef BHSR_TIMING
-              if (!p.nomma)
+              if (p.nomma != 1)
 #endif
 #pragma unroll
               for (int g = 0; g < 3; ++g) {
@@ -391,7 +404,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 if (mb < mb_lo || mb >= mb_hi) continue;
                 if (elect_one()) {
 #ifdef BHSR_TIMING
-                  if (!p.nomma)
+                  if (p.nomma != 1)
 #endif
 #pragma unroll
                   for (int g = 0; g < 3; ++g) {
@@ -408,7 +421,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             } else {
               if (elect_one()) {
 #ifdef BHSR_TIMING
-                if (!p.nomma)
+                if (p.nomma != 1)
 #endif
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {

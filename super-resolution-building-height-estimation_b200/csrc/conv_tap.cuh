@@ -245,7 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 const uint32_t ppar = slot == 0 ? par_w_next
                                                 : (slot == 1 ? static_cast<uint32_t>(a_ph_next) : par_t_next);
 #ifdef BHSR_TIMING
-                if (p.nomma) { if (tt < 3) okbits |= static_cast<uint32_t>(mbar_try_wait(pbar, ppar)) << tt; continue; }
+                if (p.nomma == 1) { if (tt < 3) okbits |= static_cast<uint32_t>(mbar_try_wait(pbar, ppar)) << tt; continue; }
 #endif
                 uint32_t ok;
                 if (MB == 1 || sel < 0)
