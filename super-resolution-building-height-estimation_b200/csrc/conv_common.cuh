@@ -49,7 +49,8 @@ struct ConvTcKernelParams {
   int desc_mode;
   int nomma;         // BHSR_TIMING builds only: 1 = skip the MMAs (measures the TMA supply rate alone);
                      // 2 = skip the activation reloads after the first fill of each ring stage
-                     // (dx kernel: measures the MMA stream without TMA traffic; results are garbage)
+                     // (dx kernel: measures the MMA stream without TMA traffic; results are garbage);
+                     // 3 / 4 = dx epilogue without the lane-shift combine / without anything after the drain
   // the tiles of an incomplete last round are dealt as single 128-row blocks so that
   // twice as many SMs share them (item index split_round, CTAs [0, split_items)); -1 = off
   int split_round, split_items, split_tile0;

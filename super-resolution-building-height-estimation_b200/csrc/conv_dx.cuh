@@ -539,6 +539,20 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         drain(64, v2);
         tc_fence_before();
         if (PAIR) mbar_arrive_leader(bar(B_TEMPTY + slot)); else mbar_arrive(bar(B_TEMPTY + slot));
+#ifdef BHSR_TIMING
+        // diagnostics (garbage results): 3 = no lane-shift combine (no shuffles / exchange / named
+        // barrier), 4 = drain only (nothing after the accumulator release)
+        if (p.nomma == 4) continue;
+        if (p.nomma == 3) {
+          const int f3 = (t * MB + mb) * kDxBlk - 1 + row;
+          const int py3 = f3 / kPitch, pc3 = f3 - py3 * kPitch, px3 = s * kStrip + pc3;
+          const bool valid3 = (row >= 1) && (row <= kDxBlk) && (pc3 < kStrip) && (py3 < p.h) && (px3 < p.w);
+          const size_t pix3 = (static_cast<size_t>(n) * p.h + py3) * p.w + px3;
+          finish_slice32(p, v1, 0, valid3, n, py3, px3, pix3, pix3, py3, px3, warp, lane, false, s_stage, s_bias,
+                         s_scale);
+          continue;
+        }
+#endif
         // out[row] = g0[row-1] + g1[row] + g2[row+1]: lane shifts inside the warp, smem across warps
         float* xb = s_xchg + ((grp * 2 + xpar) * 4) * 64;
         if (lane == 31) {
