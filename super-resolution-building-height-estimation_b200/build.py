@@ -22,13 +22,17 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, timing: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, timing: bool = False, epi_swz: bool = False) -> str:
     """timing=True builds lib/libbhsr_timing.so with the in-kernel cycle counters (-DBHSR_TIMING);
-    select it at run time with BHSR_LIB=<path> BHSR_DEBUG_TIMING=1 (profiling only)."""
+    select it at run time with BHSR_LIB=<path> BHSR_DEBUG_TIMING=1 (profiling only).  epi_swz adds
+    -DBHSR_EPI_SWZ (experimental conflict-free epilogue staging, DESIGN.md §8 Finding 3) and writes
+    lib/libbhsr_timing_episwz.so / lib/libbhsr_episwz.so — never the product library."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    if timing:
-        out = LIB.replace("libbhsr.so", "libbhsr_timing.so")
-        cmd = [os.environ.get("NVCC", "nvcc")] + FLAGS + ["-DBHSR_TIMING", "-o", out] + srcs
+    if timing or epi_swz:
+        name = "libbhsr" + ("_timing" if timing else "") + ("_episwz" if epi_swz else "") + ".so"
+        out = LIB.replace("libbhsr.so", name)
+        defs = (["-DBHSR_TIMING"] if timing else []) + (["-DBHSR_EPI_SWZ"] if epi_swz else [])
+        cmd = [os.environ.get("NVCC", "nvcc")] + FLAGS + defs + ["-o", out] + srcs
         print("[bhsr build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
         return out
@@ -43,4 +47,5 @@ def build(force: bool = False, verbose: bool = False, timing: bool = False) -> s
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv, timing="--timing" in sys.argv)
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv, timing="--timing" in sys.argv,
+          epi_swz="--epi-swz" in sys.argv)

@@ -50,7 +50,8 @@ struct ConvTcKernelParams {
   int nomma;         // BHSR_TIMING builds only: 1 = skip the MMAs (measures the TMA supply rate alone);
                      // 2 = skip the activation reloads after the first fill of each ring stage
                      // (dx kernel: measures the MMA stream without TMA traffic; results are garbage);
-                     // 3 / 4 = dx epilogue without the lane-shift combine / without anything after the drain
+                     // 3 / 4 = dx epilogue without the lane-shift combine / without anything after the drain;
+                     // 5 / 6 = plane stores: staging without global stores / global stores without staging
   // the tiles of an incomplete last round are dealt as single 128-row blocks so that
   // twice as many SMs share them (item index split_round, CTAs [0, split_items)); -1 = off
   int split_round, split_items, split_tile0;
@@ -117,8 +118,16 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
                                                bool nchw, uint8_t* s_stage, const float* s_bias,
                                                const float* s_scale) {
   if (cc * 32 >= p.cout_valid) return;  // padded output channels: nothing to store (uniform)
+#ifdef BHSR_EPI_SWZ
+  if (p.scale == nullptr) {   // experimental build: half the broadcast shared loads when there is no scale
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[cc * 32 + j], s_bias[cc * 32 + j]);
+    for (int j = 0; j < 32; ++j) v[j] += s_bias[cc * 32 + j];
+  } else
+#endif
+  {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[cc * 32 + j], s_bias[cc * 32 + j]);
+  }
   if (p.epilogue & BHSR_EPI_LRELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
@@ -168,10 +177,38 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
     // through shared memory, a store instruction covers 8 pixels x 64 B (8 lines).
     uint8_t* stg = s_stage + warp * (32 * 80);
     const uint32_t pix32 = valid ? static_cast<uint32_t>(out_pix) : 0xFFFFFFFFu;
+#ifdef BHSR_EPI_SWZ
+    // experimental build (build.py --epi-swz): 64-byte pitch with the 16-byte chunk index XOR-ed by
+    // (row >> 1) & 3 — conflict-free for the per-lane 16-byte writes AND the 8-rows-x-64-B reads
+    // (the 80-byte pitch below makes every other row pair of a read overlap on 4 banks)
+    constexpr int kStgPitch = 64;
+#define BHSR_STG_W(ROW, CH) (stg + (ROW) * kStgPitch + ((((CH) ^ (((ROW) >> 1) & 3))) << 4))
+#else
+    constexpr int kStgPitch = 80;
+#define BHSR_STG_W(ROW, CH) (stg + (ROW) * kStgPitch + ((CH) << 4))
+#endif
 #pragma unroll
     for (int part = 0; part < 2; ++part) {
       __half* dst_plane = part == 0 ? p.out_hi : p.out_lo;
       if (dst_plane == nullptr) break;  // warp-uniform
+#ifdef BHSR_TIMING
+      if (p.nomma == 6) {   // diagnostic: no staging, every lane stores its own pixel's four 16-byte chunks
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __align__(16) __half hh[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = v[g * 8 + j];
+            const __half hi = __float2half_rn(x);
+            hh[j] = part == 0 ? hi : __float2half_rn((x - __half2float(hi)) * 2048.f);
+          }
+          if (valid && g * 8 < nvalid)
+            *reinterpret_cast<uint4*>(dst_plane + out_pix * p.out_ctot + p.out_choff + cc * 32 + g * 8) =
+                *reinterpret_cast<const uint4*>(hh);
+        }
+        continue;
+      }
+#endif
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         __align__(16) __half hh[8];
@@ -181,14 +218,20 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
           const __half hi = __float2half_rn(x);
           hh[j] = part == 0 ? hi : __float2half_rn((x - __half2float(hi)) * 2048.f);
         }
-        *reinterpret_cast<uint4*>(stg + lane * 80 + g * 16) = *reinterpret_cast<const uint4*>(hh);
+        *reinterpret_cast<uint4*>(BHSR_STG_W(lane, g)) = *reinterpret_cast<const uint4*>(hh);
       }
       __syncwarp();
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const int src = 8 * j4 + (lane >> 2);
-        const uint4 val = *reinterpret_cast<const uint4*>(stg + src * 80 + (lane & 3) * 16);
+        const uint4 val = *reinterpret_cast<const uint4*>(BHSR_STG_W(src, lane & 3));
         const uint32_t pp = __shfl_sync(0xffffffffu, pix32, src);
+#ifdef BHSR_TIMING
+        if (p.nomma == 5) {   // diagnostic: staging without the global stores
+          if (val.x == 0x7fc07fc0u && pp == 1u) printf("%u", val.y);   // keep the loads alive
+          continue;
+        }
+#endif
         if (pp != 0xFFFFFFFFu && (lane & 3) * 8 < nvalid) {
           __half* o = dst_plane + static_cast<size_t>(pp) * p.out_ctot + p.out_choff + cc * 32 +
                       (lane & 3) * 8;
@@ -197,6 +240,7 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
       }
       __syncwarp();
     }
+#undef BHSR_STG_W
   }
 }
 

@@ -140,3 +140,35 @@ def test_dx_pair_columns_match_the_epilogue_mapping():
                 if part == 0:
                     assert narrow[col] == (0, dx, cout)             # lo' x W_hi lands on the same channel
     assert len(wide) == 192 and len(set(wide)) == 192 and len(narrow) == 96
+
+
+# ---------------------------------------------------------------------------------------------
+# Epilogue store-transpose staging (conv_common.cuh: finish_slice32): shared-memory bank pressure of
+# the shipped 80-byte pitch and of the experimental XOR-swizzled 64-byte pitch (-DBHSR_EPI_SWZ).
+def _wavefronts(addresses_16B):
+    """Shared-memory wavefronts of one 16-byte-per-lane access: 128-bit accesses are served a quarter
+    warp (8 lanes, 128 B) at a time; a quarter needs as many passes as the busiest bank has distinct
+    4-byte words (the model that matches ncu's bank-conflict counter for this epilogue)."""
+    total = 0
+    for q in range(0, len(addresses_16B), 8):
+        per_bank = {}
+        for a in addresses_16B[q:q + 8]:
+            for wd in range(a // 4, a // 4 + 4):
+                per_bank.setdefault(wd % 32, set()).add(wd)
+        total += max(len(v) for v in per_bank.values())
+    return total
+
+
+def _staging(pitch, swizzle):
+    def off(row, chunk):
+        return row * pitch + (((chunk ^ ((row >> 1) & 3)) if swizzle else chunk) << 4)
+    writes = max(_wavefronts([off(lane, g) for lane in range(32)]) for g in range(4))
+    reads = max(_wavefronts([off(8 * j4 + (lane >> 2), lane & 3) for lane in range(32)]) for j4 in range(4))
+    return writes, reads
+
+
+def test_staging_layout_bank_pressure():
+    # 512 bytes per instruction = 4 wavefronts at best
+    assert _staging(80, False) == (4, 8)     # shipped: conflict-free writes, 2x on the reads (ncu: ~0.9 M conflicts / launch)
+    assert _staging(64, True) == (4, 4)      # experimental layout (-DBHSR_EPI_SWZ): both conflict-free
+    assert _staging(64, False) == (16, 4)    # an unswizzled 64-byte pitch would move the conflicts to the writes
