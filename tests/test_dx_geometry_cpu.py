@@ -172,3 +172,70 @@ def test_staging_layout_bank_pressure():
     assert _staging(80, False) == (4, 8)     # shipped: conflict-free writes, 2x on the reads (ncu: ~0.9 M conflicts / launch)
     assert _staging(64, True) == (4, 4)      # experimental layout (-DBHSR_EPI_SWZ): both conflict-free
     assert _staging(64, False) == (16, 4)    # an unswizzled 64-byte pitch would move the conflicts to the writes
+
+
+# ---------------------------------------------------------------------------------------------
+# Shared-memory plans of the launchers (conv_tc.cu: launch, launch_dx, launch_pair, launch_dx_pair)
+# restated: every trunk layer fits the 227 KB limit and gets the ring depths DESIGN.md describes.
+SMEM_LIMIT = 232448
+K_MAX_A, K_MAX_W = 4, 32
+
+
+def _tile_bytes(mb, ch):
+    raw = (5 if mb == 1 else 7) * PITCH * ch * 2
+    return raw, (raw + 1023) // 1024 * 1024
+
+
+def plan_dx(cin, exact, mb, pair=False):
+    ch = 32 if exact else 64
+    npart = 2 if exact else 1
+    n_chunks = (cin + ch - 1) // ch
+    tail = (4 * K_MAX_A + 8 + 2 * K_MAX_W) * 8 + 16 + 2 * 64 * 4 + 64 + 8 * 32 * 80 + 2 * 2 * 4 * 64 * 4
+    w_slab = (144 if pair else 96 * npart) * ch * 2
+    a_stage = _tile_bytes(mb, ch)[1] * npart
+    slabs = n_chunks * 3
+    slots = lambda ns: max(0, (SMEM_LIMIT - 1024 - ns * a_stage - tail) // w_slab)
+    if pair:
+        ns, ws = 2, min(slots(2), K_MAX_W)
+        resident = slabs <= ws
+        ws = slabs if resident else ws
+    else:
+        ns = ws = None
+        for cand in range(K_MAX_A, 1, -1):
+            if slots(cand) >= slabs:
+                ns, ws = cand, slots(cand)
+                break
+        if ns is None:
+            for cand in range(K_MAX_A, 1, -1):
+                if slots(cand) >= 6:
+                    ns, ws = cand, slots(cand)
+                    break
+        ws = min(ws, K_MAX_W)
+        resident = slabs <= ws
+        ws = slabs if resident else ws
+    total = 1024 + ns * a_stage + ws * w_slab + tail
+    return dict(astages=ns, wslots=ws, resident=resident, bytes=total)
+
+
+def test_dx_shared_memory_plans_of_the_trunk_layers():
+    exp = {64: (True, 2), 96: (False, 2), 128: (False, 2), 160: (False, 2)}     # conv1..conv4, exact, MB=2
+    for cin, (resident, ns) in exp.items():
+        pl = plan_dx(cin, True, 2)
+        assert pl["bytes"] <= SMEM_LIMIT and pl["resident"] == resident and pl["astages"] == ns, (cin, pl)
+        assert pl["wslots"] >= 6 or pl["resident"]
+    assert plan_dx(64, True, 1)["astages"] == 3 and plan_dx(64, True, 1)["resident"]       # MB=1: a third stage fits
+    for cin in (64, 96, 128, 160):
+        assert plan_dx(cin, False, 2)["bytes"] <= SMEM_LIMIT                                   # fast numerics
+    # CTA pairs keep 144 of 192 weight rows: conv2's weights become resident as well
+    assert plan_dx(96, True, 2, pair=True)["resident"] and not plan_dx(128, True, 2, pair=True)["resident"]
+    assert all(plan_dx(c, True, 2, pair=True)["bytes"] <= SMEM_LIMIT for c in (64, 96, 128, 160))
+
+
+def test_pair_kernel_shared_memory_plan():
+    tail = (2 * K_MAX_A + 4 + 2 * K_MAX_W) * 8 + 16 + 2 * 64 * 4 + 64 + 4 * 32 * 80
+    a_stage = _tile_bytes(2, 32)[1] * 2
+    w_slab = 3 * 96 * 64
+    wslots = (SMEM_LIMIT - 1024 - 2 * a_stage - tail) // w_slab
+    assert wslots == 5 and 1024 + 2 * a_stage + wslots * w_slab + tail <= SMEM_LIMIT
+    # bytes both CTAs report to the leader's barriers stay far below the mbarrier tx-count range (2^20 - 1)
+    assert 2 * (2 * _tile_bytes(2, 32)[0]) < (1 << 20) and 2 * w_slab < (1 << 20)
