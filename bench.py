@@ -11,10 +11,15 @@ the RGB view x[:, :3] like train.py:244), random-init weights of the reference a
 value  : tiles/s with inputs resident in HBM (CUDA events, max over ranks).
 e2e    : same metric through the public nn.Module call with HOST (pinned) input every step
          (H2D inside the timed region) and a D2H read of the per-tile feature checksums.
-roofline: tensor bound; achieved = algorithmic conv FLOPs of one step (146.630 GFLOP/tile,
-         SURVEY §8d — the reference formulation, counted once regardless of split-precision
-         passes) / step time; peak = MEASURED_PEAKS.json bf16 sustained (kernels timed inside a
-         long step).
+roofline: tensor bound; the top-level figure is the kernel with the largest share of the step (its
+         layer shapes timed live with CUDA events), `roofline.step` is the whole network: algorithmic
+         conv FLOPs of one step (146.630 GFLOP/tile, SURVEY §8d — the reference formulation, counted
+         once regardless of split-precision passes) / step time; peak = MEASURED_PEAKS.json bf16
+         sustained (kernels timed inside a long step).
+train  : BASELINE configs[2] / [3] — the fwd+bwd step the metric string names (frozen RRDBNet-23
+         features -> SRRegress_Cls_feature head -> three uncertainty-weighted losses -> backward ->
+         Adam), batch 32 per GPU; at N > 1 the data-parallel step with ONE NCCL all-reduce of the flat
+         gradient bucket per step.  Reported as the `train` sub-record of the same JSON line.
 """
 from __future__ import annotations
 
@@ -31,6 +36,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 GFLOP_PER_TILE = 146.630       # forward_feature, SURVEY.md §8(d) / BASELINE.md §5
+GFLOP_PER_TILE_HEAD_TRAIN = 23.0   # head (ex-smp) fwd+bwd, SURVEY.md §8(d)
+CPU_ARM_BUDGET_S = 150.0       # the reference arm sizes its per-step sample to end within this
 NUM_BLOCK = 23
 FALLBACK_PEAK_TFLOPS = 1590.0  # B200_PROFILING.md fallback (burst); sustained ~1400
 
@@ -43,9 +50,13 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="tiles per GPU per step")
     ap.add_argument("--numerics", default=os.environ.get("BHSR_NUMERICS", "exact"), choices=["exact", "fast"])
     ap.add_argument("--impl", default="bhsr", choices=["bhsr", "reference"])
-    ap.add_argument("--cpu-sample-tiles", type=int, default=8, help="tiles per CPU-baseline step")
+    ap.add_argument("--cpu-sample-tiles", type=int, default=0,
+                    help="tiles per CPU step (0 = auto: 8 for the cpu_baseline leg; the arm's batch, shrunk to fit the "
+                         "time budget, for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other-numerics and full-D2H extras")
+    ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (config 3 / 4) sub-record")
+    ap.add_argument("--train-batch", type=int, default=32, help="tiles per GPU per training step")
     return ap.parse_args()
 
 
@@ -200,28 +211,124 @@ def cpu_reference_run(args, steps, warmup, tiles_per_step):
     return tiles_per_step * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+def forward_config(B, tiles, numerics, world):
+    """`config` of the forward workload — shared by both arms so the driver sees one configuration."""
+    return {"workload": "BASELINE configs[1]: RRDBNet-23 x4 forward_feature, batch 64 per GPU, 6ch 64x64 "
+                        "synthetic tiles (net reads x[:, :3]), random-init reference architecture",
+            "batch_per_gpu": B, "global_batch": tiles, "numerics": numerics,
+            "parallelism": f"dp{world} (independent tile shards, no collective on this path)",
+            "l2": "inputs alternate between two batches; per-step working set (>=2 GB planes + 1.07 GB "
+                  "output) exceeds the 126 MB L2"}
+
+
 def reference_main(args):
+    """`--impl reference`: the reference's own CPU path for the same config on the box's host cores — the oracle
+    port (oracle/ref_torch.py: the stock torch.nn.functional calls the reference modules dispatch to; the
+    reference is a script repo that cannot be installed and /root/reference is not on the GPU box).  Honours
+    --steps / --warmup; each step is the arm's batch (64 tiles), shrunk only if a probe step says the whole run
+    would not end within CPU_ARM_BUDGET_S."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 1))
-    tiles = args.cpu_sample_tiles
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    probe_tps, _, cores = cpu_reference_run(args, 1, 0, 2 if args.cpu_sample_tiles in (1, 2) else 4)
+    tiles = int(min(args.batch, max(1, CPU_ARM_BUDGET_S * probe_tps / (steps + warmup))))
+    if args.cpu_sample_tiles > 0:
+        tiles = min(tiles, args.cpu_sample_tiles)
     tps, ms, cores = cpu_reference_run(args, steps, warmup, tiles)
+    cfg = forward_config(args.batch, args.batch, "f32 (reference CPU path)", 1)
+    cfg["cpu_tiles_per_step"] = tiles
     line = {
         "impl": "reference", "metric": "tiles/sec (6x64x64->256x256) RRDBNet-23 x4 forward_feature",
         "value": tps, "unit": "tiles/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: RRDBNet-23 x4 forward_feature, 6ch 64x64 synthetic tiles, "
-                               f"CPU sample of {tiles} tiles/step", "tiles_per_step": tiles},
+        "config": cfg,
         "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps x {tiles} tiles, oracle/ref_torch.py (torch.nn.functional on CPU, "
-                                   f"{cores} threads) — /root/reference is not on the GPU box"},
+                         "sample": f"{steps} steps x {tiles} tiles (+{warmup} warm-up), oracle/ref_torch.py = oracle PORT of "
+                                   f"the reference modules (torch.nn.functional on CPU, {cores} threads) — /root/reference "
+                                   f"is not on the GPU box"},
         "e2e": {"value": tps, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- fwd+bwd leg
+def train_leg(args, dev, dist, world, rank, K, W, peak):
+    """BASELINE configs[2] (N = 1) / configs[3] (N > 1): one training iteration of train.py:243-257 per step —
+    frozen RRDBNet-23 features (no_grad) -> SRRegress_Cls_feature(efficientnet-b4 stand-in, isaggre) -> weighted
+    MSE (height) + weighted MSE (4x4 aggregate) + weighted CE+Dice (height levels), uncertainty weighted ->
+    backward -> [one NCCL all-reduce of the flat fp32 gradient bucket, N > 1] -> Adam.  Batch 32 per GPU."""
+    import torch
+    from bhsr import dp
+    from bhsr.models import SRRegress_Cls_feature
+    import synth
+    B = args.train_batch
+    net_g = synth_state_torch(NUM_BLOCK).to(dev).eval()
+    net_g.numerics = args.numerics
+    for p_ in net_g.parameters():
+        p_.requires_grad = False
+    torch.manual_seed(4321)
+    net = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64, super_mid=16,
+                                upscale=4, isaggre=True, chans_build=7).to(dev).train()
+    dp.broadcast_module(net)
+    crit = [dp.MSE_adapt_weight(0.0, dev), dp.MSE_adapt_weight(0.0, dev), dp.CE_DICE_adapt_weight(0.0, dev)]
+    params = list(net.parameters()) + [c.log_var for c in crit]
+    opt = torch.optim.Adam([{"params": list(net.parameters())},
+                            {"params": [c.log_var for c in crit], "name": "lossweight"}], lr=1e-3, weight_decay=1e-4)
+    bucket = dp.FlatGradAllReduce(params)
+    xs = [torch.from_numpy(synth.tiles(B, 8, seed=1337 + 17 * rank + i)).to(dev) for i in range(2)]
+    labels = [dp.synthetic_labels(B, dev, seed=2 * rank + i) for i in range(2)]
+    box = {}
+
+    def step(i):
+        h, h_aggre, build, w, w_aggre = labels[i % 2]
+        box["loss"] = dp.train_step(net_g, net, crit, opt, bucket, xs[i % 2], h, h_aggre, build, w, w_aggre)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    loss = float(box["loss"].item())
+    gflop_tile = GFLOP_PER_TILE + GFLOP_PER_TILE_HEAD_TRAIN
+    tflops = gflop_tile * B * K / ms          # per GPU
+    rec = {
+        "metric": "tiles/sec fwd+bwd (frozen RRDBNet-23 features + SRRegress_Cls_feature head + weighted losses + Adam)",
+        "value": B * world * K / ms * 1e3, "unit": "tiles/s", "ms_per_step": ms / K, "steps": K, "warmup": W,
+        "batch_per_gpu": B, "global_batch": B * world, "numerics": args.numerics, "loss": loss,
+        "config": ("BASELINE configs[2]: full SR + feature-aggregation head fwd+bwd, batch 32, weighted losses, 1 GPU"
+                   if world == 1 else
+                   f"BASELINE configs[3]: data-parallel training step, {B} tiles/GPU x {world} GPUs, Adam, one NCCL "
+                   "all-reduce of the flat gradient bucket per step"),
+        "collective": ({"op": "ncclAllReduce(sum, fp32) over one flat gradient bucket, then x 1/world",
+                        "per_step": 1, "bytes": bucket.numel * 4} if world > 1 else None),
+        "grad_bucket_floats": bucket.numel,
+        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": tflops, "peak": peak, "frac": tflops / peak,
+                     "algorithmic_gflop_per_tile": gflop_tile,
+                     "note": "146.630 (RRDBNet forward_feature) + 23.0 (head ex-smp fwd+bwd, SURVEY §8d) GFLOP per tile / "
+                             "step time, per GPU; the smp encoder/decoders (~0.9 GFLOP fwd) are not counted"},
+        "data": "synthetic tiles (8 bands) and labels (82 % zero heights, height-level LUT, inverse-sqrt-frequency weights)",
+    }
+    del net, net_g, opt, bucket
+    torch.cuda.empty_cache()
+    return rec
 
 
 # ---------------------------------------------------------------------------------- our arm
@@ -360,12 +467,7 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16x3-split products, f32 accumulate" if args.numerics == "exact" else "f16 products, f32 accumulate",
         "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: RRDBNet-23 x4 forward_feature, batch 64 per GPU, 6ch 64x64 "
-                               "synthetic tiles (net reads x[:, :3]), random-init reference architecture",
-                   "batch_per_gpu": B, "global_batch": tiles, "numerics": args.numerics,
-                   "parallelism": f"dp{world} (independent tile shards, no collective on this path)",
-                   "l2": "inputs alternate between two batches; per-step working set (>=2 GB planes + 1.07 GB "
-                         "output) exceeds the 126 MB L2"},
+        "config": forward_config(B, tiles, args.numerics, world),
         "e2e": {"value": tiles * K / ms_e2e * 1e3, "unit": "tiles/s",
                 "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": B * 4,
                 "note": "nn.Module.forward_feature on pinned host tiles, H2D of every step's tiles inside the timed "
@@ -375,32 +477,55 @@ def main():
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
     }
-    # roofline of the dominant kernel (the RDB conv5 instance, CTA-pair kernel: ~38 % of the step) from its live
-    # CUDA-event duration; the whole-step figure (all 356 launches) sits beside it
-    dom = next((k for k in kernels if k["layer"] == "rdb.conv5"), None)
+    # roofline of the DOMINANT kernel = the kernel (by name) with the largest share of the step, from the live
+    # CUDA-event durations of its layer shapes x their launches per step; the whole-step figure sits beside it
+    groups = {}
+    for k in kernels:
+        g = groups.setdefault(k["kernel"], {"us": 0.0, "gflop": 0.0, "launches": 0, "layers": [], "traffic": []})
+        g["us"] += k["us"] * k["launches_per_step"]
+        g["gflop"] += k["gflop"] * k["launches_per_step"]
+        g["launches"] += k["launches_per_step"]
+        g["layers"].append(k["layer"])
+        if k["traffic_bytes"] is not None:
+            g["traffic"].append(k["traffic_bytes"])
+    dom_name = max(groups, key=lambda n: groups[n]["us"]) if groups else None
+    dom = groups.get(dom_name)
+    dom_tflops = dom["gflop"] / (dom["us"] * 1e-6) / 1e3 if dom else achieved_tflops
     line["roofline"] = {
         "bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_source": peak_src,
-        "kernel": dom["kernel"] if dom else None,
-        "achieved": dom["tflops"] if dom else achieved_tflops,
-        "frac": (dom["tflops"] if dom else achieved_tflops) / peak,
-        "traffic": dom["traffic_bytes"] if dom else None,
-        "traffic_source": dom["traffic_source"] if dom else None,
-        "algorithmic_gflop_per_launch": dom["gflop"] if dom else None,
-        "us_per_launch": dom["us"] if dom else None,
+        "kernel": dom_name,
+        "kernel_layers": dom["layers"] if dom else None,
+        "kernel_share_of_step": dom["us"] * 1e-3 / (ms / K) if dom else None,
+        "achieved": dom_tflops, "frac": dom_tflops / peak,
+        "traffic": sum(dom["traffic"]) / len(dom["traffic"]) if dom and dom["traffic"] else None,
+        "traffic_source": (kernels[0]["traffic_source"] if kernels else None),
+        "algorithmic_gflop_per_launch": dom["gflop"] / dom["launches"] if dom else None,
+        "us_per_launch": dom["us"] / dom["launches"] if dom else None,
+        "launches_per_step": dom["launches"] if dom else None,
         "step": {"achieved": achieved_tflops, "frac": achieved_tflops / peak,
+                 "sum_of_kernels_ms": sum(g["us"] for g in groups.values()) * 1e-3 if groups else None,
                  "note": "algorithmic conv FLOPs of forward_feature (146.630 GFLOP/tile, counted once whatever the "
-                         "split-precision passes) / step time, per GPU"},
+                         "split-precision passes) / step time, per GPU; sum_of_kernels_ms = the RDB trunk's 345 launches at "
+                         "their isolated (burst-clock) durations"},
         "kernels": kernels,
-        "note": f"numerics={args.numerics}; per-kernel durations: CUDA events around 50 back-to-back launches of the "
-                "layer shape at this batch on torch's current stream (the stream the library launches on), inputs "
-                "200 MB > L2; traffic = dram__bytes_read+write per launch from the committed ncu capture",
+        "note": f"numerics={args.numerics}; dominant kernel = largest (duration x launches) by kernel name; per-launch figures are "
+                "means over its layer shapes; durations: CUDA events around 50 back-to-back launches of each layer shape at this "
+                "batch on torch's current stream (the stream the library launches on), inputs 200 MB > L2; traffic = "
+                "dram__bytes_read+write per launch from the committed ncu capture",
     }
     line.update(extras)
+    if not args.no_train:
+        del net, resident, dev_in
+        sink.clear()
+        torch.cuda.empty_cache()
+        line["train"] = train_leg(args, dev, dist, world, rank, K, W, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        tps, cms, cores = cpu_reference_run(args, 2, 1, args.cpu_sample_tiles)
+        cpu_tiles = args.cpu_sample_tiles or 8
+        tps, cms, cores = cpu_reference_run(args, 2, 1, cpu_tiles)
         line["cpu_baseline"] = {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
-                                "sample": f"2 steps x {args.cpu_sample_tiles} tiles of the same workload, "
-                                          "oracle/ref_torch.py (torch.nn.functional, all host threads)"}
+                                "sample": f"2 steps x {cpu_tiles} tiles of the same workload, "
+                                          "oracle/ref_torch.py = oracle PORT of the reference modules "
+                                          "(torch.nn.functional, all host threads)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

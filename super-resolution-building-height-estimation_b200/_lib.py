@@ -177,6 +177,93 @@ def stream_ptr(device=None) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def on_device(t: torch.Tensor):
+    """Context that makes `t`'s GPU the current CUDA device for the ctypes call inside it: the library
+    launches with `<<<>>>` on the caller's stream and builds tensor maps / reads the SM count of the
+    CURRENT device, so a tensor living on another GPU than the current one must switch first."""
+    return torch.cuda.device(t.device)
+
+
+def device_guarded(fn):
+    """Decorator: run `fn` with the GPU of its first CUDA-tensor argument as the current device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+
+    return wrapper
+
+
+# ------------------------------------------------------------------ packed-weight cache keys
+# Packed weights / folded BatchNorm vectors are private caches keyed on (data_ptr, _version) of the
+# source tensors.  `_version` is bumped by every in-place op on the tensor itself (optimizer steps,
+# `copy_`, `load_state_dict`, `.to()` re-allocation) but NOT by writes through `.data` / `.detach()`
+# aliases (EMA loops of the form `p.data.mul_(d).add_(...)`), nor by raw-pointer writes from a kernel.
+# Three safety nets: (1) modules drop their caches in `_apply` and `_load_from_state_dict`;
+# (2) `invalidate_cache(module)` for callers that mutate through `.data`; (3) BHSR_STRICT_CACHE=1 adds a
+# device-side content fingerprint to every key (one host sync per forward — correctness over speed).
+STRICT_CACHE = os.environ.get("BHSR_STRICT_CACHE", "0") == "1"
+
+
+def tensor_key(tensors) -> tuple:
+    ts = [t for t in tensors if t is not None]
+    key = tuple((t.data_ptr(), t._version) for t in ts)
+    if STRICT_CACHE and ts:
+        fl = [t.detach().float() for t in ts if t.is_floating_point() and t.numel()]
+        if fl:
+            norms = torch._foreach_norm(fl)
+            sums = [t.sum() for t in fl[:8]]           # sign-sensitive part on a few tensors
+            key += (float(torch.stack(norms).double().sum()), float(torch.stack(sums).double().sum()))
+    return key
+
+
+def bump_version(*tensors) -> None:
+    """Mark tensors a kernel wrote through their raw pointer as modified (autograd version counter)."""
+    inc = getattr(torch._C, "_increment_version", None)
+    for t in tensors:
+        if t is None:
+            continue
+        if inc is not None:
+            try:
+                inc(t)
+                continue
+            except Exception:
+                pass
+        t.add_(0)
+
+
+def invalidate_cache(module) -> None:
+    """Drop every packed-weight / folded-BatchNorm cache under `module` (call after mutating parameters
+    or buffers through `.data`, e.g. an EMA update `p.data.mul_(d).add_(q.data, alpha=1-d)`)."""
+    for m in module.modules():
+        m.__dict__.pop("_tc_cache", None)
+        m.__dict__.pop("_tc_own", None)
+        if "_packed" in m.__dict__:
+            m.__dict__["_packed"] = None
+
+
+class CacheMixin:
+    """nn.Module mixin: caches die with `.to()/.cuda()/.half()` (`_apply`) and with `load_state_dict`."""
+
+    def invalidate_cache(self):
+        invalidate_cache(self)
+
+    def _apply(self, fn, *args, **kwargs):
+        invalidate_cache(self)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        invalidate_cache(self)
+        return super()._load_from_state_dict(*args, **kwargs)
+
+
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 

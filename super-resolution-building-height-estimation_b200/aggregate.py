@@ -23,8 +23,9 @@ def _block_aggregate(data: torch.Tensor, step: int, thr: float, strict: bool) ->
         x = data.float().contiguous()
         out = torch.empty(lead + (oh, ow), dtype=torch.float32, device=data.device)
         nimg = int(np.prod(lead)) if lead else 1
-        _lib.check(_lib.load().bhsr_aggregate(x.data_ptr(), nimg, h, w, step, float(thr), int(strict),
-                                              out.data_ptr(), _lib.stream_ptr(data.device)), "bhsr_aggregate")
+        with _lib.on_device(data):
+            _lib.check(_lib.load().bhsr_aggregate(x.data_ptr(), nimg, h, w, step, float(thr), int(strict),
+                                                  out.data_ptr(), _lib.stream_ptr(data.device)), "bhsr_aggregate")
         return out
     x = data.float()[..., : oh * step, : ow * step].reshape(lead + (oh, step, ow, step))
     s1 = x.sum(dim=(-3, -1))

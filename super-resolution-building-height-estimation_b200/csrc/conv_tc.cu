@@ -46,6 +46,19 @@ namespace bhsr {
 // ------------------------------------------------------------------ host side
 static long long* g_dbg_buf = nullptr;
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: one flag per
+// (template instantiation, device).  Returns true the first time it is asked about the current device.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;  // unknown: always set
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 static constexpr int kStageBytes = 4 * 32 * 80;  // epilogue store-transpose staging
 static constexpr int kTailBytes = (2 * kMaxAStages + 4 + 2 * kMaxWSlots) * 8 + 16 + 2 * 64 * 4 + 64 + kStageBytes;
 
@@ -113,12 +126,10 @@ template <int N, bool EXACT, int MB, int KS, int WMODE>
 static int launch_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
                          const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
   auto kern = conv_tc_kernel<N, EXACT, MB, KS, WMODE>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;  // per template instantiation
+  if (attr_once.first())
     BHSR_CUDA_CHECK(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set = true;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -233,12 +244,10 @@ template <bool EXACT, int MB, bool WRES>
 static int launch_dx_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
                             const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
   auto kern = conv_dx_kernel<EXACT, MB, WRES, false>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
     BHSR_CUDA_CHECK(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set = true;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kDxThreads);
@@ -325,11 +334,9 @@ static int launch_pair(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStrea
   auto kern = conv_pair_kernel;
   static int max_clusters = -1;
   const int smem_bytes = 1024 + astages * A_STAGE + wslots * kPairWSlab + kTailBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
     BHSR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set = true;
-  }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -386,11 +393,10 @@ static int launch_dx_pair(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaSt
   const int smem_bytes = 1024 + astages * A_STAGE + wslots * W_SLAB + kDxTailBytes;
   auto kern_r = conv_dx_kernel<true, 2, true, true>;
   auto kern_s = conv_dx_kernel<true, 2, false, true>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     BHSR_CUDA_CHECK(cudaFuncSetAttribute(kern_r, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     BHSR_CUDA_CHECK(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];

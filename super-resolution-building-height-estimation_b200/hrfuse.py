@@ -63,7 +63,8 @@ def _conv(x: Tensor, w: Tensor, b: Optional[Tensor] = None, *, in_affine=None, i
     d.y_shuffle = int(y_shuffle)
     d.stats = _lib.ptr(stats)
     d.accumulate = int(accumulate)
-    _lib.check(_lib.load().bhsr_head_conv(C.byref(d), _st(x)), "bhsr_head_conv")
+    with _lib.on_device(x):
+        _lib.check(_lib.load().bhsr_head_conv(C.byref(d), _st(x)), "bhsr_head_conv")
     return y
 
 
@@ -79,8 +80,9 @@ def _wgrad(x: Tensor, dy: Tensor, cout: int, cin: int, k: int, *, in_affine=None
     d.cout, d.ksize = cout, k
     dw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
     db = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_db else None
-    _lib.check(_lib.load().bhsr_head_conv_wgrad(C.byref(d), dy.data_ptr(), dy.shape[1], 0, int(dy_unshuffle),
-                                                dw.data_ptr(), _lib.ptr(db), _st(x)), "bhsr_head_conv_wgrad")
+    with _lib.on_device(x):
+        _lib.check(_lib.load().bhsr_head_conv_wgrad(C.byref(d), dy.data_ptr(), dy.shape[1], 0, int(dy_unshuffle),
+                                                    dw.data_ptr(), _lib.ptr(db), _st(x)), "bhsr_head_conv_wgrad")
     return dw, db
 
 
@@ -110,10 +112,17 @@ def _bn_from_stats(stats: Tensor, count: int, bn: "_BNParams", training_update: 
                                             _lib.ptr(rv), s.scale.data_ptr(), s.shift.data_ptr(),
                                             s.mean.data_ptr(), s.invstd.data_ptr(), _st(stats)),
                "bhsr_bn_finalize")
+    if training_update:   # the kernel wrote the running statistics through raw pointers
+        _lib.bump_version(rm, rv)
     return s
 
 
 def _bn_eval(bn: "_BNParams") -> _BNState:
+    with _lib.on_device(bn.gamma):
+        return _bn_eval_impl(bn)
+
+
+def _bn_eval_impl(bn: "_BNParams") -> _BNState:
     c = bn.gamma.numel()
     dev = bn.gamma.device
     s = _BNState()
@@ -133,7 +142,9 @@ class _BNParams:
         self.gamma, self.beta = gamma, beta
         self.running_mean, self.running_var = running_mean, running_var
         self.eps = float(eps)
-        self.momentum = float(momentum if momentum is not None else 0.1)
+        if momentum is None:
+            raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative moving average) has no B200 kernel")
+        self.momentum = float(momentum)
 
 
 # ------------------------------------------------------------------ autograd: plain conv
@@ -169,6 +180,7 @@ def conv2d(x, weight, bias=None, pixel_shuffle=False):
 # ------------------------------------------------------------------ autograd: BasicBlock
 class _BasicBlockFn(torch.autograd.Function):
     @staticmethod
+    @_lib.device_guarded
     def forward(ctx, x, training, bn_cfg, w1, g1, b1, w2, g2, b2, wd, gd, bd, *buffers):
         # buffers: rm1, rv1, rm2, rv2 [, rmd, rvd]  (updated in place in training mode)
         x = _prep(x)
@@ -217,6 +229,7 @@ class _BasicBlockFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.device_guarded
     def backward(ctx, g_out):
         lib = _lib.load()
         t = ctx.saved_tensors
@@ -322,7 +335,7 @@ def _planes(nb, h, w, c, dev):
 
 def _cache_get(module: nn.Module, build):
     """Packed weights / folded BN vectors of `module`, rebuilt when any tensor changed."""
-    key = tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    key = _lib.tensor_key(list(module.parameters()) + list(module.buffers()))
     cached = module.__dict__.get("_tc_cache")
     if cached is None or cached[0] != key:
         cached = (key, build())
@@ -468,7 +481,7 @@ def conv1x1(in_planes, out_planes, stride=1):
     return nn.Conv2d(in_planes, out_planes, kernel_size=1, stride=stride, bias=False)
 
 
-class BasicBlock(nn.Module):
+class BasicBlock(_lib.CacheMixin, nn.Module):
     """SR/HRfuse.py:109-159."""
 
     def __init__(self, inplanes: int, planes: int, stride: int = 1, groups: int = 1, base_width: int = 64,
@@ -500,6 +513,13 @@ class BasicBlock(nn.Module):
             if not isinstance(bn, nn.BatchNorm2d) or not bn.affine or not bn.track_running_stats:
                 raise NotImplementedError("BasicBlock kernels expect affine nn.BatchNorm2d with running stats")
         training = self.training
+        for bn in bns:
+            if bn.training != training:
+                raise NotImplementedError(
+                    "BasicBlock: its BatchNorm layers must be in the same train/eval mode as the block (freezing "
+                    "only the BatchNorm submodules with .eval() is not supported by the fused kernels)")
+            if bn.momentum is None:
+                raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative moving average) has no B200 kernel")
         if training:
             for bn in bns:
                 bn.num_batches_tracked.add_(1)
@@ -544,7 +564,7 @@ class HRfeature(nn.Sequential):
         return super().forward(x)
 
 
-class HRfuse_residual(nn.Module):
+class HRfuse_residual(_lib.CacheMixin, nn.Module):
     """SR/HRfuse.py:173-190."""
 
     def __init__(self, hr_chans=16, lr_chans=16, mid_chans=16, out_chans=3, upscale=4):
@@ -569,8 +589,8 @@ class HRfuse_residual(nn.Module):
                     "last": (_pack3x3(self.conv_last.weight, 32), _padvec(self.conv_last.bias, 32, dev))}
 
         c = self.__dict__.get("_tc_own")
-        key = tuple((t.data_ptr(), t._version) for t in [m.weight for m in convs] + [m.bias for m in convs] +
-                    [self.conv_last.weight, self.conv_last.bias])
+        key = _lib.tensor_key([m.weight for m in convs] + [m.bias for m in convs] +
+                              [self.conv_last.weight, self.conv_last.bias])
         if c is None or c[0] != key:
             c = (key, build())
             self.__dict__["_tc_own"] = c

@@ -36,6 +36,7 @@ def packed_conv_weight_elems(cout: int, cin: int, ntaps: int, numerics: int) -> 
     return _lib.load().bhsr_packed_conv_weight_bytes(cout, cin, ntaps, numerics) // 2
 
 
+@_lib.device_guarded
 def pack_conv_weights(w: torch.Tensor, numerics: int, fold_phase: int = -1,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """OIHW fp32 [cout, cin, 3, 3] -> packed fp16 blob for conv_tc (see bhsr.h)."""
@@ -54,6 +55,7 @@ def pack_conv_weights(w: torch.Tensor, numerics: int, fold_phase: int = -1,
     return out
 
 
+@_lib.device_guarded
 def conv_tc(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: int, cin: int,
             w_packed: torch.Tensor, cout: int, bias: Optional[torch.Tensor],
             taps: Sequence[Tuple[int, int]],
@@ -116,6 +118,7 @@ def conv_tc(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: int, c
     _lib.check(_lib.load().bhsr_conv_tc(d, _lib.stream_ptr(in_hi.device)), "bhsr_conv_tc")
 
 
+@_lib.device_guarded
 def nchw_to_planes(x: torch.Tensor, out_hi: torch.Tensor, out_lo: Optional[torch.Tensor],
                    choff: int = 0) -> None:
     _lib.require_cuda(x, "x")
@@ -128,6 +131,7 @@ def nchw_to_planes(x: torch.Tensor, out_hi: torch.Tensor, out_lo: Optional[torch
                "bhsr_nchw_f32_to_planes")
 
 
+@_lib.device_guarded
 def planes_to_nchw(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], c: int, choff: int = 0,
                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _lib.require_cuda(in_hi, "in_hi")
@@ -141,6 +145,7 @@ def planes_to_nchw(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], c: int, c
     return out
 
 
+@_lib.device_guarded
 def conv3x3_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
                   out_hi: torch.Tensor, out_lo: Optional[torch.Tensor], out_choff: int = 0) -> None:
     """fp32 NCHW (any strides) -> planes; SR/rrdbnet_arch.py:232."""
@@ -156,6 +161,7 @@ def conv3x3_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Te
                "bhsr_conv3x3_first")
 
 
+@_lib.device_guarded
 def conv3x3_last(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: int, cin: int,
                  weight: torch.Tensor, bias: Optional[torch.Tensor], lrelu_in: bool,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:

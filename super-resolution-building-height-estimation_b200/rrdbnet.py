@@ -164,7 +164,7 @@ def _check_widths(num_feat, num_grow_ch):
 
 
 # ------------------------------------------------------------------ the network
-class _RRDBNetBase(nn.Module):
+class _RRDBNetBase(_lib.CacheMixin, nn.Module):
     """Shared engine: subclasses define the child-module names."""
 
     # attribute names: (conv_first, body, conv_body, conv_up1, conv_up2, conv_hr, conv_last)
@@ -191,10 +191,8 @@ class _RRDBNetBase(nn.Module):
         return convs
 
     def _cache_key(self, convs, device, numerics):
-        key = [str(device), numerics]
-        for c in convs:
-            key.append((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version))
-        return tuple(key)
+        # see _lib.tensor_key for what invalidates the packed-weight cache (and what cannot: `.data` writes)
+        return (str(device), numerics) + _lib.tensor_key([t for c in convs for t in (c.weight, c.bias)])
 
     def _get_packed(self, device):
         lib = _lib.load()

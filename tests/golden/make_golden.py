@@ -6,7 +6,7 @@ SR/RRDBNet.py, SR/HRfuse.py and aggregate_utils.py import after stubbing their u
 matplotlib / rasterio imports; mymodels.py does not parse (IndentationError at line 467), so
 its hot class is exec'd from the source slice lines 7-14 + 231-337 with the smp names bound to
 this repo's stand-in encoder/decoder (smp is a third-party dependency absent from the reference
-tree).  Inputs and parameters come from tests/golden/synth.py.
+tree) — exec_reference_srregress() / srregress_goldens() below.  Inputs and parameters come from tests/golden/synth.py.
 
 Also stages the one real checkpoint the reference ships (SR/pretrained/RealESRGAN_x4plus.pth)
 into oracle/_ref/ (git-ignored; travels to the GPU box) for the realistic-weights parity test.
@@ -57,7 +57,82 @@ def import_reference():
     old = load("SR.RRDBNet", "SR/RRDBNet.py")
     hrf = load("SR.HRfuse", "SR/HRfuse.py")
     agg = load("aggregate_utils", "aggregate_utils.py")
+    load("SR.edsr", "SR/edsr.py")   # imported by mymodels.py:10
     return arch, old, hrf, agg
+
+
+def exec_reference_srregress():
+    """The reference `SRRegress_Cls_feature` (mymodels.py:231-337).  mymodels.py cannot be imported
+    (IndentationError at :467), so the class is exec'd from the source slice lines 7-14 (imports) +
+    231-337 (the class), SURVEY.md §8(c), with `segmentation_models_pytorch{,.encoders,.decoders.unet}`
+    bound to this repo's stand-in (bhsr.smp_compat: the third-party package is absent from the
+    reference tree).  Everything else the class touches — SR.HRfuse.{HRfeature, HRfuse_residual},
+    nn.Conv2d — is the reference's own code imported by import_reference()."""
+    import bhsr  # noqa: F401  (package alias)
+    from bhsr import smp_compat
+    smp = types.ModuleType("segmentation_models_pytorch")
+    enc = types.ModuleType("segmentation_models_pytorch.encoders")
+    dec = types.ModuleType("segmentation_models_pytorch.decoders")
+    unet = types.ModuleType("segmentation_models_pytorch.decoders.unet")
+    enc.get_encoder = smp_compat.get_encoder
+    unet.UnetDecoder = smp_compat.UnetDecoder
+    smp.encoders, smp.decoders, dec.unet = enc, dec, unet
+    for m in (smp, enc, dec, unet):
+        sys.modules[m.__name__] = m
+    with open(os.path.join(REF, "mymodels.py")) as f:
+        lines = f.readlines()
+    src = "".join(lines[6:14]) + "\n" + "".join(lines[230:337])
+    ns = {"__name__": "mymodels_slice"}
+    exec(compile(src, os.path.join(REF, "mymodels.py") + "[7-14,231-337]", "exec"), ns)
+    return ns["SRRegress_Cls_feature"]
+
+
+def srregress_goldens(out):
+    """a16: forward / forward_unsup / forward_nobuild of the reference class, isaggre True and False,
+    eval mode, on CPU.  The reference-owned parameters come from synth.head_state; the stand-in
+    encoder / decoders are built under torch.manual_seed(synth.SRREGRESS_SEED) and perturbed by
+    synth.perturb_smp_state (a checksum of them is stored so the tests can prove they rebuilt the
+    same tensors)."""
+    cls = exec_reference_srregress()
+    x = synth.tiles(2, 8, seed=3)
+    sf = synth.features(2, 64, 256, 256, seed=4)
+    for isaggre in (True, False):
+        torch.manual_seed(synth.SRREGRESS_SEED)
+        net = cls("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64, super_mid=16,
+                  upscale=4, isaggre=isaggre, chans_build=7)
+        sd = synth.head_state(64, 16, 7, isaggre, seed=100)
+        missing, unexpected = net.load_state_dict({k: t(v) for k, v in sd.items()}, strict=False)
+        assert not unexpected and all(k.split(".")[0] in ("encoder", "decoder1", "decoder2") for k in missing)
+        synth.perturb_smp_state(net)
+        net.eval()
+        tag = "aggre" if isaggre else "noaggre"
+        out[f"srregress_{tag}_smp_checksum"] = synth.smp_checksum(net)
+        with torch.no_grad():
+            res = net(t(x), t(sf))
+            names = ("height", "build", "height_aggre")[:len(res)]
+            for n, r in zip(names, res):
+                r = r.numpy()
+                out[f"srregress_{tag}_{n}_stats"] = synth.stats(r)
+                if n == "height_aggre":
+                    out[f"srregress_{tag}_{n}"] = r
+                else:
+                    out[f"srregress_{tag}_{n}_sub"] = synth.subsample(r, 1, 4)
+                    out[f"srregress_{tag}_{n}_corner"] = np.ascontiguousarray(r[0, :, :24, :24])
+                    out[f"srregress_{tag}_{n}_edge"] = np.ascontiguousarray(r[1, :, 232:, 232:])
+            if isaggre:
+                u = net.forward_unsup(t(x), t(sf)).numpy()
+                assert u.shape == (2, 256, 256)
+                out["srregress_aggre_unsup_sub"] = np.ascontiguousarray(u[:, ::4, ::4])
+                nb = net.forward_nobuild(t(x), t(sf))
+                assert len(nb) == 2
+                out["srregress_aggre_nobuild_height_sub"] = synth.subsample(nb[0].numpy(), 1, 4)
+                out["srregress_aggre_nobuild_height_aggre"] = nb[1].numpy()
+            else:
+                nb = net.forward_nobuild(t(x), t(sf))
+                assert isinstance(nb, torch.Tensor)
+                out["srregress_noaggre_nobuild_height_sub"] = synth.subsample(nb.numpy(), 1, 4)
+        print(f"srregress {tag}: height range", float(res[0].min()), float(res[0].max()),
+              "build range", float(res[1].min()), float(res[1].max()))
 
 
 def t(a):
@@ -74,6 +149,14 @@ def main():
     torch.manual_seed(0)
     arch, old, hrf, agg = import_reference()
     out = {}
+    if "--only-srregress" in sys.argv:   # add / refresh the a16 vectors, keep every other array as it is
+        path = os.path.join(HERE, "reference_vectors.npz")
+        with np.load(path) as z:
+            out = {k: z[k] for k in z.files if not k.startswith("srregress_")}
+        srregress_goldens(out)
+        np.savez_compressed(path, **out)
+        print("updated reference_vectors.npz", os.path.getsize(path) / 1e6, "MB;", len(out), "arrays")
+        return
 
     # ---------------------------------------------------------------- RRDBNet, 2 blocks
     with torch.no_grad():
@@ -170,6 +253,9 @@ def main():
         up_in = synth.features(1, 2, 3, 4, seed=10)
         out["nearest_in"] = up_in
         out["nearest_x2"] = torch.nn.functional.interpolate(t(up_in), scale_factor=2, mode="nearest").numpy()
+
+    # ---------------------------------------------------------------- SRRegress_Cls_feature (a16)
+    srregress_goldens(out)
 
     # ---------------------------------------------------------------- aggregation
     h256 = (np.random.RandomState(8).rand(1, 1, 256, 256) * 60).astype(np.float32)

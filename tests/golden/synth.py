@@ -129,6 +129,45 @@ def head_state(super_in=64, super_mid=16, chans_build=7, isaggre=True, seed=0):
     return sd
 
 
+SRREGRESS_SEED = 4321  # torch seed under which the a16 golden model is constructed
+
+
+def perturb_smp_state(model, seed=77):
+    """Make the third-party (encoder / decoder) part of an SRRegress_Cls_feature non-trivial and
+    identical wherever it is built: after a `torch.manual_seed(SRREGRESS_SEED)` construction the
+    BatchNorm affine parameters and running statistics of `encoder.*`, `decoder1.*`, `decoder2.*`
+    are overwritten in state_dict key order from a numpy RandomState (a fresh BatchNorm is the
+    identity in eval mode, which would hide wiring errors).  Used by make_golden.py on the
+    REFERENCE class and by the tests on the drop-in class."""
+    import torch
+    rng = np.random.RandomState(seed)
+    sd = model.state_dict()
+    new = {}
+    for k in sd:
+        if k.split(".")[0] not in ("encoder", "decoder1", "decoder2"):
+            continue
+        v = sd[k]
+        base = k.rsplit(".", 1)[0]
+        if k.endswith("running_mean") and (base + ".running_var") in sd:
+            c = v.numel()
+            new[k] = torch.from_numpy((0.1 * rng.standard_normal(c)).astype(np.float32))
+            new[base + ".running_var"] = torch.from_numpy((0.6 + 0.8 * rng.rand(c)).astype(np.float32))
+            new[base + ".weight"] = torch.from_numpy((1.0 + 0.2 * rng.standard_normal(c)).astype(np.float32))
+            new[base + ".bias"] = torch.from_numpy((0.1 * rng.standard_normal(c)).astype(np.float32))
+    model.load_state_dict(new, strict=False)
+    return model
+
+
+def smp_checksum(model) -> np.ndarray:
+    """[sum, abs-sum, count] over the encoder / decoder tensors: guards the seeded construction."""
+    s = a = n = 0.0
+    for k, v in model.state_dict().items():
+        if k.split(".")[0] in ("encoder", "decoder1", "decoder2") and v.dtype.is_floating_point:
+            vd = v.double()
+            s += float(vd.sum()); a += float(vd.abs().sum()); n += v.numel()
+    return np.array([s, a, n])
+
+
 def tiles(nb, c, h=64, w=64, seed=1337) -> np.ndarray:
     """Synthetic Sentinel tiles: uniform [0,1] like the loader's clipped min-max normalisation
     (BH_loader.py:367-369)."""

@@ -142,6 +142,56 @@ def test_hrfuse_residual_backward(dev, training):
         assert_close(p.grad.cpu().numpy(), grads_ref[name], rtol=2e-3, atol=scale(grads_ref[name]), what=f"grad {name}")
 
 
+def test_head_backward_config3_shape(dev):
+    """BASELINE config 3's shapes (64x64 tiles -> 256x256 maps, train-mode BatchNorm, weighted MSE), batch 8:
+    HRfeature(64->16) + HRfuse_residual(out=1) forward and EVERY parameter gradient (conv weights / biases,
+    BatchNorm affine) plus the gradient flowing back into the decoder features, against fp64 autograd of the
+    oracle.  Covers the order-dependent atomics of wgrad / BN statistics at the real reduction length
+    (8 x 65536 pixels)."""
+    from bhsr import hrfuse
+    nb = 8
+    sdf = synth.hrfeature_state(seed=71)
+    sdr = synth.hrfuse_residual_state(out=1, seed=72)
+    hr = synth.features(nb, 64, 256, 256, seed=11)
+    lr = synth.features(nb, 16, 64, 64, seed=12)
+    rng = np.random.RandomState(13)
+    target = (rng.rand(nb, 1, 256, 256) * 30 * (rng.rand(nb, 1, 256, 256) > 0.8)).astype(np.float32)
+    weight = (0.1 + 3 * rng.rand(nb, 1, 256, 256)).astype(np.float32)
+
+    def leaf(v, name):
+        if v.dtype == np.int64:
+            return torch.from_numpy(np.ascontiguousarray(v))
+        tns = torch.from_numpy(np.ascontiguousarray(v)).double()
+        return tns.requires_grad_("running" not in name)
+
+    pf = {k: leaf(v, k) for k, v in sdf.items()}
+    pr = {k: leaf(v, k) for k, v in sdr.items()}
+    a = torch.from_numpy(lr).double().requires_grad_(True)
+    f = T.hrfeature(torch.from_numpy(hr).double(), pf, training=True)
+    y = T.hrfuse_residual(a, f, pr, training=True)
+    loss = ((y - torch.from_numpy(target).double()) ** 2 * torch.from_numpy(weight).double()).mean()
+    loss.backward()
+
+    feat = load_np_state(hrfuse.HRfeature(64, 16, 16), sdf, dev).train()
+    fuse = load_np_state(hrfuse.HRfuse_residual(16, 16, 16, 1, 4), sdr, dev).train()
+    ag = cuda(lr, dev).requires_grad_(True)
+    yg = fuse(ag, feat(cuda(hr, dev)))
+    lg = ((yg - cuda(target, dev)) ** 2 * cuda(weight, dev)).mean()
+    lg.backward()
+    assert_close(yg.detach().cpu().numpy(), y.detach().numpy(), what="forward (train-mode BN, B=8, 256x256)")
+    np.testing.assert_allclose(float(lg), float(loss), rtol=1e-4)
+    scale = lambda r: 1e-4 * max(1e-3, float(np.abs(r).max()))
+    assert_close(ag.grad.cpu().numpy(), a.grad.numpy(), rtol=2e-3, atol=scale(a.grad.numpy()), what="grad decoder features")
+    for mod, ref in ((feat, pf), (fuse, pr)):
+        for name, p in mod.named_parameters():
+            assert p.grad is not None, name
+            r = ref[name].grad.numpy()
+            assert_close(p.grad.cpu().numpy(), r, rtol=2e-3, atol=scale(r), what=f"grad {name}")
+        for name, buf in mod.named_buffers():     # running statistics updated like nn.BatchNorm2d
+            if "running" in name:
+                np.testing.assert_allclose(buf.cpu().numpy(), ref[name].detach().numpy(), rtol=1e-4, atol=1e-5, err_msg=name)
+
+
 def test_srregress_head_vs_oracle(dev):
     """hrfeat + reg + seg + aggre_height wiring of SRRegress_Cls_feature.forward (mymodels.py:270-293)
     given the decoder features (the smp part is third-party, not under test here)."""
@@ -204,3 +254,42 @@ def test_aggregate_kernel_vs_golden(dev, golden):
     y2 = aggregate.aggregate_torch_gpu(cuda(x, dev), 0.25, device=dev)
     assert y2.shape == (1, 1, 64, 64)
     assert_close(y2.cpu().numpy(), golden["aggregate_torch_gpu"], rtol=1e-5, atol=1e-3, what="aggregate_torch_gpu")
+
+
+@pytest.mark.parametrize("isaggre", [True, False])
+def test_srregress_forward_vs_reference_golden(dev, golden, isaggre):
+    """a16: the drop-in SRRegress_Cls_feature.forward / forward_unsup / forward_nobuild on the GPU against
+    the outputs of the REFERENCE class itself (mymodels.py:270-337, exec'd by tests/golden/make_golden.py
+    with the same stand-in encoder/decoders) — pins the wiring end to end, eval mode."""
+    from test_oracle_golden import build_srregress, check_srregress_outputs
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False       # the smp part is stock PyTorch: compare in true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        tag = "aggre" if isaggre else "noaggre"
+        net, _ = build_srregress(isaggre, dev)
+        np.testing.assert_allclose(synth.smp_checksum(net), golden[f"srregress_{tag}_smp_checksum"], rtol=1e-6)
+        x = cuda(synth.tiles(2, 8, seed=3), dev)
+        sf = cuda(synth.features(2, 64, 256, 256, seed=4), dev)
+        with torch.no_grad():
+            out = net(x, sf)
+            assert len(out) == (3 if isaggre else 2)
+            check_srregress_outputs(golden, tag, out[0].cpu().numpy(), out[1].cpu().numpy(),
+                                    out[2].cpu().numpy() if isaggre else None)
+            if isaggre:
+                u = net.forward_unsup(x, sf)
+                assert u.shape == (2, 256, 256)
+                assert_close(u.cpu().numpy()[:, ::4, ::4], golden["srregress_aggre_unsup_sub"], what="forward_unsup")
+                h2, a2 = net.forward_nobuild(x, sf)
+                assert_close(synth.subsample(h2.cpu().numpy(), 1, 4), golden["srregress_aggre_nobuild_height_sub"])
+                assert_close(a2.cpu().numpy(), golden["srregress_aggre_nobuild_height_aggre"])
+            else:
+                h2 = net.forward_nobuild(x, sf)
+                assert_close(synth.subsample(h2.cpu().numpy(), 1, 4), golden["srregress_noaggre_nobuild_height_sub"])
+        # the autograd (training-kernel) path of the same modules in eval mode must agree too
+        xg = x.clone().requires_grad_(True)
+        out_g = net(xg, sf)
+        check_srregress_outputs(golden, tag, out_g[0].detach().cpu().numpy(), out_g[1].detach().cpu().numpy(),
+                                out_g[2].detach().cpu().numpy() if isaggre else None)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32

@@ -114,3 +114,56 @@ def test_hierweight_known_answer(golden):
     """BH_loader.py:1116-1124: the reference prints these weights for the globe statistics."""
     w = R.hierweight(golden["bh_stats_globe"], (0, 3, 12, 21, 30, 60, 90, 255))
     np.testing.assert_allclose(w, golden["hierweight_kat"], rtol=0, atol=5e-9)
+
+
+def build_srregress(isaggre, device="cpu"):
+    """The drop-in SRRegress_Cls_feature exactly as make_golden.py built the reference class: seeded
+    construction, synth.head_state for the reference-owned parameters, perturbed stand-in smp part."""
+    from bhsr.models import SRRegress_Cls_feature
+    torch.manual_seed(synth.SRREGRESS_SEED)
+    net = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64,
+                                super_mid=16, upscale=4, isaggre=isaggre, chans_build=7)
+    sd = synth.head_state(64, 16, 7, isaggre, seed=100)
+    missing, unexpected = net.load_state_dict(tdict(sd), strict=False)
+    assert not unexpected and all(k.split(".")[0] in ("encoder", "decoder1", "decoder2") for k in missing)
+    synth.perturb_smp_state(net)
+    return net.to(device).eval(), sd
+
+
+def check_srregress_outputs(golden, tag, height, build, aggre=None, **tol):
+    """Compare full outputs with every a16 golden array of configuration `tag`."""
+    for name, r in (("height", height), ("build", build)):
+        assert_close(synth.subsample(r, 1, 4), golden[f"srregress_{tag}_{name}_sub"], what=f"{tag} {name}", **tol)
+        assert_close(r[0, :, :24, :24], golden[f"srregress_{tag}_{name}_corner"], what=f"{tag} {name} corner", **tol)
+        assert_close(r[1, :, 232:, 232:], golden[f"srregress_{tag}_{name}_edge"], what=f"{tag} {name} edge", **tol)
+        np.testing.assert_allclose(synth.stats(r)[1:3], golden[f"srregress_{tag}_{name}_stats"][1:3], rtol=1e-3)
+    if aggre is not None:
+        assert_close(aggre, golden[f"srregress_{tag}_height_aggre"], what=f"{tag} height_aggre", **tol)
+
+
+@pytest.mark.parametrize("isaggre", [True, False])
+def test_srregress_wiring_vs_reference_golden(golden, isaggre):
+    """a16: the oracle's restatement of SRRegress_Cls_feature.forward (mymodels.py:270-293) against the
+    outputs of the REFERENCE class (exec'd source slice, tests/golden/make_golden.py).  The decoder
+    features come from the stand-in smp modules run on CPU — the same modules the generator bound into
+    the reference class; their rebuilt tensors are proven identical by the stored checksum."""
+    tag = "aggre" if isaggre else "noaggre"
+    net, sd = build_srregress(isaggre)
+    np.testing.assert_allclose(synth.smp_checksum(net), golden[f"srregress_{tag}_smp_checksum"], rtol=1e-12)
+    x = torch.from_numpy(synth.tiles(2, 8, seed=3))
+    sf = torch.from_numpy(synth.features(2, 64, 256, 256, seed=4))
+    with torch.no_grad():
+        enc = net.encoder(x)
+        hfea, bfea = net.decoder1(*enc), net.decoder2(*enc)
+        out = T.srregress_head(hfea, bfea, sf, tdict(sd), isaggre)
+    check_srregress_outputs(golden, tag, out[0].numpy(), out[1].numpy(), out[2].numpy() if isaggre else None,
+                            rtol=1e-4, atol=1e-4)
+    if isaggre:   # forward_unsup = height squeezed, forward_nobuild = (height, height_aggre)  (:295-337)
+        assert_close(out[0].numpy()[:, 0, ::4, ::4], golden["srregress_aggre_unsup_sub"], rtol=1e-4, atol=1e-4)
+        assert_close(synth.subsample(out[0].numpy(), 1, 4), golden["srregress_aggre_nobuild_height_sub"], rtol=1e-4, atol=1e-4)
+        assert_close(out[2].numpy(), golden["srregress_aggre_nobuild_height_aggre"], rtol=1e-4, atol=1e-4)
+        # numpy oracle on the same decoder features
+        ref = R.srregress_head(hfea.numpy(), bfea.numpy(), sf.numpy(), sd, True)
+        check_srregress_outputs(golden, tag, ref[0], ref[1], ref[2], rtol=1e-4, atol=1e-4)
+    else:
+        assert_close(synth.subsample(out[0].numpy(), 1, 4), golden["srregress_noaggre_nobuild_height_sub"], rtol=1e-4, atol=1e-4)

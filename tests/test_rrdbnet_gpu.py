@@ -376,6 +376,37 @@ def test_rrdbnet_full_batch_properties(dev):
     assert torch.isfinite(a).all()
 
 
+def test_rrdbnet_full_batch_full_tensor_vs_oracle(dev, golden):
+    """BASELINE config 2 size (B=64, 23 blocks): FULL-tensor elementwise parity (every one of the
+    64x256x256 outputs of a tile, north-star tolerance) on four tiles spread over the batch — incl. the
+    first / last image of the CTA-pair kernels — against the torch-functional oracle run live on the host
+    (oracle/ref_torch.py is pinned to the reference's 23-block golden in tests/test_oracle_golden.py),
+    for the synthetic trained-like weights and for the reference's own constructor init."""
+    from bhsr import rrdbnet
+    from oracle import ref_torch as T
+    picks = [0, 1, 37, 63]
+    x = synth.tiles(64, 3, seed=2024)
+    for which in ("synth", "ctor"):
+        if which == "synth":
+            sd = synth.rrdbnet_state(num_block=23, seed=23)
+            net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=23, num_grow_ch=32), sd, dev)
+            tsd = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+        else:
+            torch.manual_seed(1337)   # bench.py's weights: kaiming*0.1 RDB convs, default init elsewhere
+            net = rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=23, num_grow_ch=32)
+            tsd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+            net = net.to(dev).eval()
+        with torch.no_grad():
+            fea = net.forward_feature(cuda(x, dev))
+        got = fea[picks].cpu().numpy()
+        del fea
+        ref = T.rrdbnet_forward_feature(torch.from_numpy(x[picks]).double(),
+                                        {k: v.double() for k, v in tsd.items()}).numpy()
+        assert got.shape == ref.shape == (len(picks), 64, 256, 256)
+        assert_close(got, ref, what=f"B=64 23-block full tensor ({which} weights)")
+        del net
+
+
 def test_error_behaviour(dev):
     from bhsr import rrdbnet
     from bhsr._lib import BhsrError

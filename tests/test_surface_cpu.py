@@ -187,3 +187,67 @@ def test_realesrgan_shell_has_no_side_effects():
     assert len(m.net_g.state_dict()) == 42 and m.net_g.training
     with pytest.raises(AttributeError, match="fine-tuning"):
         m.net_d
+
+
+def test_packed_weight_caches_are_invalidated():
+    """caches keyed on (data_ptr, _version) miss writes through `.data`; modules must
+    drop them on load_state_dict / .to() / explicit invalidate_cache(), and the strict mode must see the
+    content change."""
+    import torch
+    from bhsr import _lib, hrfuse, rrdbnet
+    net = rrdbnet.RRDBNet(3, 3, num_block=1)
+    blk = hrfuse.BasicBlock(32, 16)
+    fuse = hrfuse.HRfuse_residual(16, 16, 16, 1, 4)
+    for m in (net, blk, fuse):
+        m.__dict__["_tc_cache"] = ("k", "v")
+        m.__dict__["_tc_own"] = ("k", "v")
+    net._packed = ("key", None, None)
+    net.load_state_dict(net.state_dict())
+    assert net._packed is None and "_tc_cache" not in net.__dict__
+    blk.load_state_dict(blk.state_dict())
+    assert "_tc_cache" not in blk.__dict__
+    fuse.__dict__["_tc_own"] = ("k", "v")
+    fuse.double()                       # _apply
+    assert "_tc_own" not in fuse.__dict__ and "_tc_cache" not in fuse.fuse[0].__dict__
+    blk.__dict__["_tc_cache"] = ("k", "v")
+    parent = torch.nn.Sequential(blk)
+    _lib.invalidate_cache(parent)       # explicit, from any ancestor
+    assert "_tc_cache" not in blk.__dict__
+    # version keys: in-place ops on the parameter change the key, `.data` writes do not (documented) ...
+    w = blk.conv1.weight
+    k0 = _lib.tensor_key([w])
+    with torch.no_grad():
+        w.mul_(1.0)
+    assert _lib.tensor_key([w]) != k0
+    k1 = _lib.tensor_key([w])
+    w.data.mul_(2.0)
+    assert _lib.tensor_key([w]) == k1
+    # ... unless the strict (fingerprint) mode is on
+    old = _lib.STRICT_CACHE
+    try:
+        _lib.STRICT_CACHE = True
+        k2 = _lib.tensor_key([w])
+        w.data.mul_(2.0)
+        assert _lib.tensor_key([w]) != k2
+    finally:
+        _lib.STRICT_CACHE = old
+    # kernels that write running statistics through raw pointers bump the version
+    rm = blk.bn1.running_mean
+    v = rm._version
+    _lib.bump_version(rm)
+    assert rm._version > v
+
+
+def test_basic_block_rejects_unsupported_batchnorm_modes():
+    import pytest
+    import torch
+    from bhsr import hrfuse
+    blk = hrfuse.BasicBlock(16, 16)
+    blk.train()
+    blk.bn1.eval()                      # "freeze BN only": not supported by the fused kernels -> loud error
+    with pytest.raises(NotImplementedError):
+        blk(torch.zeros(1, 16, 4, 4))
+    blk2 = hrfuse.BasicBlock(16, 16)
+    blk2.bn2.momentum = None
+    with pytest.raises(NotImplementedError):
+        blk2(torch.zeros(1, 16, 4, 4))
