@@ -225,16 +225,17 @@ def reference_main(args):
     """`--impl reference`: the reference's own CPU path for the same config on the box's host cores — the oracle
     port (oracle/ref_torch.py: the stock torch.nn.functional calls the reference modules dispatch to; the
     reference is a script repo that cannot be installed and /root/reference is not on the GPU box).  Honours
-    --steps / --warmup; each step is the arm's batch (64 tiles), shrunk only if a probe step says the whole run
-    would not end within CPU_ARM_BUDGET_S."""
+    --steps / --warmup; each step is a bounded sample of the arm's batch (8 tiles: the host path's best batch size),
+    shrunk only if a probe step says the whole run would not end within CPU_ARM_BUDGET_S."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     probe_tps, _, cores = cpu_reference_run(args, 1, 0, 2 if args.cpu_sample_tiles in (1, 2) else 4)
-    tiles = int(min(args.batch, max(1, CPU_ARM_BUDGET_S * probe_tps / (steps + warmup))))
-    if args.cpu_sample_tiles > 0:
-        tiles = min(tiles, args.cpu_sample_tiles)
+    # 8 tiles per CPU step is where the host path peaks (measured on the GPU box: 11.2 tiles/s at 8 tiles per
+    # step, 5.8 tiles/s at the arm's 64 — the 1 GB activations of a 64-tile batch fall out of the host caches),
+    # so the reference is timed at ITS best batch; fewer only if the run would not fit the time budget
+    tiles = int(min(args.batch, args.cpu_sample_tiles or 8, max(1, CPU_ARM_BUDGET_S * probe_tps / (steps + warmup))))
     tps, ms, cores = cpu_reference_run(args, steps, warmup, tiles)
     cfg = forward_config(args.batch, args.batch, "f32 (reference CPU path)", 1)
     cfg["cpu_tiles_per_step"] = tiles

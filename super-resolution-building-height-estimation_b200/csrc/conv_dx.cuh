@@ -543,6 +543,28 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         // diagnostics (garbage results): 3 = no lane-shift combine (no shuffles / exchange / named
         // barrier), 4 = drain only (nothing after the accumulator release)
         if (p.nomma == 4) continue;
+        // 7 / 8: drain + ~1000 ALU instructions per thread and block with NO memory operations, as a 16 KB
+        // unrolled stream (7: instruction-cache footprint like the real epilogue) or a rolled loop (8: same
+        // dynamic count, ~0.5 KB footprint) — separates instruction-fetch pressure from issue-slot pressure
+        if (p.nomma == 7) {
+#pragma unroll
+          for (int rep = 0; rep < 32; ++rep) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v1[jj] = fmaf(v1[jj], 1.0001f + 0.001f * rep, v0[(jj + rep) & 31]);
+          }
+          if (v1[lane] == 12345.678f) printf("%f", v1[3]);
+          continue;
+        }
+        if (p.nomma == 8) {
+#pragma unroll 1
+          for (int rep = 0; rep < 32; ++rep) {
+            const float cst = 1.0001f + 0.001f * rep;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v1[jj] = fmaf(v1[jj], cst, v0[jj]);
+          }
+          if (v1[lane] == 12345.678f) printf("%f", v1[3]);
+          continue;
+        }
         if (p.nomma == 3) {
           const int f3 = (t * MB + mb) * kDxBlk - 1 + row;
           const int py3 = f3 / kPitch, pc3 = f3 - py3 * kPitch, px3 = s * kStrip + pc3;

@@ -542,7 +542,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
       p.dbg = g_dbg_buf;
     }
     static const char* nomma = getenv("BHSR_DEBUG_NOMMA");
-    p.nomma = (nomma && nomma[0] >= '1' && nomma[0] <= '6') ? nomma[0] - '0' : 0;
+    p.nomma = (nomma && nomma[0] >= '1' && nomma[0] <= '9') ? nomma[0] - '0' : 0;
   }
 
   // 32-output plain 3x3 layers with plane outputs: the dx-in-N kernel (BHSR_DXN=0 keeps the per-tap one)
