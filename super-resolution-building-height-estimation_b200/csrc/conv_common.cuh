@@ -244,6 +244,106 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
   }
 }
 
+// Eight consecutive channels of a residual pixel (hi [+ lo]) folded into x[].
+__device__ __forceinline__ void add_residual8(float (&x)[8], float alpha, const __half* hi, const __half* lo,
+                                              size_t off) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + off));
+  const __half2* ah = reinterpret_cast<const __half2*>(&a);
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(ah[j]);
+    r[2 * j] = f.x;
+    r[2 * j + 1] = f.y;
+  }
+  if (lo) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(lo + off));
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(bh[j]);
+      r[2 * j] = fmaf(f.x, 1.f / 2048.f, r[2 * j]);
+      r[2 * j + 1] = fmaf(f.y, 1.f / 2048.f, r[2 * j + 1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], alpha, r[j]);
+}
+
+// Compact epilogue of the dx-in-N kernel (32-channel plane outputs).  Round 2 measured that the size of
+// the epilogue's instruction stream, not its memory traffic, is what slows the MMA issue loop
+// (profiles/r02_icache_diagnostics.log), so everything per-channel happens AFTER the store transpose, in a
+// rolled loop with a small body:
+//   1. the lane that owns pixel `lane` of this warp's 32 writes its 32 raw fp32 sums into the warp's 4 KB
+//      staging tile (row = lane, 16-byte chunks XOR-ed with row & 7: conflict-free both ways);
+//   2. four rolled iterations: lane -> (row = it*8 + lane/4, channels 8*(lane&3)..+7): scale/bias (loop-
+//      invariant registers), LeakyReLU, residuals, ReLU, hi/lo split, one 16-byte store per plane — a
+//      store instruction covers 8 pixels x 64 B like the unrolled version did.
+constexpr int kStageRowBytes = 128;
+constexpr int kStageWarpBytes = 32 * kStageRowBytes;
+__device__ __forceinline__ void finish_planes32_rolled(const ConvTcKernelParams& p, const float (&v)[32], bool valid,
+                                                       size_t in_pix, size_t out_pix, int lane, uint8_t* stg,
+                                                       const float* s_bias, const float* s_scale) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(stg + lane * kStageRowBytes + ((g ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  const uint32_t opix32 = valid ? static_cast<uint32_t>(out_pix) : 0xFFFFFFFFu;
+  const uint32_t ipix32 = static_cast<uint32_t>(in_pix);
+  const int cg = lane & 3;
+  float b8[8], s8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    b8[j] = s_bias[cg * 8 + j];
+    s8[j] = s_scale[cg * 8 + j];
+  }
+  const bool chan_ok = cg * 8 < p.cout_valid;
+  const int epi = p.epilogue;
+  __syncwarp();
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2);
+    const uint8_t* rowp = stg + r * kStageRowBytes;
+    const float4 lo4 = *reinterpret_cast<const float4*>(rowp + (((2 * cg) ^ (r & 7)) << 4));
+    const float4 hi4 = *reinterpret_cast<const float4*>(rowp + (((2 * cg + 1) ^ (r & 7)) << 4));
+    const uint32_t op = __shfl_sync(0xffffffffu, opix32, r);
+    const uint32_t ip = __shfl_sync(0xffffffffu, ipix32, r);
+    float x[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], s8[j], b8[j]);
+    if (epi & BHSR_EPI_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = lrelu02(x[j]);
+    }
+    const bool ok = (op != 0xFFFFFFFFu) && chan_ok;
+    if (ok) {
+      if (epi & BHSR_EPI_RES1)
+        add_residual8(x, p.alpha1, p.res1_hi, p.res1_lo, static_cast<size_t>(ip) * p.res1_ctot + p.res1_choff + cg * 8);
+      if (epi & BHSR_EPI_RES2)
+        add_residual8(x, p.alpha2, p.res2_hi, p.res2_lo, static_cast<size_t>(ip) * p.res2_ctot + p.res2_choff + cg * 8);
+    }
+    if (epi & BHSR_EPI_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+    if (ok) {
+      __align__(16) __half2 hh[4];
+      __align__(16) __half2 ll[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 h2 = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+        const float2 back = __half22float2(h2);
+        hh[j] = h2;
+        ll[j] = __floats2half2_rn((x[2 * j] - back.x) * 2048.f, (x[2 * j + 1] - back.y) * 2048.f);
+      }
+      const size_t off = static_cast<size_t>(op) * p.out_ctot + p.out_choff + cg * 8;
+      *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hh);
+      if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(ll);
+    }
+  }
+  __syncwarp();   // the staging tile is rewritten by this warp's next block
+}
+
 // Work item `it` of this CTA: a whole tile (sel = -1) or, in the split last round, one block of it.
 __device__ __forceinline__ bool dx_item_at(const ConvTcKernelParams& p, int it, int idx, int cnt, int& tile,
                                            int& sel) {

@@ -43,7 +43,7 @@ namespace bhsr {
 // [tap][part][cout] to [part][dx][cout] on the way into shared memory.
 constexpr int kDxThreads = 352;
 constexpr int kDxWarpProdA = 8, kDxWarpProdW = 9, kDxWarpMma = 10;
-constexpr int kDxStageBytes = 8 * 32 * 80;          // store-transpose staging, 8 epilogue warps
+constexpr int kDxStageBytes = 8 * kStageWarpBytes;   // raw fp32 store-transpose staging, 8 epilogue warps
 constexpr int kDxXchgFloats = 2 * 2 * 4 * 64;       // [group][parity][warp][v0 of lane 31 | v2 of lane 0]
 constexpr int kDxBars = 4 * kMaxAStages + 8 + 2 * kMaxWSlots;
 constexpr int kDxTailBytes = kDxBars * 8 + 16 + 2 * 64 * 4 + 64 + kDxStageBytes + kDxXchgFloats * 4;
@@ -485,8 +485,8 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       const int sn = tile / p.tiles_per_strip;
       const int s = sn % p.n_strips;
       const int n = PAIR ? 2 * (sn / p.n_strips) + static_cast<int>(rank) : sn / p.n_strips;
-#pragma unroll
-      for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll 1
+      for (int mb = 0; mb < MB; ++mb) {                  // rolled: one copy of the epilogue body (I-cache)
         if (sel >= 0 && mb != sel) continue;             // split last round: one block of the tile
         const uint32_t blk = tile_it * MB + mb;
         if (static_cast<int>(blk & 1u) != grp) continue;   // warp-uniform
@@ -570,8 +570,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
           const int py3 = f3 / kPitch, pc3 = f3 - py3 * kPitch, px3 = s * kStrip + pc3;
           const bool valid3 = (row >= 1) && (row <= kDxBlk) && (pc3 < kStrip) && (py3 < p.h) && (px3 < p.w);
           const size_t pix3 = (static_cast<size_t>(n) * p.h + py3) * p.w + px3;
-          finish_slice32(p, v1, 0, valid3, n, py3, px3, pix3, pix3, py3, px3, warp, lane, false, s_stage, s_bias,
-                         s_scale);
+          finish_planes32_rolled(p, v1, valid3, pix3, pix3, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
           continue;
         }
 #endif
@@ -623,8 +622,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int oy = py * p.out_scale + p.out_oy;
         const int ox = px * p.out_scale + p.out_ox;
         const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
-        finish_slice32(p, v, 0, valid, n, py, px, in_pix, out_pix, oy, ox, warp, lane, false, s_stage,
-                       s_bias, s_scale);
+        finish_planes32_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
       }
     }
 #ifdef BHSR_TIMING

@@ -309,7 +309,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       t_epi_wait += clock64() - tw0;
 #endif
       tc_fence_after();
-#pragma unroll
+      // (rolled: ONE inlined copy of the epilogue body keeps the kernel's hot code inside the instruction
+      // cache — measured in round 2, profiles/r02_icache_diagnostics.log: a 16 KB unrolled epilogue stream
+      // slows the MMA issue loop as much as the whole epilogue does, the same work as a rolled loop does not)
+#pragma unroll 1
       for (int mb = 0; mb < MB; ++mb) {
         if (sel >= 0 && mb != sel) continue;             // split last round: one m-block of the tile
         const int f = t * MT + mb * 128 + row;
@@ -323,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS +
                                mb * ROWS_B;
-#pragma unroll
+#pragma unroll 1
         for (int cc = 0; cc < N / 32; ++cc) {
           uint32_t raw[32];
           float v[32];
@@ -601,7 +604,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       const int as = tile_it & 1;
       mbar_wait_cluster(bar(B_TFULL + as), (tile_it >> 1) & 1);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int mb = 0; mb < MB; ++mb) {
         if (sel >= 0 && mb != sel) continue;             // split last round: one m-block of the tile
         const int f = t * MT + mb * 128 + row;
@@ -614,7 +617,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int ox = px * p.out_scale + p.out_ox;
         const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + as * ACC_COLS + mb * ROWS_B;
-#pragma unroll
+#pragma unroll 1
         for (int cc = 0; cc < N / 32; ++cc) {
           uint32_t raw[32], rawl[32];
           float v[32];
