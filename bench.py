@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true", help="skip the other-numerics and full-D2H extras")
     ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (config 3 / 4) sub-record")
     ap.add_argument("--train-batch", type=int, default=32, help="tiles per GPU per training step")
+    ap.add_argument("--no-train-graph", action="store_true", help="time the training step eagerly only")
     return ap.parse_args()
 
 
@@ -277,7 +278,8 @@ def train_leg(args, dev, dist, world, rank, K, W, peak):
     crit = [dp.MSE_adapt_weight(0.0, dev), dp.MSE_adapt_weight(0.0, dev), dp.CE_DICE_adapt_weight(0.0, dev)]
     params = list(net.parameters()) + [c.log_var for c in crit]
     opt = torch.optim.Adam([{"params": list(net.parameters())},
-                            {"params": [c.log_var for c in crit], "name": "lossweight"}], lr=1e-3, weight_decay=1e-4)
+                            {"params": [c.log_var for c in crit], "name": "lossweight"}], lr=1e-3, weight_decay=1e-4,
+                           capturable=True)
     bucket = dp.FlatGradAllReduce(params)
     xs = [torch.from_numpy(synth.tiles(B, 8, seed=1337 + 17 * rank + i)).to(dev) for i in range(2)]
     labels = [dp.synthetic_labels(B, dev, seed=2 * rank + i) for i in range(2)]
@@ -293,20 +295,38 @@ def train_leg(args, dev, dist, world, rank, K, W, peak):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(W):
-        step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def timed_steps(fn):
+        for i in range(W):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(i)
+        e1.record()
+        barrier()
+        t_ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([t_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms
+
+    ms_eager = timed_steps(step)
+    ms, launch = ms_eager, "eager (one launch per kernel)"
+    if not args.no_train_graph:
+        try:      # the same step replayed from CUDA graphs (dp.GraphedTrainStep): inputs copied into static buffers
+            h0, ha0, b0, w0, wa0 = labels[0]
+            graphed = dp.GraphedTrainStep(net_g, net, crit, opt, bucket, (xs[0], h0, ha0, b0, w0, wa0))
+
+            def gstep(i):
+                h, h_aggre, build, w, w_aggre = labels[i % 2]
+                box["loss"] = graphed(xs[i % 2], h, h_aggre, build, w, w_aggre)
+
+            ms = timed_steps(gstep)
+            launch = "cuda-graph (fwd+bwd graph, eager NCCL all-reduce, optimiser graph)"
+        except Exception as e:  # capture refused: keep the eager number, say why
+            launch = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
     loss = float(box["loss"].item())
     gflop_tile = GFLOP_PER_TILE + GFLOP_PER_TILE_HEAD_TRAIN
     tflops = gflop_tile * B * K / ms          # per GPU
@@ -314,6 +334,7 @@ def train_leg(args, dev, dist, world, rank, K, W, peak):
         "metric": "tiles/sec fwd+bwd (frozen RRDBNet-23 features + SRRegress_Cls_feature head + weighted losses + Adam)",
         "value": B * world * K / ms * 1e3, "unit": "tiles/s", "ms_per_step": ms / K, "steps": K, "warmup": W,
         "batch_per_gpu": B, "global_batch": B * world, "numerics": args.numerics, "loss": loss,
+        "launch": launch, "eager_ms_per_step": ms_eager / K,
         "config": ("BASELINE configs[2]: full SR + feature-aggregation head fwd+bwd, batch 32, weighted losses, 1 GPU"
                    if world == 1 else
                    f"BASELINE configs[3]: data-parallel training step, {B} tiles/GPU x {world} GPUs, Adam, one NCCL "

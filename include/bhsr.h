@@ -47,7 +47,8 @@ enum {
   BHSR_EPI_RES2 = 4,       /* v = v * alpha2 + res2  (after 1) (rrdbnet_arch.py:167)              */
   BHSR_EPI_OUT_NCHW_F32 = 8, /* write fp32 NCHW instead of fp16 planes (rrdbnet_arch.py:238)     */
   BHSR_EPI_RELU = 16,      /* v = max(v, 0) after the residual adds (HRfuse.py:146-157)          */
-  BHSR_EPI_SHUFFLE2 = 32   /* scatter through nn.PixelShuffle(2) into planes (HRfuse.py:24)      */
+  BHSR_EPI_SHUFFLE2 = 32,  /* scatter through nn.PixelShuffle(2) into planes (HRfuse.py:24)      */
+  BHSR_EPI_ACCUM = 64      /* with OUT_NCHW_F32: y += v (sums gradient contributions in backward)  */
 };
 
 int bhsr_version(void);
@@ -229,6 +230,35 @@ int bhsr_bn_bwd_apply(const float* g_out, int32_t g_ctot, int32_t g_choff, const
                       const float* kb2, const float* kb3, float* g_b, int32_t gb_ctot,
                       int32_t gb_choff, int32_t gb_accumulate, int32_t nb, int32_t c, int32_t hw,
                       void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core TRAINING path of the head (head_tc.cu): the forward, data-gradient and weight-gradient convs of
+ * BasicBlock / Upsampler / conv_last under autograd (SR/HRfuse.py:143-159, 185-190; train.py:246-257) on tcgen05.
+ * A BhsrHeadXform describes how a conv reads an fp32 NCHW tensor: channel window, optional BatchNorm-apply + ReLU
+ * fused on the read, optional inverse PixelShuffle(2), optional device-resident scalar multiplier (power-of-two
+ * gradient scale, divided out again by the consumer).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct BhsrHeadXform {
+  const float* x; int32_t x_ctot, x_choff;
+  int32_t c, h, w;            /* LOGICAL channels / grid seen by the conv (after the inverse shuffle) */
+  int32_t unshuffle;          /* x is stored [.., c/4, 2h, 2w]: read through the inverse of PixelShuffle(2) */
+  const float* in_scale;      /* optional per-channel x' = relu?(x * in_scale + in_shift) */
+  const float* in_shift;
+  int32_t in_relu;
+  const float* premul;        /* optional device scalar */
+} BhsrHeadXform;
+/* fp32 NCHW -> NHWC hi/lo fp16 planes [nb][h][w][ctot], channels [choff, choff+cpad): c values then zeros */
+int bhsr_head_to_planes(const BhsrHeadXform* t, int32_t nb, void* out_hi, void* out_lo, int32_t ctot,
+                        int32_t choff, int32_t cpad, void* stream);
+/* stats[0..c) += sum, stats[c..2c) += sum of squares over (n, pixels) of channels [choff, choff+c) of y */
+int bhsr_channel_stats(const float* y, int32_t y_ctot, int32_t y_choff, int32_t nb, int32_t c, int32_t hw,
+                       double* stats, void* stream);
+size_t bhsr_head_wgrad_workspace_bytes(int32_t nb, int32_t cin, int32_t cout, int32_t ksize, int32_t h, int32_t w);
+/* dw[cout][cin][k][k] = sum dy * x' on tcgen05 (deterministic: per-CTA partials reduced in fp64);
+ * db_sum (optional, double[cout], zero-initialised by the caller) += sum dy.  xt: the forward conv's input, gt: the
+ * output gradient (gt->premul is divided out of dw and db_sum).  workspace: 1024-byte aligned device scratch. */
+int bhsr_head_wgrad_tc(const BhsrHeadXform* xt, const BhsrHeadXform* gt, int32_t nb, int32_t ksize, float* dw,
+                       double* db_sum, void* workspace, size_t workspace_bytes, void* stream);
+
 /* step x step block aggregation: out = sum(x) / (count(x >= thr | x > thr) + 1e-10)
  * (aggregate_utils.py:29-41 uses >= 0; :44-59 uses > 1.0) on [nimg][h][w] -> [nimg][h/step][w/step] */
 int bhsr_aggregate(const float* x, int32_t nimg, int32_t h, int32_t w, int32_t step,

@@ -25,6 +25,7 @@ EPI_RES2 = 4
 EPI_OUT_NCHW_F32 = 8
 EPI_RELU = 16
 EPI_SHUFFLE2 = 32
+EPI_ACCUM = 64
 
 
 class BhsrError(RuntimeError):
@@ -93,6 +94,18 @@ class HeadConvDesc(C.Structure):
     ]
 
 
+class HeadXform(C.Structure):
+    """Mirror of `BhsrHeadXform` (include/bhsr.h)."""
+
+    _fields_ = [
+        ("x", C.c_void_p), ("x_ctot", C.c_int32), ("x_choff", C.c_int32),
+        ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("unshuffle", C.c_int32),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
+        ("premul", C.c_void_p),
+    ]
+
+
 # symbol -> (restype, argtypes); tests check every symbol of include/bhsr.h is listed here
 # and exported by the shared object.
 _SIGNATURES = {
@@ -136,6 +149,13 @@ _SIGNATURES = {
     "bhsr_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32] +
                           [C.c_void_p] * 8 + [C.c_int32, C.c_int32] + [C.c_void_p] * 4 +
                           [C.c_int32] * 6 + [C.c_void_p]),
+    "bhsr_head_to_planes": (C.c_int, [C.POINTER(HeadXform), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p]),
+    "bhsr_channel_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p]),
+    "bhsr_head_wgrad_workspace_bytes": (C.c_size_t, [C.c_int32] * 6),
+    "bhsr_head_wgrad_tc": (C.c_int, [C.POINTER(HeadXform), C.POINTER(HeadXform), C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "bhsr_aggregate": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p,
                                  C.c_void_p]),
     "bhsr_rrdbnet_forward": (C.c_int, [C.POINTER(RrdbNetDesc), C.c_void_p] + [C.c_int64] * 4 +

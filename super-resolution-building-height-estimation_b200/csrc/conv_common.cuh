@@ -150,9 +150,15 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
       const size_t plane = static_cast<size_t>(p.oh) * p.ow;
       float* o = p.out_f32 + (static_cast<size_t>(n) * p.out_ctot + p.out_choff + cc * 32) *
                                  plane + static_cast<size_t>(oy) * p.ow + ox;
+      if (p.epilogue & BHSR_EPI_ACCUM) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) o[j * plane] = v[j];
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) o[j * plane] += v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) o[j * plane] = v[j];
+      }
     }
   } else if (p.epilogue & BHSR_EPI_SHUFFLE2) {
     // nn.PixelShuffle(2) scatter (SR/HRfuse.py:24): conv channel 4c'+2i+j of pixel (y,x)

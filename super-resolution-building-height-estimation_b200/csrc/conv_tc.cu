@@ -469,6 +469,8 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   BHSR_REQUIRE(d.cin > 0 && d.cin % (d.numerics == BHSR_NUMERICS_EXACT_F16X3 ? 16 : 32) == 0,
                "conv_tc: cin must be a multiple of 16 (exact) / 32 (fast), got %d", d.cin);
   BHSR_REQUIRE(d.cout_valid >= 0 && d.cout_valid <= d.cout, "conv_tc: cout_valid out of range");
+  BHSR_REQUIRE(!(d.epilogue & BHSR_EPI_ACCUM) || (d.epilogue & BHSR_EPI_OUT_NCHW_F32),
+               "conv_tc: BHSR_EPI_ACCUM needs the fp32 NCHW output");
   if (d.epilogue & BHSR_EPI_SHUFFLE2)
     BHSR_REQUIRE(!(d.epilogue & BHSR_EPI_OUT_NCHW_F32) && d.out_scale == 1 && d.oh >= 2 * d.h && d.ow >= 2 * d.w &&
                      (d.cout_valid == 0 || d.cout_valid % 32 == 0),

@@ -56,7 +56,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must trap (launch error surfaced to the host) instead of
 // hanging the device. ~4e9 cycles is seconds; a healthy wait is microseconds.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {

@@ -148,6 +148,61 @@ def train_step(net_g, net, criterion: Sequence[nn.Module], optimizer, bucket: Op
     return loss.detach()
 
 
+class GraphedTrainStep:
+    """`train_step` replayed from CUDA graphs.  One iteration is ~4000 kernel launches, most of them the tiny
+    kernels of the smp encoder / decoders; captured once, a step costs two graph launches:
+        graph A: frozen RRDBNet features, head forward, the three losses, backward into the flat gradient bucket
+        (eager)  the step's single NCCL all-reduce of the bucket (world > 1)
+        graph B: optimiser step
+    The optimiser must be built with `capturable=True` (its step counter lives on the device).  Inputs are copied
+    into static buffers before each replay.  Tensors produced inside a graph (the loss) are overwritten by the next
+    replay."""
+
+    def __init__(self, net_g, net, criterion, optimizer, bucket: "FlatGradAllReduce", example, warmup: int = 3):
+        self.bucket, self.optimizer = bucket, optimizer
+        self.static = [t.clone() for t in example]          # lr, height, height_aggre, build, weight, weight_aggre
+        self._args = (net_g, net, criterion)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                          # allocator / cache warm-up outside the capture
+                self._fwd_bwd()
+                bucket.all_reduce()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self.loss = self._fwd_bwd()
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b):
+            optimizer.step()
+
+    def _fwd_bwd(self):
+        net_g, net, criterion = self._args
+        lr, height, height_aggre, build, weight, weight_aggre = self.static
+        with torch.no_grad():
+            # train.py:244 indexes lr[:, [0, 1, 2]]; a Python index list becomes a host tensor copied to the device,
+            # which a graph capture refuses — the equivalent strided view needs no copy at all
+            hr_fea = net_g.forward_feature(lr[:, :3])
+        height_pred, build_pred, height_pred_aggre = net(lr, hr_fea)
+        loss = criterion[0](height_pred.squeeze(1), height, weight) + \
+            criterion[1](height_pred_aggre.squeeze(1), height_aggre, weight_aggre) + \
+            criterion[2](build_pred, build, weight)
+        self.bucket.zero_()
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, lr, height, height_aggre, build, weight, weight_aggre) -> torch.Tensor:
+        for dst, src in zip(self.static, (lr, height, height_aggre, build, weight, weight_aggre)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph_a.replay()
+        self.bucket.all_reduce()
+        self.graph_b.replay()
+        return self.loss
+
+
 @torch.no_grad()
 def predict_shard(net_g, net, tiles: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """predict_realesanet_feature_globe.py:167-177 on a batch of tiles already on the GPU:

@@ -86,6 +86,88 @@ def _wgrad(x: Tensor, dy: Tensor, cout: int, cin: int, k: int, *, in_affine=None
     return dw, db
 
 
+# ------------------------------------------------------------------ tensor-core training convs (head_tc.cu)
+# BHSR_HEAD_TC_TRAIN=0 keeps the round-1 fp32 CUDA-core kernels (head.cu) for the autograd path.
+TC_TRAIN = os.environ.get("BHSR_HEAD_TC_TRAIN", "1") != "0"
+
+
+def _grad_scale(g: Tensor) -> Tensor:
+    """Power-of-two factor that brings max|g| into [8, 16): gradients of a mean-reduced loss are ~1e-6 and would
+    sit in fp16's subnormal range; the factor is applied before the hi/lo split and divided out by the consumer
+    (exact: a power of two).  A device scalar — no host synchronisation."""
+    amax = torch.linalg.vector_norm(g.detach(), ord=float("inf")).clamp_min(1e-30)
+    return torch.exp2(torch.floor(4.0 - torch.log2(amax))).to(torch.float32).reshape(1)
+
+
+def _pad_weight(w: Tensor, cout_pad: int, cin_pad: int) -> Tensor:
+    """OIHW (1x1 or 3x3) -> zero-padded [cout_pad, cin_pad, 3, 3] (a 1x1 conv is the centre tap of a 3x3)."""
+    w = w.detach().float()
+    if w.shape[2] == 1:
+        w = torch.nn.functional.pad(w, (1, 1, 1, 1))
+    full = torch.zeros((cout_pad, cin_pad, 3, 3), dtype=torch.float32, device=w.device)
+    full[: w.shape[0], : w.shape[1]] = w
+    return full
+
+
+def _tc_train_ok(cout: int, cin: int) -> bool:
+    return TC_TRAIN and cout <= 64 and cin <= 64
+
+
+def _conv_tc_train(x: Tensor, w: Tensor, b: Optional[Tensor] = None, *, in_affine=None, in_relu=False,
+                   y: Optional[Tensor] = None, y_shuffle=False, x_unshuffle=False, stats: Optional[Tensor] = None,
+                   accumulate=False, gscale: Optional[Tensor] = None) -> Tensor:
+    """Same contract as `_conv` on the tcgen05 conv (exact numerics): fp32 NCHW -> planes with the fused input
+    transform, bhsr_conv_tc with an fp32 NCHW (or PixelShuffle-scattered plane) output, BatchNorm statistics from
+    the stored output.  `gscale`: device scalar the input is multiplied by and the output divided by."""
+    cout, cin, k, _ = w.shape
+    nb = x.shape[0]
+    dev = x.device
+    if x_unshuffle:
+        assert x.shape[1] * 4 == cin
+        h, wd = x.shape[2] // 2, x.shape[3] // 2
+    else:
+        assert x.shape[1] == cin, (x.shape, w.shape)
+        h, wd = x.shape[2], x.shape[3]
+    cin_pad = (cin + 15) // 16 * 16
+    ctot_in = (cin_pad + 31) // 32 * 32
+    cop = 32 if cout <= 32 else 64
+    xin = _planes(nb, h, wd, ctot_in, dev)
+    xf = ops.head_xform(x, cin, h, wd, unshuffle=x_unshuffle, in_affine=in_affine, in_relu=in_relu, premul=gscale)
+    ops.head_to_planes(x, xf, xin[0], xin[1], 0, ctot_in)
+    wp = ops.pack_conv_weights(_pad_weight(w, cop, cin_pad), NUMERICS_EXACT)
+    bias = _padvec(b, cop, dev) if b is not None else None
+    scale = None
+    if gscale is not None:
+        scale = (1.0 / gscale).expand(cop).contiguous()
+        if bias is not None:
+            raise NotImplementedError("a scaled (gradient) conv has no bias")
+    if y_shuffle:
+        if accumulate or stats is not None or cop != 64 or cout % 32:
+            raise NotImplementedError("PixelShuffle conv: 64 outputs, no accumulate / statistics")
+        out = _planes(nb, 2 * h, 2 * wd, 32, dev)
+        ops.conv_tc(xin[0], xin[1], 0, cin_pad, wp, cop, bias, ops.PLAIN_TAPS, out[0], out[1], out_choff=0,
+                    shuffle2=True, scale=scale, numerics=NUMERICS_EXACT)
+        res = ops.planes_to_nchw(out[0], out[1], cout // 4, 0, out=y)
+        return res
+    if y is None:
+        if accumulate:
+            raise ValueError("accumulate needs an output tensor")
+        y = torch.empty((nb, cout, h, wd), dtype=torch.float32, device=dev)
+    ops.conv_tc(xin[0], xin[1], 0, cin_pad, wp, cop, bias, ops.PLAIN_TAPS, None, None, out_f32=y, cout_valid=cout,
+                scale=scale, accumulate=accumulate, numerics=NUMERICS_EXACT)
+    if stats is not None:
+        ops.channel_stats(y, stats)
+    return y
+
+
+def _wgrad_tc_train(x: Tensor, dy: Tensor, cout: int, cin: int, k: int, *, in_affine=None, in_relu=False,
+                    dy_unshuffle=False, want_db=False, gscale: Optional[Tensor] = None):
+    nb, _, h, wd = x.shape
+    xf = ops.head_xform(x, cin, h, wd, in_affine=in_affine, in_relu=in_relu)
+    gf = ops.head_xform(dy, cout, h, wd, unshuffle=dy_unshuffle, premul=gscale)
+    return ops.head_wgrad_tc(x, xf, gf, nb, cin, cout, k, want_db)
+
+
 def _transpose_weight(w: Tensor) -> Tensor:
     """Weights of the data-gradient conv: swap in/out channels, rotate the 3x3 kernel by 180 deg."""
     return w.flip(2, 3).transpose(0, 1).contiguous()
@@ -158,6 +240,9 @@ class _ConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, w)
         ctx.shuffle = bool(shuffle)
         ctx.has_bias = b is not None
+        ctx.tc = _tc_train_ok(w.shape[0], w.shape[1]) and w.shape[2] in (1, 3) and (not shuffle or w.shape[0] == 64)
+        if ctx.tc:
+            return _conv_tc_train(x, w, b, y_shuffle=bool(shuffle))
         return _conv(x, w, b, y_shuffle=bool(shuffle))
 
     @staticmethod
@@ -166,6 +251,13 @@ class _ConvFn(torch.autograd.Function):
         g = g.contiguous()
         cout, cin, k, _ = w.shape
         dw = db = dx = None
+        if ctx.tc:
+            gs = _grad_scale(g)
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                dw, db = _wgrad_tc_train(x, g, cout, cin, k, dy_unshuffle=ctx.shuffle, want_db=ctx.has_bias, gscale=gs)
+            if ctx.needs_input_grad[0]:
+                dx = _conv_tc_train(g, _transpose_weight(w), None, x_unshuffle=ctx.shuffle, gscale=gs)
+            return dx, dw, db, None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = _wgrad(x, g, cout, cin, k, dy_unshuffle=ctx.shuffle, want_db=ctx.has_bias)
         if ctx.needs_input_grad[0]:
@@ -199,16 +291,18 @@ class _BasicBlockFn(torch.autograd.Function):
         def stats_buf():
             return torch.zeros(2 * planes, dtype=torch.float64, device=dev) if training else None
 
+        tc = _tc_train_ok(planes, cin)      # tensor-core convs (head_tc.cu) or the round-1 CUDA-core kernels
+        conv = _conv_tc_train if tc else _conv
         st1 = stats_buf()
-        c1 = _conv(x, w1c, None, stats=st1)
+        c1 = conv(x, w1c, None, stats=st1)
         s1 = _bn_from_stats(st1, count, bn1, True) if training else _bn_eval(bn1)
         st2 = stats_buf()
-        c2 = _conv(c1, w2c, None, in_affine=(s1.scale, s1.shift), in_relu=True, stats=st2)
+        c2 = conv(c1, w2c, None, in_affine=(s1.scale, s1.shift), in_relu=True, stats=st2)
         s2 = _bn_from_stats(st2, count, bn2, True) if training else _bn_eval(bn2)
         d = sd = None
         if wd is not None:
             std = stats_buf()
-            d = _conv(x, wdc, None, stats=std)
+            d = conv(x, wdc, None, stats=std)
             sd = _bn_from_stats(std, count, bnd, True) if training else _bn_eval(bnd)
         out = torch.empty((nb, planes, h, wdt), dtype=torch.float32, device=dev)
         short = d if d is not None else x
@@ -221,6 +315,7 @@ class _BasicBlockFn(torch.autograd.Function):
         ctx.training = bool(training)
         ctx.has_ds = wd is not None
         ctx.count = count
+        ctx.tc = tc
         tensors = [x, c1, c2, out, w1c, w2c, g1, g2, s1.scale, s1.shift, s1.mean, s1.invstd,
                    s2.scale, s2.shift, s2.mean, s2.invstd]
         if ctx.has_ds:
@@ -281,8 +376,14 @@ class _BasicBlockFn(torch.autograd.Function):
                                          g_short.data_ptr() if want_short else None, planes, 0, 0,
                                          nb, planes, hw, st), "bhsr_bn_bwd_apply")
         # ---- conv2 (input a1 = relu(bn1(c1)) is re-materialised on the fly by the input transform)
-        dw2, _ = _wgrad(c1, g_c2, planes, planes, 3, in_affine=(s1_scale, s1_shift), in_relu=True)
-        g_a1 = _conv(g_c2, _transpose_weight(w2), None)
+        if ctx.tc:      # tcgen05 convs; one power-of-two gradient scale per block (see _grad_scale)
+            gs = _grad_scale(g_out)
+            conv = lambda *a, **k: _conv_tc_train(*a, gscale=gs, **k)
+            wgrad = lambda *a, **k: _wgrad_tc_train(*a, gscale=gs, **k)
+        else:
+            conv, wgrad = _conv, _wgrad
+        dw2, _ = wgrad(c1, g_c2, planes, planes, 3, in_affine=(s1_scale, s1_shift), in_relu=True)
+        g_a1 = conv(g_c2, _transpose_weight(w2), None)
         # ---- bn1 + relu
         sums1 = torch.empty(3 * planes, dtype=torch.float64, device=dev)
         _lib.check(lib.bhsr_bn_bwd_reduce(g_a1.data_ptr(), planes, 0, None, 0, 0, c1.data_ptr(),
@@ -296,17 +397,17 @@ class _BasicBlockFn(torch.autograd.Function):
                                          g_c1.data_ptr(), None, 0, 0, None, None, None, None, 0, 0, 0,
                                          nb, planes, hw, st), "bhsr_bn_bwd_apply")
         # ---- conv1 / shortcut
-        dw1, _ = _wgrad(x, g_c1, planes, cin, 3)
+        dw1, _ = wgrad(x, g_c1, planes, cin, 3)
         dwd = None
         gx = None
         if ctx.has_ds:
-            dwd, _ = _wgrad(x, g_short, planes, cin, 1)
+            dwd, _ = wgrad(x, g_short, planes, cin, 1)
             if need_x:
-                gx = _conv(g_c1, _transpose_weight(w1), None)
-                _conv(g_short, _transpose_weight(wd), None, y=gx, accumulate=True)
+                gx = conv(g_c1, _transpose_weight(w1), None)
+                conv(g_short, _transpose_weight(wd), None, y=gx, accumulate=True)
         elif need_x:
             gx = g_short
-            _conv(g_c1, _transpose_weight(w1), None, y=gx, accumulate=True)
+            conv(g_c1, _transpose_weight(w1), None, y=gx, accumulate=True)
         grads = [gx, None, None, dw1, dg1, db1, dw2, dg2, db2, dwd, dgd, dbd]
         return tuple(grads) + (None,) * 6
 

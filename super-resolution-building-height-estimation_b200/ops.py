@@ -10,7 +10,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_LRELU, EPI_OUT_NCHW_F32, EPI_RELU, EPI_RES1, EPI_RES2, EPI_SHUFFLE2, NUMERICS,
+from ._lib import (EPI_ACCUM, EPI_LRELU, EPI_OUT_NCHW_F32, EPI_RELU, EPI_RES1, EPI_RES2, EPI_SHUFFLE2, NUMERICS,
                    NUMERICS_EXACT, NUMERICS_FAST, ConvTcDesc)
 
 PLAIN_TAPS: Tuple[Tuple[int, int], ...] = tuple((ky - 1, kx - 1) for ky in range(3) for kx in range(3))
@@ -67,7 +67,7 @@ def conv_tc(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: int, c
             res2: Optional[Tuple[torch.Tensor, Optional[torch.Tensor], int]] = None, alpha2: float = 1.0,
             numerics: int = NUMERICS_EXACT, mblocks: int = 0, max_ctas: int = 0,
             desc_mode: int = 0, scale: Optional[torch.Tensor] = None, cout_valid: int = 0,
-            relu: bool = False, shuffle2: bool = False) -> None:
+            relu: bool = False, shuffle2: bool = False, accumulate: bool = False) -> None:
     """Enqueue one tensor-core convolution on the current stream (bhsr_conv_tc)."""
     _lib.require_cuda(in_hi, "in_hi")
     nb, h, w, ctot = in_hi.shape
@@ -104,6 +104,8 @@ def conv_tc(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: int, c
         epi |= EPI_RELU
     if shuffle2:
         epi |= EPI_SHUFFLE2
+    if accumulate:
+        epi |= EPI_ACCUM
     if res1 is not None:
         epi |= EPI_RES1
         d.res1_hi, d.res1_lo = res1[0].data_ptr(), _lib.ptr(res1[1])
@@ -177,3 +179,60 @@ def conv3x3_last(in_hi: torch.Tensor, in_lo: Optional[torch.Tensor], in_choff: i
                                              _lib.stream_ptr(in_hi.device)),
                "bhsr_conv3x3_last")
     return out
+
+
+# ------------------------------------------------------------------ tensor-core training head (head_tc.cu)
+def head_xform(x: torch.Tensor, c: int, h: int, w: int, *, unshuffle: bool = False, in_affine=None,
+               in_relu: bool = False, premul: Optional[torch.Tensor] = None) -> "_lib.HeadXform":
+    """How a conv reads the contiguous fp32 NCHW tensor `x` (BhsrHeadXform).  The returned struct holds raw
+    pointers: keep `x`, the affine vectors and `premul` alive until the call that uses it has been enqueued."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    t = _lib.HeadXform()
+    t.x, t.x_ctot, t.x_choff = x.data_ptr(), x.shape[1], 0
+    t.c, t.h, t.w = c, h, w
+    t.unshuffle = int(unshuffle)
+    if in_affine is not None:
+        t.in_scale, t.in_shift = in_affine[0].data_ptr(), in_affine[1].data_ptr()
+    t.in_relu = int(in_relu)
+    t.premul = _lib.ptr(premul)
+    return t
+
+
+@_lib.device_guarded
+def head_to_planes(x: torch.Tensor, xf: "_lib.HeadXform", out_hi: torch.Tensor, out_lo: torch.Tensor,
+                   choff: int, cpad: int) -> None:
+    """fp32 NCHW -> NHWC hi/lo planes with the fused input transform; channels [choff, choff+cpad) of the
+    planes receive the xf.c values followed by zeros (bhsr_head_to_planes)."""
+    import ctypes as C
+    nb = x.shape[0]
+    assert out_hi.shape[:3] == (nb, xf.h, xf.w) and out_hi.dtype == torch.float16
+    _lib.check(_lib.load().bhsr_head_to_planes(C.byref(xf), nb, out_hi.data_ptr(), out_lo.data_ptr(),
+                                               out_hi.shape[3], choff, cpad, _lib.stream_ptr(x.device)),
+               "bhsr_head_to_planes")
+
+
+@_lib.device_guarded
+def channel_stats(y: torch.Tensor, stats: torch.Tensor) -> None:
+    """stats[0:c] += sum, stats[c:2c] += sum of squares of the fp32 NCHW tensor y (BatchNorm batch statistics)."""
+    nb, c, h, w = y.shape
+    assert y.dtype == torch.float32 and y.is_contiguous() and stats.dtype == torch.float64 and stats.numel() == 2 * c
+    _lib.check(_lib.load().bhsr_channel_stats(y.data_ptr(), c, 0, nb, c, h * w, stats.data_ptr(),
+                                              _lib.stream_ptr(y.device)), "bhsr_channel_stats")
+
+
+@_lib.device_guarded
+def head_wgrad_tc(x: torch.Tensor, xf: "_lib.HeadXform", gf: "_lib.HeadXform", nb: int, cin: int, cout: int, k: int,
+                  want_db: bool):
+    """dw [cout, cin, k, k] (and db) on the tensor cores (bhsr_head_wgrad_tc)."""
+    import ctypes as C
+    lib = _lib.load()
+    dev = x.device
+    n = lib.bhsr_head_wgrad_workspace_bytes(nb, cin, cout, k, xf.h, xf.w)
+    ws = torch.empty(n + 1024, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+    dw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=dev)
+    db_sum = torch.zeros(cout, dtype=torch.float64, device=dev) if want_db else None
+    _lib.check(lib.bhsr_head_wgrad_tc(C.byref(xf), C.byref(gf), nb, k, dw.data_ptr(), _lib.ptr(db_sum), ws_ptr,
+                                      ws.numel() - (ws_ptr - ws.data_ptr()), _lib.stream_ptr(dev)),
+               "bhsr_head_wgrad_tc")
+    return dw, (db_sum.float() if want_db else None)

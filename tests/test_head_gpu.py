@@ -118,10 +118,13 @@ def _grad_reference(sd, lr, hr16, training, oc):
     return y.detach().numpy(), g.numpy(), a.grad.numpy(), b.grad.numpy(), grads
 
 
+@pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("training", [True, False])
-def test_hrfuse_residual_backward(dev, training):
-    """dgrad / wgrad / BatchNorm backward kernels vs autograd of the oracle."""
+def test_hrfuse_residual_backward(dev, training, tc, monkeypatch):
+    """dgrad / wgrad / BatchNorm backward kernels vs autograd of the oracle — on the tcgen05 training convs
+    (head_tc.cu, the default) and on the round-1 fp32 CUDA-core kernels (BHSR_HEAD_TC_TRAIN=0)."""
     from bhsr import hrfuse
+    monkeypatch.setattr(hrfuse, "TC_TRAIN", tc)
     oc = 7
     sd = synth.hrfuse_residual_state(out=oc, seed=47)
     lr = synth.features(2, 16, 8, 8, seed=1)
@@ -185,22 +188,31 @@ def test_head_backward_config3_shape(dev):
     # changes the gradient of the few hundred elements in its receptive field by a finite amount.  The
     # elementwise bound therefore tolerates a small fraction of outliers (measured: 0.7 % of the decoder-feature
     # gradient) next to a tight relative-L2 bound; parameter gradients average over 524288 pixels.
-    def check(got, ref, what, max_bad_frac):
+    def check(got, ref, what, max_bad_frac, rel_l2):
         got = np.asarray(got, np.float64)
         ref = np.asarray(ref, np.float64)
         tol = 1e-4 * float(np.abs(ref).max()) + 2e-3 * np.abs(ref)
         bad = float((np.abs(got - ref) > tol).mean())
         rel = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
-        assert bad <= max_bad_frac and rel < 2e-2, f"{what}: {bad:.2%} of elements outside tolerance, rel-L2 {rel:.2e}"
+        assert bad <= max_bad_frac and rel < rel_l2, f"{what}: {bad:.2%} of elements outside tolerance, rel-L2 {rel:.2e}"
 
-    check(ag.grad.cpu().numpy(), a.grad.numpy(), "grad decoder features", 0.03)
+    check(ag.grad.cpu().numpy(), a.grad.numpy(), "grad decoder features", 0.03, 2e-2)
+    # a parameter gradient is a cancellation-heavy sum over 524288 pixels: the ~50 flipped masks of a pass move it
+    # by ~sqrt(50 / 524288) = 1e-2 of its norm whatever computes it (measured 2.8e-3 with either conv path), so
+    # parameters get the relative-L2 bound only; the kernels themselves are pinned to 1e-3 / 1e-4 in
+    # test_wgrad_tc_kernel_vs_fp64 and test_hrfuse_residual_backward (no mask ambiguity at those sizes)
+    worst = 0.0
     for mod, ref in ((feat, pf), (fuse, pr)):
         for name, p in mod.named_parameters():
             assert p.grad is not None, name
-            check(p.grad.cpu().numpy(), ref[name].grad.numpy(), f"grad {name}", 0.02)
+            g_, r_ = p.grad.double().cpu().numpy(), ref[name].grad.numpy()
+            rel = float(np.linalg.norm(g_ - r_) / max(np.linalg.norm(r_), 1e-30))
+            worst = max(worst, rel)
+            assert rel < 2e-2, f"grad {name}: rel-L2 {rel:.2e}"
         for name, buf in mod.named_buffers():     # running statistics updated like nn.BatchNorm2d
             if "running" in name:
                 np.testing.assert_allclose(buf.cpu().numpy(), ref[name].detach().numpy(), rtol=1e-4, atol=1e-5, err_msg=name)
+    print(f"config-3 backward: worst parameter-gradient rel-L2 {worst:.2e}")
 
 
 def test_srregress_head_vs_oracle(dev):
@@ -304,3 +316,68 @@ def test_srregress_forward_vs_reference_golden(dev, golden, isaggre):
                                 out_g[2].detach().cpu().numpy() if isaggre else None)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+@pytest.mark.parametrize("cin,cout,k,nb,h,w,unshuffle", [(16, 16, 3, 2, 40, 72, False), (64, 16, 3, 2, 33, 64, False),
+                                                         (32, 16, 1, 3, 20, 130, False), (16, 64, 3, 2, 24, 40, True),
+                                                         (16, 7, 3, 1, 9, 5, False), (16, 1, 3, 2, 64, 64, False)])
+def test_wgrad_tc_kernel_vs_fp64(dev, cin, cout, k, nb, h, w, unshuffle):
+    """The tcgen05 weight-gradient kernel (head_tc.cu: wgrad_tc_kernel + wgrad_reduce_kernel) against an fp64
+    torch reference: 3x3 and 1x1, padded channel counts, several strips / ragged widths (TMA zero fill), the fused
+    BatchNorm-apply + ReLU on the input read, the PixelShuffle inverse on the gradient, the bias gradient, and a
+    tiny gradient magnitude (power-of-two pre-scale)."""
+    from bhsr import hrfuse
+    rng = np.random.RandomState(cin + cout + h)
+    x = rng.standard_normal((nb, cin, h, w)).astype(np.float32)
+    sc = (0.5 + rng.rand(cin)).astype(np.float32)
+    sh = (0.2 * rng.standard_normal(cin)).astype(np.float32)
+    gshape = (nb, cout // 4, 2 * h, 2 * w) if unshuffle else (nb, cout, h, w)
+    g = (rng.standard_normal(gshape) * 3e-6).astype(np.float32)
+    xt = torch.relu(torch.from_numpy(x).double() * torch.from_numpy(sc).double().view(1, -1, 1, 1) +
+                    torch.from_numpy(sh).double().view(1, -1, 1, 1))
+    gt = torch.from_numpy(g).double()
+    if unshuffle:
+        gt = torch.nn.functional.pixel_unshuffle(gt, 2)
+    wref = torch.zeros((cout, cin, k, k), dtype=torch.float64, requires_grad=True)
+    yref = torch.nn.functional.conv2d(xt, wref, None, padding=k // 2)
+    (yref * gt).sum().backward()
+    xs, gs_ = cuda(x, dev), cuda(g, dev)
+    scale = hrfuse._grad_scale(gs_)
+    dw, db = hrfuse._wgrad_tc_train(xs, gs_, cout, cin, k, in_affine=(cuda(sc, dev), cuda(sh, dev)), in_relu=True,
+                                    dy_unshuffle=unshuffle, want_db=True, gscale=scale)
+    ref = wref.grad.numpy()
+    tol = 1e-4 * float(np.abs(ref).max())
+    assert_close(dw.cpu().numpy(), ref, rtol=1e-3, atol=tol, what=f"wgrad {cin}->{cout} k{k}")
+    dbref = gt.sum(dim=(0, 2, 3)).numpy()
+    assert_close(db.cpu().numpy(), dbref, rtol=1e-3, atol=1e-4 * float(np.abs(dbref).max()) + 1e-12, what="bias grad")
+
+
+@pytest.mark.parametrize("cin,cout,k,shuffle,unshuffle", [(16, 16, 3, False, False), (64, 16, 1, False, False),
+                                                          (16, 64, 3, True, False), (64, 16, 3, False, True),
+                                                          (7, 16, 3, False, False)])
+def test_conv_tc_train_vs_cuda_core_conv(dev, cin, cout, k, shuffle, unshuffle):
+    """The tcgen05 training conv (to_planes + bhsr_conv_tc + channel statistics) against the fp32 CUDA-core
+    conv of round 1 on the same arguments: fused input transform, BatchNorm statistics, PixelShuffle scatter /
+    inverse, accumulate, padded channel counts, ragged sizes."""
+    from bhsr import hrfuse
+    rng = np.random.RandomState(cin * 3 + cout + k)
+    nb, h, w = 2, 37, 70
+    xshape = (nb, cin // 4, 2 * h, 2 * w) if unshuffle else (nb, cin, h, w)
+    x = cuda(rng.standard_normal(xshape).astype(np.float32), dev)
+    wt = cuda((rng.standard_normal((cout, cin, k, k)) * 0.2).astype(np.float32), dev)
+    kw = {}
+    if not unshuffle and not shuffle:
+        kw = dict(in_affine=(cuda((0.5 + rng.rand(cin)).astype(np.float32), dev),
+                             cuda((0.2 * rng.standard_normal(cin)).astype(np.float32), dev)), in_relu=True)
+    st_a = torch.zeros(2 * cout, dtype=torch.float64, device=dev) if not shuffle else None
+    st_b = torch.zeros(2 * cout, dtype=torch.float64, device=dev) if not shuffle else None
+    bias = cuda((0.1 * rng.standard_normal(cout)).astype(np.float32), dev) if shuffle else None
+    ya = hrfuse._conv_tc_train(x, wt, bias, y_shuffle=shuffle, x_unshuffle=unshuffle, stats=st_a, **kw)
+    yb = hrfuse._conv(x, wt, bias, y_shuffle=shuffle, x_unshuffle=unshuffle, stats=st_b, **kw)
+    assert ya.shape == yb.shape
+    assert_close(ya.cpu().numpy(), yb.cpu().numpy(), what="conv")
+    if st_a is not None:
+        np.testing.assert_allclose(st_a.cpu().numpy(), st_b.cpu().numpy(), rtol=1e-4, atol=1e-3)
+        base = ya.clone()
+        hrfuse._conv_tc_train(x, wt, None, x_unshuffle=unshuffle, y=ya, accumulate=True, **kw)
+        assert_close(ya.cpu().numpy(), 2 * base.cpu().numpy(), rtol=1e-3, atol=2e-4, what="accumulate")
