@@ -249,6 +249,11 @@ typedef struct BhsrHeadXform {
 /* fp32 NCHW -> NHWC hi/lo fp16 planes [nb][h][w][ctot], channels [choff, choff+cpad): c values then zeros */
 int bhsr_head_to_planes(const BhsrHeadXform* t, int32_t nb, void* out_hi, void* out_lo, int32_t ctot,
                         int32_t choff, int32_t cpad, void* stream);
+/* NHWC hi/lo planes -> fp32 NCHW: y[:, y_choff + j] (=|+=) (hi + lo' * 2^-11) / *unscale for plane channels
+ * [choff, choff + c); stats (optional, double[2c]) += sum / sum of squares of the stored values */
+int bhsr_head_from_planes(const void* in_hi, const void* in_lo, int32_t nb, int32_t h, int32_t w, int32_t ctot,
+                          int32_t choff, int32_t c, const float* unscale, float* y, int32_t y_ctot, int32_t y_choff,
+                          int32_t accumulate, double* stats, void* stream);
 /* stats[0..c) += sum, stats[c..2c) += sum of squares over (n, pixels) of channels [choff, choff+c) of y */
 int bhsr_channel_stats(const float* y, int32_t y_ctot, int32_t y_choff, int32_t nb, int32_t c, int32_t hw,
                        double* stats, void* stream);

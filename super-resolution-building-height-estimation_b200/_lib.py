@@ -151,6 +151,8 @@ _SIGNATURES = {
                           [C.c_int32] * 6 + [C.c_void_p]),
     "bhsr_head_to_planes": (C.c_int, [C.POINTER(HeadXform), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_void_p]),
+    "bhsr_head_from_planes": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bhsr_channel_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p]),
     "bhsr_head_wgrad_workspace_bytes": (C.c_size_t, [C.c_int32] * 6),

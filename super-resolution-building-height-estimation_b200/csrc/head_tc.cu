@@ -64,35 +64,160 @@ __device__ __forceinline__ float load_xform(const InXform& t, int n, int ch, int
 }
 
 // ---------------------------------------------------------------- fp32 NCHW -> NHWC hi/lo planes
-// block = (image, row, 32-pixel segment): coalesced reads along x per channel, 16-byte plane stores.
+// work item = (image, row, 128-pixel segment), dealt to a persistent grid: coalesced 128-bit reads along x per
+// channel into a padded shared tile, 16-byte plane stores (8 channels of one pixel per thread).
+constexpr int kTpPx = 128;
 __global__ void __launch_bounds__(256)
-head_to_planes_kernel(InXform t, __half* __restrict__ out_hi, __half* __restrict__ out_lo, int ctot, int choff,
-                      int cpad) {
-  extern __shared__ float tile[];  // [cpad][33]
-  const int segs = (t.w + 31) / 32;
-  const int seg = blockIdx.x % segs;
-  const int y = (blockIdx.x / segs) % t.h;
-  const int n = blockIdx.x / (segs * t.h);
-  const int x0 = seg * 32;
+head_to_planes_kernel(InXform t, int nb, __half* __restrict__ out_hi, __half* __restrict__ out_lo, int ctot,
+                      int choff, int cpad) {
+  extern __shared__ float tile[];  // [cpad][kTpPx + 1]
+  constexpr int P = kTpPx + 1;
+  const int segs = (t.w + kTpPx - 1) / kTpPx;
+  const int items = nb * t.h * segs;
   const float pm = t.premul ? *t.premul : 1.f;
-  for (int i = threadIdx.x; i < cpad * 32; i += blockDim.x) {
-    const int ch = i >> 5, xx = i & 31;
-    float v = 0.f;
-    if (ch < t.c && x0 + xx < t.w) v = load_xform(t, n, ch, y, x0 + xx, pm);
-    tile[ch * 33 + xx] = v;
-  }
-  __syncthreads();
-  const int chunks = cpad >> 3;
-  for (int i = threadIdx.x; i < chunks * 32; i += blockDim.x) {
-    const int xx = i / chunks, ck = i % chunks;
-    if (x0 + xx >= t.w) continue;
-    __align__(16) __half hh[8];
-    __align__(16) __half ll[8];
+  const bool vec = !t.unshuffle && (t.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(t.x) & 15) == 0);
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int seg = it % segs;
+    const int y = (it / segs) % t.h;
+    const int n = it / (segs * t.h);
+    const int x0 = seg * kTpPx;
+    if (vec) {
+      for (int i = threadIdx.x; i < t.c * (kTpPx / 4); i += blockDim.x) {
+        const int ch = i / (kTpPx / 4), xq = (i % (kTpPx / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x0 + xq < t.w) {
+          v = *reinterpret_cast<const float4*>(
+              t.x + ((static_cast<size_t>(n) * t.x_ctot + t.x_choff + ch) * t.h + y) * t.w + x0 + xq);
+          if (t.in_scale) {
+            const float sc = t.in_scale[ch], sh = t.in_shift[ch];
+            v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh); v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+          }
+          if (t.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          v.x *= pm; v.y *= pm; v.z *= pm; v.w *= pm;
+        }
+        float* d = tile + ch * P + xq;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < t.c * kTpPx; i += blockDim.x) {
+        const int ch = i / kTpPx, xx = i % kTpPx;
+        float v = 0.f;
+        if (x0 + xx < t.w) v = load_xform(t, n, ch, y, x0 + xx, pm);
+        tile[ch * P + xx] = v;
+      }
+    }
+    __syncthreads();
+    const int chunks = cpad >> 3;
+    for (int i = threadIdx.x; i < chunks * kTpPx; i += blockDim.x) {
+      const int xx = i / chunks, ck = i % chunks;
+      if (x0 + xx >= t.w) continue;
+      __align__(16) __half hh[8];
+      __align__(16) __half ll[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split_hl(tile[(ck * 8 + j) * 33 + xx], hh[j], ll[j]);
-    const size_t o = ((static_cast<size_t>(n) * t.h + y) * t.w + x0 + xx) * ctot + choff + ck * 8;
-    *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hh);
-    *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(ll);
+      for (int j = 0; j < 8; ++j) {
+        const int ch = ck * 8 + j;
+        split_hl(ch < t.c ? tile[ch * P + xx] : 0.f, hh[j], ll[j]);
+      }
+      const size_t o = ((static_cast<size_t>(n) * t.h + y) * t.w + x0 + xx) * ctot + choff + ck * 8;
+      *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hh);
+      *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(ll);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- NHWC hi/lo planes -> fp32 NCHW (+ statistics)
+// The tensor-core convs of the training head write planes (dx-in-N kernel); this pass returns them to the head's
+// fp32 NCHW layout: y (=|+=) unscale * (hi + lo' * 2^-11) for channels [choff, choff + c), and accumulates the
+// BatchNorm batch statistics (sum, sum of squares per channel) of what it stores — per-thread fp32 partials over a
+// persistent block's items, one fp64 atomic per channel and block at the end.
+__global__ void __launch_bounds__(256)
+head_from_planes_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int nb, int h, int w,
+                        int ctot, int choff, int c, const float* __restrict__ unscale_inv /* device scalar s: y /= s */,
+                        float* __restrict__ y_out, int y_ctot, int y_choff, int accumulate, double* __restrict__ stats) {
+  extern __shared__ float tile[];  // [c][kTpPx + 1]
+  constexpr int P = kTpPx + 1;
+  const int segs = (w + kTpPx - 1) / kTpPx;
+  const int items = nb * h * segs;
+  const float inv = unscale_inv ? 1.f / *unscale_inv : 1.f;
+  const int chunks = (c + 7) >> 3;
+  // write phase: warp k owns channels k, k+8, ...; a lane owns 4 consecutive pixels
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc_s[8], acc_q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int seg = it % segs;
+    const int yy = (it / segs) % h;
+    const int n = it / (segs * h);
+    const int x0 = seg * kTpPx;
+    for (int i = threadIdx.x; i < chunks * kTpPx; i += blockDim.x) {
+      const int xx = i / chunks, ck = i % chunks;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (x0 + xx < w) {
+        const size_t o = ((static_cast<size_t>(n) * h + yy) * w + x0 + xx) * ctot + choff + ck * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(in_hi + o);
+        const uint4 b = *reinterpret_cast<const uint4*>(in_lo + o);
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fa = __half22float2(ah[j]), fb = __half22float2(bh[j]);
+          v[2 * j] = fmaf(fb.x, 1.f / 2048.f, fa.x) * inv;
+          v[2 * j + 1] = fmaf(fb.y, 1.f / 2048.f, fa.y) * inv;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (ck * 8 + j < c) tile[(ck * 8 + j) * P + xx] = v[j];
+    }
+    __syncthreads();
+    int k = 0;
+    for (int ch = warp; ch < c; ch += 8, ++k) {
+      const int xx = lane * 4;
+      float* o = y_out + ((static_cast<size_t>(n) * y_ctot + y_choff + ch) * h + yy) * w + x0 + xx;
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = tile[ch * P + xx + j];
+      if (x0 + xx + 3 < w && (w % 4 == 0)) {
+        float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (accumulate) cur = *reinterpret_cast<const float4*>(o);
+        r[0] += cur.x; r[1] += cur.y; r[2] += cur.z; r[3] += cur.w;
+        *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (x0 + xx + j < w) {
+            if (accumulate) r[j] += o[j];
+            o[j] = r[j];
+          } else {
+            r[j] = 0.f;
+          }
+        }
+      }
+      if (stats != nullptr && k < 8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc_s[k] += r[j]; acc_q[k] = fmaf(r[j], r[j], acc_q[k]); }
+      }
+    }
+    __syncthreads();
+  }
+  if (stats != nullptr) {
+    int k = 0;
+    for (int ch = warp; ch < c && k < 8; ch += 8, ++k) {
+      float a = acc_s[k], q = acc_q[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) {
+        atomicAdd(stats + ch, static_cast<double>(a));
+        atomicAdd(stats + c + ch, static_cast<double>(q));
+      }
+    }
   }
 }
 
@@ -101,30 +226,40 @@ head_to_planes_kernel(InXform t, __half* __restrict__ out_hi, __half* __restrict
 // pad channels and pad columns are written as zeros.  block = (image, channel, row block).
 __global__ void __launch_bounds__(256)
 head_split_nchw_kernel(InXform t, __half* __restrict__ out_hi, __half* __restrict__ out_lo, int cpad, int wp,
-                       int ncopies /* 1, or 3: copy k holds x shifted by k-1 pixels (zero outside the row) */,
+                       int ncopies /* 1, or 3: copy k holds the row shifted so that copy_k[x] = v[x + 1 - k] */,
                        size_t copy_stride /* elements between copies */,
                        double* __restrict__ chan_sum /* optional [c]: += sum of the (unscaled) values */) {
   const int ch = blockIdx.y;
   const int n = blockIdx.z;
   const float pm = t.premul ? *t.premul : 1.f;
-  const size_t plane = static_cast<size_t>(t.h) * wp;
-  const size_t obase = (static_cast<size_t>(n) * cpad + ch) * plane;
+  const int wq = wp >> 3;                                   // 8-pixel groups per row
+  const size_t groups = static_cast<size_t>(t.h) * wq;
+  const size_t obase = (static_cast<size_t>(n) * cpad + ch) * (static_cast<size_t>(t.h) * wp);
   const int pad = ncopies == 3 ? 1 : 0;
   float acc = 0.f;
-  const size_t per_block = (plane + gridDim.x - 1) / gridDim.x;
-  const size_t i0 = blockIdx.x * per_block;
-  const size_t i1 = i0 + per_block < plane ? i0 + per_block : plane;
-  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    const int y = static_cast<int>(i / wp), xx = static_cast<int>(i - static_cast<size_t>(y) * wp);
-    for (int k = 0; k < ncopies; ++k) {
-      const int xs = xx + k - pad;
-      float v = 0.f;
-      if (ch < t.c && xs >= 0 && xs < t.w) v = load_xform(t, n, ch, y, xs, pm);
-      if (k == pad) acc += v;
-      __half hi, lo;
-      split_hl(v, hi, lo);
-      out_hi[k * copy_stride + obase + i] = hi;
-      out_lo[k * copy_stride + obase + i] = lo;
+  const size_t per_block = (groups + gridDim.x - 1) / gridDim.x;
+  const size_t g0 = blockIdx.x * per_block;
+  const size_t g1 = g0 + per_block < groups ? g0 + per_block : groups;
+  for (size_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+    const int y = static_cast<int>(g / wq), xq = static_cast<int>(g - static_cast<size_t>(y) * wq) * 8;
+    float v[10];                                            // pixels xq-1 .. xq+8 of the row
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const int xs = xq - 1 + j;
+      v[j] = (ch < t.c && xs >= 0 && xs < t.w && (pad || (j >= 1 && j <= 8))) ? load_xform(t, n, ch, y, xs, pm) : 0.f;
+    }
+#pragma unroll
+    for (int j = 1; j <= 8; ++j) acc += v[j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k >= ncopies) break;
+      __align__(16) __half hh[8];
+      __align__(16) __half ll[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_hl(ncopies == 3 ? v[j + 2 - k] : v[j + 1], hh[j], ll[j]);
+      const size_t o = k * copy_stride + obase + static_cast<size_t>(y) * wp + xq;
+      *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hh);
+      *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(ll);
     }
   }
   if (chan_sum != nullptr && ch < t.c) {
@@ -179,6 +314,7 @@ struct WgradParams {
   int nb, h, w, nstrips, total_items;
   int cin, ks;             // input channels (multiple of 16), kernel size 1 or 3
   int mrows, mblk;         // ks*cin rows of A, in blocks of 128
+  int a_alloc;             // bytes reserved per plane of the A tile (mrows*128 rounded up to 1024)
   int stages;
   float* partial;          // [grid][ks][mblk*128][NCO]
 };
@@ -186,6 +322,9 @@ struct WgradParams {
 constexpr int kWgThreads = 192;          // warps 0..3 epilogue, 4 TMA producer, 5 MMA issuer
 constexpr int kWgMaxStages = 8;
 
+// One stage = one work item (image n, row y, 64-pixel strip): the A tile (X rows y-1..y+1 of every input channel,
+// hi and lo' planes) is loaded ONCE and multiplied with ks B tiles — copy kx of the gradient planes holds dY shifted
+// by (1 - kx) pixels, so  dW[.., kx] += X[x'] * dY[x' + 1 - kx]  needs no shifted copy of the (wider) X operand.
 template <int NCO>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
@@ -194,10 +333,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t base = smem_u32(smem);
-  const int a_tile = p.mblk * 128 * 128;             // bytes of one plane of the A tile
-  constexpr int b_tile = NCO * 128;                   // bytes of one plane of the B tile
-  const int stage_bytes = 2 * a_tile + 2 * b_tile;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  const int a_alloc = p.a_alloc;
+  constexpr int b_tile = NCO * 128;                   // bytes of one plane of one B tile
+  const int stage_bytes = 2 * a_alloc + p.ks * 2 * b_tile;
+  // the barriers sit in FRONT of the ring: an M = 128 MMA reads 16 KB from the A tile's start whatever mrows is, so
+  // the bytes behind the last stage are padding the launcher reserves, never live data
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t ring = base + 1024;
   auto bar = [&](int i) { return smem_u32(bars + i); };
   constexpr int B_FULL = 0, B_EMPTY = kWgMaxStages, B_TFULL = 2 * kWgMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
@@ -223,22 +365,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
   if (warp == 4) {
     if (lane == 0) {
       int st = 0, ph = 1;
-      const uint32_t tx = static_cast<uint32_t>(2 * (64 * p.ks * p.cin * 2) + 2 * b_tile);
+      const uint32_t tx = static_cast<uint32_t>(2 * (64 * p.ks * p.cin * 2) + p.ks * 2 * b_tile);
       for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
         const int s = it % p.nstrips;
         const int y = (it / p.nstrips) % p.h;
         const int n = it / (p.nstrips * p.h);
-        for (int dx = 0; dx < ndx; ++dx) {
-          mbar_wait(bar(B_EMPTY + st), ph);
-          mbar_expect_tx(bar(B_FULL + st), tx);
-          const uint32_t dst = base + st * stage_bytes;
-          // copy dx of X (pre-shifted by dx-1 pixels) is "image" dx*nb + n of the plane tensor: aligned x
-          tma_load_4d(dst, &tm_x_hi, bar(B_FULL + st), s * 64, y - pad, 0, dx * p.nb + n);
-          tma_load_4d(dst + a_tile, &tm_x_lo, bar(B_FULL + st), s * 64, y - pad, 0, dx * p.nb + n);
-          tma_load_4d(dst + 2 * a_tile, &tm_g_hi, bar(B_FULL + st), s * 64, y, 0, n);
-          tma_load_4d(dst + 2 * a_tile + b_tile, &tm_g_lo, bar(B_FULL + st), s * 64, y, 0, n);
-          if (++st == p.stages) { st = 0; ph ^= 1; }
+        mbar_wait(bar(B_EMPTY + st), ph);
+        mbar_expect_tx(bar(B_FULL + st), tx);
+        const uint32_t dst = ring + st * stage_bytes;
+        tma_load_4d(dst, &tm_x_hi, bar(B_FULL + st), s * 64, y - pad, 0, n);
+        tma_load_4d(dst + a_alloc, &tm_x_lo, bar(B_FULL + st), s * 64, y - pad, 0, n);
+        for (int dx = 0; dx < ndx; ++dx) {     // gradient copy dx is "image" dx*nb + n of the plane tensor
+          const uint32_t bd = dst + 2 * a_alloc + dx * 2 * b_tile;
+          tma_load_4d(bd, &tm_g_hi, bar(B_FULL + st), s * 64, y, 0, dx * p.nb + n);
+          tma_load_4d(bd + b_tile, &tm_g_lo, bar(B_FULL + st), s * 64, y, 0, dx * p.nb + n);
         }
+        if (++st == p.stages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
@@ -246,14 +388,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
     int st = 0, ph = 0;
     bool first = true;
     for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
-      for (int dx = 0; dx < ndx; ++dx) {
-        mbar_wait(bar(B_FULL + st), ph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sb = base + st * stage_bytes;
-          const uint64_t a_hi = desc0 + ((sb >> 4) & 0x3FFF);
-          const uint64_t a_lo = desc0 + (((sb + a_tile) >> 4) & 0x3FFF);
-          const uint64_t b_all = desc0 + (((sb + 2 * a_tile) >> 4) & 0x3FFF);
+      mbar_wait(bar(B_FULL + st), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sb = ring + st * stage_bytes;
+        const uint64_t a_hi = desc0 + ((sb >> 4) & 0x3FFF);
+        const uint64_t a_lo = desc0 + (((sb + a_alloc) >> 4) & 0x3FFF);
+        for (int dx = 0; dx < ndx; ++dx) {
+          const uint64_t b_all = desc0 + (((sb + 2 * a_alloc + dx * 2 * b_tile) >> 4) & 0x3FFF);
           for (int mb = 0; mb < p.mblk; ++mb) {
             const uint32_t d = tmem_base + (dx * p.mblk + mb) * 2 * NCO;
             const uint32_t moff = (mb * 128 * 128) >> 4;
@@ -263,11 +405,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
               umma_f16_ss(d + NCO, a_lo + moff + 2 * kk, b_all + 2 * kk, IDESC_N, 1u);
             }
           }
-          umma_commit(bar(B_EMPTY + st));
         }
-        __syncwarp();
-        if (++st == p.stages) { st = 0; ph ^= 1; }
+        umma_commit(bar(B_EMPTY + st));
       }
+      __syncwarp();
+      if (++st == p.stages) { st = 0; ph ^= 1; }
       first = false;
     }
     if (elect_one()) umma_commit(bar(B_TFULL));
@@ -364,6 +506,13 @@ static InXform make_xform(const BhsrHeadXform* t) {
 
 using namespace bhsr;
 
+static int persistent_blocks(int items, int per_sm) {
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  int g = sms * per_sm;
+  return items < g ? items : g;
+}
+
 extern "C" int bhsr_head_to_planes(const BhsrHeadXform* t, int32_t nb, void* out_hi, void* out_lo, int32_t ctot,
                                    int32_t choff, int32_t cpad, void* stream) {
   BHSR_REQUIRE(t && t->x && out_hi && out_lo, "head_to_planes: null pointer");
@@ -372,11 +521,26 @@ extern "C" int bhsr_head_to_planes(const BhsrHeadXform* t, int32_t nb, void* out
                "head_to_planes: channel window [%d,+%d) must be 8-aligned inside %d", choff, cpad, ctot);
   BHSR_REQUIRE((t->in_scale == nullptr) == (t->in_shift == nullptr), "head_to_planes: scale and shift go together");
   BHSR_REQUIRE(!t->unshuffle || t->c % 4 == 0, "head_to_planes: unshuffle needs channels in fours");
-  const size_t smem = static_cast<size_t>(cpad) * 33 * sizeof(float);
-  BHSR_REQUIRE(smem <= 48 * 1024, "head_to_planes: too many channels (%d)", cpad);
-  const int segs = (t->w + 31) / 32;
-  head_to_planes_kernel<<<nb * t->h * segs, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      make_xform(t), static_cast<__half*>(out_hi), static_cast<__half*>(out_lo), ctot, choff, cpad);
+  const size_t smem = static_cast<size_t>(t->c) * (kTpPx + 1) * sizeof(float);
+  BHSR_REQUIRE(smem <= 48 * 1024, "head_to_planes: too many channels (%d)", t->c);
+  const int items = nb * t->h * ((t->w + kTpPx - 1) / kTpPx);
+  head_to_planes_kernel<<<persistent_blocks(items, 6), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      make_xform(t), nb, static_cast<__half*>(out_hi), static_cast<__half*>(out_lo), ctot, choff, cpad);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhsr_head_from_planes(const void* in_hi, const void* in_lo, int32_t nb, int32_t h, int32_t w,
+                                     int32_t ctot, int32_t choff, int32_t c, const float* unscale, float* y,
+                                     int32_t y_ctot, int32_t y_choff, int32_t accumulate, double* stats, void* stream) {
+  BHSR_REQUIRE(in_hi && in_lo && y && nb > 0 && h > 0 && w > 0, "head_from_planes: bad arguments");
+  BHSR_REQUIRE(c >= 1 && c <= 64 && choff % 8 == 0 && choff + (c + 7) / 8 * 8 <= ctot && ctot % 8 == 0,
+               "head_from_planes: channel window [%d,+%d) must start 8-aligned inside %d", choff, c, ctot);
+  const size_t smem = static_cast<size_t>(c) * (kTpPx + 1) * sizeof(float);
+  const int items = nb * h * ((w + kTpPx - 1) / kTpPx);
+  head_from_planes_kernel<<<persistent_blocks(items, 6), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(in_hi), static_cast<const __half*>(in_lo), nb, h, w, ctot, choff, c, unscale, y,
+      y_ctot, y_choff, accumulate, stats);
   BHSR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -399,11 +563,11 @@ extern "C" size_t bhsr_head_wgrad_workspace_bytes(int32_t nb, int32_t cin, int32
   const int nco = cout <= 16 ? 16 : 64;
   const int wp = (w + 7) / 8 * 8;
   const size_t xplane = static_cast<size_t>(nb) * cinp * h * wp * 2;
-  const size_t gplane = static_cast<size_t>(nb) * nco * h * wp * 2;
+  const size_t gplane = static_cast<size_t>(nb) * nco * h * wp * 2 * ksize;   // one shifted dY copy per kx
   const int mblk = (ksize * cinp + 127) / 128;
   const size_t partial = static_cast<size_t>(256) * ksize * mblk * 128 * nco * 4;
   auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
-  return 2 * up(xplane * ksize) + 2 * up(gplane) + up(partial) + 4096;   // one pre-shifted X copy per kx
+  return 2 * up(xplane) + 2 * up(gplane) + up(partial) + 4096;
 }
 
 // dw[cout][cin][k][k] (and db[cout]) of a stride-1 "same" conv from x (forward input, with the fused input
@@ -426,9 +590,9 @@ extern "C" int bhsr_head_wgrad_tc(const BhsrHeadXform* xt, const BhsrHeadXform* 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int wp = (w + 7) / 8 * 8;
   auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
-  const size_t xcopy = static_cast<size_t>(nb) * cinp * h * wp;            // elements of one X copy
-  const size_t xplane = up(xcopy * 2 * ksize);
-  const size_t gplane = up(static_cast<size_t>(nb) * nco * h * wp * 2);
+  const size_t xplane = up(static_cast<size_t>(nb) * cinp * h * wp * 2);
+  const size_t gcopy = static_cast<size_t>(nb) * nco * h * wp;             // elements of one dY copy
+  const size_t gplane = up(gcopy * 2 * ksize);
   char* ws = static_cast<char*>(workspace);
   __half* x_hi = reinterpret_cast<__half*>(ws);
   __half* x_lo = reinterpret_cast<__half*>(ws + xplane);
@@ -436,41 +600,43 @@ extern "C" int bhsr_head_wgrad_tc(const BhsrHeadXform* xt, const BhsrHeadXform* 
   __half* g_lo = reinterpret_cast<__half*>(ws + 2 * xplane + gplane);
   float* partial = reinterpret_cast<float*>(ws + 2 * xplane + 2 * gplane);
 
-  const size_t plane = static_cast<size_t>(h) * wp;
-  int bx = static_cast<int>((plane + 256 * 16 - 1) / (256 * 16));
+  const size_t groups = static_cast<size_t>(h) * (wp / 8);
+  int bx = static_cast<int>((groups + 256 * 4 - 1) / (256 * 4));
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
-  head_split_nchw_kernel<<<dim3(bx, cinp, nb), 256, 0, stream>>>(make_xform(xt), x_hi, x_lo, cinp, wp, ksize, xcopy,
-                                                                 nullptr);
+  head_split_nchw_kernel<<<dim3(bx, cinp, nb), 256, 0, stream>>>(make_xform(xt), x_hi, x_lo, cinp, wp, 1, 0, nullptr);
   BHSR_CUDA_CHECK(cudaGetLastError());
-  head_split_nchw_kernel<<<dim3(bx, nco, nb), 256, 0, stream>>>(make_xform(gt), g_hi, g_lo, nco, wp, 1, 0, db_sum);
+  head_split_nchw_kernel<<<dim3(bx, nco, nb), 256, 0, stream>>>(make_xform(gt), g_hi, g_lo, nco, wp, ksize, gcopy,
+                                                                db_sum);
   BHSR_CUDA_CHECK(cudaGetLastError());
 
   WgradParams p{};
   p.nb = nb; p.h = h; p.w = w; p.nstrips = (w + 63) / 64;
   p.total_items = nb * h * p.nstrips;
   p.cin = cinp; p.ks = ksize; p.mrows = mrows; p.mblk = mblk;
+  p.a_alloc = (mrows * 128 + 1023) / 1024 * 1024;
   p.partial = partial;
-  const int a_tile = mblk * 128 * 128, b_tile = nco * 128;
-  const int stage_bytes = 2 * a_tile + 2 * b_tile;
-  int stages = (232448 - 1024 - 256) / stage_bytes;
+  const int b_tile = nco * 128;
+  const int stage_bytes = 2 * p.a_alloc + ksize * 2 * b_tile;
+  const int tail_pad = mblk * 128 * 128;              // an M = 128 MMA may read this far past the last A tile's start
+  int stages = (232448 - 1024 - 1024 - tail_pad) / stage_bytes;
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   BHSR_REQUIRE(stages >= 2, "head_wgrad_tc: tile too large for a 2-stage ring");
   p.stages = stages;
-  const int smem = 1024 + stages * stage_bytes + 256;
+  const int smem = 1024 + 1024 + stages * stage_bytes + tail_pad;
   int sms = device_sm_count();
   if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
   int grid = p.total_items < sms ? p.total_items : sms;
   if (grid > 256) grid = 256;
 
   CUtensorMap xh, xl, gh, gl;
-  int rc = make_nchw_map(&xh, x_hi, nb * ksize, cinp, h, w, wp, cinp, ksize);
+  int rc = make_nchw_map(&xh, x_hi, nb, cinp, h, w, wp, cinp, ksize);
   if (rc) return rc;
-  rc = make_nchw_map(&xl, x_lo, nb * ksize, cinp, h, w, wp, cinp, ksize);
+  rc = make_nchw_map(&xl, x_lo, nb, cinp, h, w, wp, cinp, ksize);
   if (rc) return rc;
-  rc = make_nchw_map(&gh, g_hi, nb, nco, h, w, wp, nco, 1);
+  rc = make_nchw_map(&gh, g_hi, nb * ksize, nco, h, w, wp, nco, 1);
   if (rc) return rc;
-  rc = make_nchw_map(&gl, g_lo, nb, nco, h, w, wp, nco, 1);
+  rc = make_nchw_map(&gl, g_lo, nb * ksize, nco, h, w, wp, nco, 1);
   if (rc) return rc;
   rc = nco == 16 ? launch_wgrad<16>(xh, xl, gh, gl, p, grid, smem, stream)
                  : launch_wgrad<64>(xh, xl, gh, gl, p, grid, smem, stream);

@@ -153,6 +153,14 @@ def _conv_tc_train(x: Tensor, w: Tensor, b: Optional[Tensor] = None, *, in_affin
         if accumulate:
             raise ValueError("accumulate needs an output tensor")
         y = torch.empty((nb, cout, h, wd), dtype=torch.float32, device=dev)
+    if cop == 32:
+        # the dx-in-N kernel (planes output) + one pass back to fp32 NCHW that also divides the gradient scale out,
+        # accumulates and takes the BatchNorm statistics
+        out = _planes(nb, h, wd, 32, dev)
+        ops.conv_tc(xin[0], xin[1], 0, cin_pad, wp, cop, bias, ops.PLAIN_TAPS, out[0], out[1], out_choff=0,
+                    cout_valid=(cout + 7) // 8 * 8, numerics=NUMERICS_EXACT)
+        ops.head_from_planes(out[0], out[1], cout, y, unscale=gscale, accumulate=accumulate, stats=stats)
+        return y
     ops.conv_tc(xin[0], xin[1], 0, cin_pad, wp, cop, bias, ops.PLAIN_TAPS, None, None, out_f32=y, cout_valid=cout,
                 scale=scale, accumulate=accumulate, numerics=NUMERICS_EXACT)
     if stats is not None:

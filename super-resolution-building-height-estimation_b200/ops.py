@@ -212,6 +212,21 @@ def head_to_planes(x: torch.Tensor, xf: "_lib.HeadXform", out_hi: torch.Tensor, 
 
 
 @_lib.device_guarded
+def head_from_planes(in_hi: torch.Tensor, in_lo: torch.Tensor, c: int, y: torch.Tensor, *, choff: int = 0,
+                     unscale: Optional[torch.Tensor] = None, accumulate: bool = False,
+                     stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NHWC hi/lo planes -> fp32 NCHW `y` (bhsr_head_from_planes): y (=|+=) value / *unscale, BatchNorm statistics."""
+    nb, h, w, ctot = in_hi.shape
+    assert y.dtype == torch.float32 and y.is_contiguous() and y.shape == (nb, c, h, w)
+    assert stats is None or (stats.dtype == torch.float64 and stats.numel() == 2 * c)
+    _lib.check(_lib.load().bhsr_head_from_planes(in_hi.data_ptr(), in_lo.data_ptr(), nb, h, w, ctot, choff, c,
+                                                 _lib.ptr(unscale), y.data_ptr(), c, 0, int(accumulate),
+                                                 _lib.ptr(stats), _lib.stream_ptr(in_hi.device)),
+               "bhsr_head_from_planes")
+    return y
+
+
+@_lib.device_guarded
 def channel_stats(y: torch.Tensor, stats: torch.Tensor) -> None:
     """stats[0:c] += sum, stats[c:2c] += sum of squares of the fp32 NCHW tensor y (BatchNorm batch statistics)."""
     nb, c, h, w = y.shape
