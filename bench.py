@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (config 3 / 4) sub-record")
     ap.add_argument("--train-batch", type=int, default=32, help="tiles per GPU per training step")
     ap.add_argument("--no-train-graph", action="store_true", help="time the training step eagerly only")
+    ap.add_argument("--no-graph", action="store_true", help="launch the forward's 356 kernels one by one (no CUDA graph)")
     return ap.parse_args()
 
 
@@ -267,6 +268,8 @@ def train_leg(args, dev, dist, world, rank, K, W, peak):
     from bhsr.models import SRRegress_Cls_feature
     import synth
     B = args.train_batch
+    if os.environ.get("BHSR_CUDNN_BENCHMARK", "1") == "1":
+        torch.backends.cudnn.benchmark = True     # the smp encoder / decoders are stock cuDNN convs: let it pick
     net_g = synth_state_torch(NUM_BLOCK).to(dev).eval()
     net_g.numerics = args.numerics
     for p_ in net_g.parameters():
@@ -380,6 +383,7 @@ def main():
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     net = synth_state_torch(NUM_BLOCK).to(dev).eval()
     net.numerics = args.numerics
+    net.use_cuda_graph = not args.no_graph   # one graph launch per forward (RRDBNet._run); the 356 kernels are the same
     for p in net.parameters():
         p.requires_grad = False
     launches_per_step = 1 + 15 * NUM_BLOCK + 1 + 4 + 4 + 1

@@ -269,6 +269,7 @@ def invalidate_cache(module) -> None:
         m.__dict__.pop("_tc_own", None)
         if "_packed" in m.__dict__:
             m.__dict__["_packed"] = None
+        m.__dict__.pop("_graphs", None)
 
 
 class CacheMixin:

@@ -176,6 +176,7 @@ class _RRDBNetBase(_lib.CacheMixin, nn.Module):
         self.mblocks = int(os.environ.get("BHSR_MBLOCKS", "0"))  # 0 = auto (2)
         self._packed = None       # (key, packed, biases)
         self._workspace = {}      # (device, nb, h, w, feature) -> uint8 tensor
+        self.use_cuda_graph = False   # opt-in: replay the whole forward from a CUDA graph (see _run)
 
     # -- parameter plumbing
     def _child(self, i):
@@ -236,6 +237,48 @@ class _RRDBNetBase(_lib.CacheMixin, nn.Module):
 
     # -- the hot call
     def _run(self, x: torch.Tensor, feature: bool, scale: int) -> torch.Tensor:
+        """Eager schedule (356 launches at 23 blocks), or — with `self.use_cuda_graph = True` — one CUDA-graph launch.
+
+        Graph mode keeps one captured graph per (input address / shape / strides, feature, numerics, weights) and
+        replays it: the kernels, their tensor maps and the OUTPUT buffer are baked in, so the returned tensor is
+        overwritten by the next call with the same input buffer (callers that keep results must clone them).  It is
+        opt-in because of that aliasing; bench.py and the sharded predictor, which consume each result before the
+        next step, turn it on."""
+        if getattr(self, "use_cuda_graph", False) and x.is_cuda and not torch.cuda.is_current_stream_capturing():
+            y = self._run_graphed(x, feature, scale)
+            if y is not None:
+                return y
+        return self._run_eager(x, feature, scale)
+
+    def _run_graphed(self, x, feature, scale):
+        convs = self._tc_convs()
+        numerics = NUMERICS[self.numerics]
+        key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, bool(feature), scale, self.mblocks,
+               self._cache_key(convs, x.device, numerics))
+        graphs = self.__dict__.setdefault("_graphs", {})
+        entry = graphs.get(key)
+        if entry is None:
+            if len(graphs) >= 8:
+                graphs.clear()
+            try:
+                self._run_eager(x, feature, scale)            # warm the packed-weight / workspace caches
+                torch.cuda.current_stream(x.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    y = self._run_eager(x, feature, scale)
+                # everything whose ADDRESS the graph baked in must outlive it: the input buffer, the packed weights
+                # / biases (re-packed into new tensors when `numerics` or the parameters change) and the workspaces
+                entry = (g, y, (x, self._packed, dict(self._workspace)))
+            except Exception as e:                             # capture refused: remember, fall back to eager launches
+                entry = (None, None, str(e))
+                torch.cuda.synchronize(x.device)
+            graphs[key] = entry
+        if entry[0] is None:
+            return None
+        entry[0].replay()
+        return entry[1]
+
+    def _run_eager(self, x: torch.Tensor, feature: bool, scale: int) -> torch.Tensor:
         _lib.require_cuda(x, "x")
         _no_autograd(type(self).__name__, x, *self.parameters())
         first, last = self._child(0), self._child(6)

@@ -407,6 +407,40 @@ def test_rrdbnet_full_batch_full_tensor_vs_oracle(dev, golden):
         del net
 
 
+def test_rrdbnet_cuda_graph_replay_matches_eager(dev):
+    """Opt-in graph mode (RRDBNet.use_cuda_graph): the whole forward replayed as one CUDA-graph launch gives
+    bit-identical results to the 356 eager launches, follows new input values written into the same buffer,
+    keeps separate graphs per input buffer / numerics, and is dropped when the weights change."""
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_block=2, seed=5)
+    net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=4, num_feat=64, num_block=2, num_grow_ch=32), sd, dev)
+    xa = cuda(synth.tiles(4, 6, seed=1), dev)
+    xb = cuda(synth.tiles(4, 6, seed=2), dev)
+    with torch.no_grad():
+        ea = net.forward_feature(xa[:, :3]).clone()
+        eb = net.forward_feature(xb[:, :3]).clone()
+        net.use_cuda_graph = True
+        ga = net.forward_feature(xa[:, :3])
+        assert torch.equal(ga, ea)
+        gb = net.forward_feature(xb[:, :3])
+        assert torch.equal(gb, eb) and torch.equal(ga, ea)      # another input buffer: another graph and output
+        ga2 = net.forward_feature(xa[:, :3])                      # replay
+        assert ga2.data_ptr() == ga.data_ptr() and torch.equal(ga2, ea)
+        xa.copy_(xb)                                              # new values in the captured input buffer
+        assert torch.equal(net.forward_feature(xa[:, :3]), eb)
+        assert len(net._graphs) == 2 and all(e[0] is not None for e in net._graphs.values())
+        net.numerics = "fast"
+        fast = net.forward_feature(xb[:, :3]).clone()
+        net.use_cuda_graph = False
+        assert torch.equal(net.forward_feature(xb[:, :3]), fast)
+        net.use_cuda_graph = True
+        net.numerics = "exact"
+        net.conv_body.bias.add_(0.25)                             # weights changed: stale graphs must not be used
+        changed = net.forward_feature(xb[:, :3]).clone()
+        net.use_cuda_graph = False
+        assert torch.equal(net.forward_feature(xb[:, :3]), changed) and not torch.equal(changed, eb)
+
+
 def test_error_behaviour(dev):
     from bhsr import rrdbnet
     from bhsr._lib import BhsrError
