@@ -269,6 +269,20 @@ int bhsr_head_wgrad_tc(const BhsrHeadXform* xt, const BhsrHeadXform* gt, int32_t
 int bhsr_aggregate(const float* x, int32_t nimg, int32_t h, int32_t w, int32_t step,
                    float threshold, int32_t strict, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The element-wise ends of the path (post.cu).
+ * bhsr_predict_postproc: predict_realesanet_feature_globe.py:172-177 — height [nb][1][h][w]: negatives -> 0,
+ *   round(h * 10) -> uint16; build [nb][k][h][w]: softmax over k, round(p * 255) -> uint16 (round half to even,
+ *   like numpy).  Either input may be NULL (with its output).
+ * bhsr_weighted_mse: losses_pytorch/selfloss.py:81-90 — loss = mean(weight * (pred - target)^2) * exp(-log_var) +
+ *   log_var, forward and backward in one pass: grad_pred[n] (may be NULL), *grad_log_var (may be NULL), *loss;
+ *   scratch = one double of device memory.
+ * ------------------------------------------------------------------------------------------ */
+int bhsr_predict_postproc(const float* height, const float* build, int32_t nb, int32_t k, int32_t h, int32_t w,
+                          uint16_t* out_height, uint16_t* out_build, void* stream);
+int bhsr_weighted_mse(const float* pred, const float* target, const float* weight, int64_t n, const float* log_var,
+                      float* loss, float* grad_pred, float* grad_log_var, double* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -302,3 +302,25 @@ def weighted_mse_adapt(pred: np.ndarray, target: np.ndarray, weight: np.ndarray,
     mean(weight * (pred-target)^2) * exp(-log_var) + log_var."""
     loss = np.mean(weight.astype(np.float64) * (pred.astype(np.float64) - target.astype(np.float64)) ** 2)
     return float(loss * np.exp(-log_var) + log_var)
+
+
+# --------------------------------------------------------------------------- predictor post-processing / loss
+def predict_postprocess(ypred: np.ndarray, build_pred: np.ndarray):
+    """predict_realesanet_feature_globe.py:172-177: `ypred[ypred<0] = 0; round(ypred*10).astype(uint16)` and
+    `round(softmax(build_pred, dim=1) * 255).astype(uint16)` (numpy rounding: half to even), float32 arithmetic."""
+    y = ypred.astype(np.float32).copy()
+    y[y < 0] = 0
+    y = np.round(y * np.float32(10)).astype(np.uint16)
+    b = build_pred.astype(np.float32)
+    e = np.exp(b - b.max(axis=1, keepdims=True), dtype=np.float32)
+    p = e / e.sum(axis=1, keepdims=True, dtype=np.float32)
+    return y, np.round(p * np.float32(255)).astype(np.uint16)
+
+
+def mse_adapt_weight(pred: np.ndarray, target: np.ndarray, weight: np.ndarray, log_var: float):
+    """losses_pytorch/selfloss.py:81-90 with its gradients (float64): loss, d loss/d pred, d loss/d log_var."""
+    d = pred.astype(np.float64) - target.astype(np.float64)
+    w = weight.astype(np.float64)
+    mean = (w * d * d).mean()
+    prec = np.exp(-float(log_var))
+    return mean * prec + float(log_var), 2.0 * w * d * prec / d.size, 1.0 - mean * prec

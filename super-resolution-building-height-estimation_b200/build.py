@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libbhsr.so")
-SOURCES = ["common.cu", "conv_tc.cu", "plumbing.cu", "rrdbnet.cu", "head.cu", "head_tc.cu"]
+SOURCES = ["common.cu", "conv_tc.cu", "plumbing.cu", "rrdbnet.cu", "head.cu", "head_tc.cu", "post.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]
 

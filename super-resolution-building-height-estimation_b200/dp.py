@@ -41,14 +41,48 @@ class Dice(nn.Module):
         return 1 - (2. * intersection + smooth) / (m1.sum() + m2.sum() + smooth)
 
 
+class _WeightedMSEFn(torch.autograd.Function):
+    """`bhsr_weighted_mse` (post.cu): loss and both gradients from ONE pass over prediction / target / weight."""
+
+    @staticmethod
+    def forward(ctx, pred, target, weight, log_var):
+        import ctypes as C  # noqa: F401
+        from . import _lib
+        p = pred.contiguous().float()
+        t = target.expand_as(pred).contiguous().float()
+        w = weight.expand_as(pred).contiguous().float()
+        dev = p.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[3]
+        gp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        gs = torch.empty((), dtype=torch.float32, device=dev) if need else None
+        scratch = torch.empty(1, dtype=torch.float64, device=dev)
+        with _lib.on_device(p):
+            _lib.check(_lib.load().bhsr_weighted_mse(p.data_ptr(), t.data_ptr(), w.data_ptr(), p.numel(),
+                                                     log_var.data_ptr(), loss.data_ptr(), _lib.ptr(gp), _lib.ptr(gs),
+                                                     scratch.data_ptr(), _lib.stream_ptr(dev)), "bhsr_weighted_mse")
+        ctx.save_for_backward(gp, gs)
+        ctx.shape = pred.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        gp, gs = ctx.saved_tensors
+        return (gp.view(ctx.shape) * go if gp is not None else None, None, None, gs * go if gs is not None else None)
+
+
 class MSE_adapt_weight(nn.Module):
-    """mean(weight * (x - y)^2) * exp(-log_var) + log_var   (selfloss.py:81-90)."""
+    """mean(weight * (x - y)^2) * exp(-log_var) + log_var   (selfloss.py:81-90).  CUDA tensors run the fused
+    forward+backward kernel (`bhsr_weighted_mse`); host tensors (loader-side checks, gloo tests) the same formula in
+    torch."""
 
     def __init__(self, log_var=0.0, device="cuda"):
         super().__init__()
         self.log_var = nn.Parameter(torch.tensor(float(log_var), device=device))
 
     def forward(self, inputs, targets, weight):
+        if inputs.is_cuda and inputs.dtype == torch.float32 and self.log_var.is_cuda:
+            return _WeightedMSEFn.apply(inputs, targets, weight, self.log_var)
         loss = F.mse_loss(inputs, targets, reduction='none')
         loss = (loss * weight).mean()
         return loss * torch.exp(-self.log_var) + self.log_var
@@ -205,14 +239,135 @@ class GraphedTrainStep:
 
 @torch.no_grad()
 def predict_shard(net_g, net, tiles: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """predict_realesanet_feature_globe.py:167-177 on a batch of tiles already on the GPU:
-    returns (height*10 as uint16-valued int32 [B,1,256,256], softmax*255 as int32 [B,K,256,256])
-    — torch has no uint16 arithmetic; values are the reference's uint16 numbers."""
+    """predict_realesanet_feature_globe.py:167-177 on a batch of tiles already on the GPU: features, head, then the
+    fused post-processing kernel (`bhsr_predict_postproc`): height -> max(h, 0), round(h * 10) -> uint16; height
+    levels -> softmax over the K channels, round(p * 255) -> uint16.  Returns (uint16 [B,1,256,256], uint16
+    [B,K,256,256]) — the reference's numbers, one pass over the head's outputs."""
     hr_fea = net_g.forward_feature(tiles[:, :3])
     ypred, build_pred = net(tiles, hr_fea)[:2]
-    ypred = torch.round(ypred.clamp_min(0) * 10).to(torch.int32)
-    build = torch.round(torch.softmax(build_pred, dim=1) * 255).to(torch.int32)
-    return ypred, build
+    return predict_postprocess(ypred, build_pred)
+
+
+@torch.no_grad()
+def predict_postprocess(ypred: torch.Tensor, build_pred: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    from . import _lib
+    _lib.require_cuda(ypred, "ypred")
+    y = ypred.contiguous().float()
+    b = build_pred.contiguous().float()
+    nb, k, h, w = b.shape
+    assert y.shape == (nb, 1, h, w)
+    out_h = torch.empty((nb, 1, h, w), dtype=torch.uint16, device=y.device)
+    out_b = torch.empty((nb, k, h, w), dtype=torch.uint16, device=y.device)
+    with _lib.on_device(y):
+        _lib.check(_lib.load().bhsr_predict_postproc(y.data_ptr(), b.data_ptr(), nb, k, h, w, out_h.data_ptr(),
+                                                     out_b.data_ptr(), _lib.stream_ptr(y.device)),
+                   "bhsr_predict_postproc")
+    return out_h, out_b
+
+
+# ------------------------------------------------------------------ epoch loops (row N1: train.py:225-343)
+class _DeviceMeter:
+    """AverageMeter (train.py:55-64) whose sums stay on the device: the reference calls `.item()` three times per
+    iteration (train.py:260-265), each a host synchronisation; here the epoch ends with one."""
+
+    def __init__(self, device):
+        self.sum = torch.zeros((), dtype=torch.float64, device=device)
+        self.count = 0
+
+    def update(self, val: torch.Tensor, n: int) -> None:
+        self.sum += val.detach().double() * n
+        self.count += n
+
+    @property
+    def avg(self) -> float:
+        return float(self.sum.item()) / max(self.count, 1)
+
+
+def train_epoch_aggre_weight(net, net_g, criterion, dataloader, optimizer, device, rgbseq=(0, 1, 2),
+                             bucket: Optional["FlatGradAllReduce"] = None):
+    """train.py:225-271: one epoch of the isaggre=True recipe.  `dataloader` yields (lr, (height, height_aggre),
+    build, (weight, weight_aggre)) like BH_loader.myImageFloder_S12_globe.  Returns (mean loss, mean RMSE,
+    [log_var of each criterion]) — per-sample weighted by batch size like the reference's AverageMeter."""
+    net.train()
+    losses, acc = _DeviceMeter(device), _DeviceMeter(device)
+    for lr, heightall, build, weightall in dataloader:
+        lr = lr.to(device, non_blocking=True)
+        height = heightall[0].to(device, non_blocking=True)
+        height_aggre = heightall[1].to(device, non_blocking=True)
+        build = build.to(device, non_blocking=True)
+        weight = weightall[0].to(device, non_blocking=True)
+        weight_aggre = weightall[1].to(device, non_blocking=True)
+        with torch.no_grad():
+            hr_fea = net_g.forward_feature(lr[:, list(rgbseq)])
+        height_pred, build_pred, height_pred_aggre = net(lr, hr_fea)
+        height_pred = height_pred.squeeze(1)
+        height_pred_aggre = height_pred_aggre.squeeze(1)
+        loss = criterion[0](height_pred, height, weight) + \
+            criterion[1](height_pred_aggre, height_aggre, weight_aggre) + \
+            criterion[2](build_pred, build, weight)
+        if bucket is not None:
+            bucket.zero_()
+        else:
+            optimizer.zero_grad()
+        loss.backward()
+        if bucket is not None:
+            bucket.all_reduce()
+        optimizer.step()
+        bsize = lr.size(0)
+        losses.update(loss, bsize)
+        with torch.no_grad():
+            acc.update(torch.sqrt(((height_pred - height) ** 2).mean()), bsize)
+    lossweight = [float(c.log_var.item()) for c in criterion]
+    return losses.avg, acc.avg, lossweight
+
+
+@torch.no_grad()
+def vtest_epoch(net, net_g, dataloader, device, rgbseq=(0, 1, 2)):
+    """train.py:318-343: validation MSE / RMSE of the height output (eval mode: the head runs on the tensor-core
+    eval path).  `dataloader` yields (x, y_true, _, _)."""
+    net.eval()
+    losses, acc = _DeviceMeter(device), _DeviceMeter(device)
+    for x, y_true, _, _ in dataloader:
+        x = x.to(device, non_blocking=True)
+        y_true = y_true.to(device, non_blocking=True)
+        hr_fea = net_g.forward_feature(x[:, list(rgbseq)])
+        ypred = net(x, hr_fea)[0].squeeze(1)
+        mse = torch.mean((ypred - y_true) ** 2)
+        losses.update(mse, x.size(0))
+        acc.update(torch.sqrt(mse), x.size(0))
+    return losses.avg, acc.avg
+
+
+def fit(net, net_g, train_loader, val_loader, logdir: str, epochs: int, init_lr: float = 1e-3, device="cuda",
+        rgbseq=(0, 1, 2), bucket_params: bool = True, log=None):
+    """The epoch loop of train.py:150-222 for the isaggre recipe: resume from `logdir/checkpoint.tar`, per-epoch
+    step LR schedule, train epoch, validation, checkpoint (+ best / every-5th copies).  Gradients live in one flat
+    bucket (`FlatGradAllReduce`), so under torch.distributed every step is ONE all-reduce.  Returns the per-epoch
+    records [{'epoch', 'lr', 'train_loss', 'train_rmse', 'val_loss', 'val_rmse', 'log_vars'}]."""
+    start_epoch, best_acc, log_vars = load_checkpoint(logdir, net, map_location=device)
+    if best_acc is None:
+        best_acc = 0            # train.py:108 (with this start `is_best` never fires; kept as in the reference)
+    optimizer, criterion = build_training_state(net, init_lr, True, log_vars, device)
+    bucket = None
+    if bucket_params:
+        params = [p for g in optimizer.param_groups for p in g['params']]
+        bucket = FlatGradAllReduce(params)
+    history = []
+    for epoch in range(epochs):
+        if epoch < start_epoch:
+            continue
+        epoch = epoch + 1
+        lr = adjust_learning_rate(init_lr, epoch, optimizer)
+        train_loss, train_rmse, lossweight = train_epoch_aggre_weight(net, net_g, criterion, train_loader, optimizer,
+                                                                      device, rgbseq, bucket)
+        val_loss, val_rmse = vtest_epoch(net, net_g, val_loader, device, rgbseq)
+        best_acc, _ = save_checkpoint(logdir, epoch, net, lossweight, best_acc, val_rmse, True)
+        rec = {'epoch': epoch, 'lr': lr, 'train_loss': train_loss, 'train_rmse': train_rmse, 'val_loss': val_loss,
+               'val_rmse': val_rmse, 'log_vars': lossweight}
+        history.append(rec)
+        if log is not None:
+            log(rec)
+    return history
 
 
 def hierweight(stats, hir: Sequence[int], mode: str = "sqrt") -> torch.Tensor:

@@ -781,21 +781,21 @@ class Refine_residual(nn.Module):
 
 
 class _ConvBNReLUStack(nn.Sequential):
-    """The `fuse` stack of the HRfuse / HRfuse_x2 ablation heads (SR/HRfuse.py:51-57, 75-81):
-    conv3x3-BN-ReLU twice.  State-dict surface only: the ablation heads are never instantiated by
-    train.py / predict_realesanet_feature_globe.py and have no kernel schedule yet."""
+    """The `fuse` stack of the HRfuse / HRfuse_x2 ablation heads (SR/HRfuse.py:51-57, 75-81): conv3x3-BN-ReLU twice.
+    The convs run on the head's conv kernels (autograd included); BatchNorm / ReLU are the stock modules."""
 
     def __init__(self, cin, mid):
         super().__init__(nn.Conv2d(cin, mid, 3, 1, 1, bias=False), nn.BatchNorm2d(mid), nn.ReLU(inplace=True),
                          nn.Conv2d(mid, mid, 3, 1, 1, bias=False), nn.BatchNorm2d(mid), nn.ReLU(inplace=True))
 
     def forward(self, x):
-        raise NotImplementedError("HRfuse / HRfuse_x2 (ablation heads, SR/HRfuse.py:47-89) are outside the "
-                                  "B200 hot path; use HRfuse_residual")
+        for m in self:
+            x = conv2d(x, m.weight, m.bias) if isinstance(m, nn.Conv2d) else m(x)
+        return x
 
 
 class HRfuse(nn.Module):
-    """SR/HRfuse.py:47-66 (ablation; parameter surface only)."""
+    """SR/HRfuse.py:47-66 (ablation head: fuse at the low resolution, then upsample)."""
 
     def __init__(self, hr_channel=16, lr_channel=16, mid_channel=16, out_channel=3, upscale=4):
         super().__init__()
@@ -804,11 +804,13 @@ class HRfuse(nn.Module):
         self.conv_last = nn.Conv2d(mid_channel, out_channel, 3, 1, 1)
 
     def forward(self, x_lr, x_hr):
-        return self.fuse(torch.cat([x_lr, x_hr], dim=1))
+        x = self.fuse(torch.cat([x_lr, x_hr], dim=1))
+        x = self.upsampler(x)
+        return conv2d(x, self.conv_last.weight, self.conv_last.bias)
 
 
 class HRfuse_x2(nn.Module):
-    """SR/HRfuse.py:69-89 (ablation; parameter surface only)."""
+    """SR/HRfuse.py:69-89 (ablation head: upsample the LR features, then fuse at the high resolution)."""
 
     def __init__(self, hr_channel=16, lr_channel=16, mid_channel=16, out_channel=3, upscale=4):
         super().__init__()
@@ -817,4 +819,6 @@ class HRfuse_x2(nn.Module):
         self.conv_last = nn.Conv2d(mid_channel, out_channel, 3, 1, 1)
 
     def forward(self, x_lr, x_hr):
-        return self.fuse(torch.cat([self.upsampler(x_lr), x_hr], dim=1))
+        x_lr = self.upsampler(x_lr)
+        x = self.fuse(torch.cat([x_lr, x_hr], dim=1))
+        return conv2d(x, self.conv_last.weight, self.conv_last.bias)

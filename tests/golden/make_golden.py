@@ -135,6 +135,22 @@ def srregress_goldens(out):
               "build range", float(res[1].min()), float(res[1].max()))
 
 
+def hrfuse_ablation_goldens(out, hrf):
+    """HRfuse / HRfuse_x2 (SR/HRfuse.py:47-89), eval and train mode."""
+    lr = synth.features(2, 16, 16, 16, seed=22)
+    hr_lr = synth.features(2, 16, 16, 16, seed=24)      # HRfuse concatenates at the LOW resolution
+    hr16 = synth.features(2, 16, 64, 64, seed=23)
+    for training in (False, True):
+        tag = "train" if training else "eval"
+        with torch.no_grad():
+            m = load_sd(hrf.HRfuse(16, 16, 16, 3, 4), synth.hrfuse_plain_state(seed=81))
+            m.train(training)
+            out[f"hrfuse_plain_{tag}"] = m(t(lr), t(hr_lr)).numpy()
+            m = load_sd(hrf.HRfuse_x2(16, 16, 16, 3, 4), synth.hrfuse_plain_state(seed=82))
+            m.train(training)
+            out[f"hrfuse_x2_{tag}"] = m(t(lr), t(hr16)).numpy()
+
+
 def t(a):
     return torch.from_numpy(np.ascontiguousarray(a))
 
@@ -149,6 +165,14 @@ def main():
     torch.manual_seed(0)
     arch, old, hrf, agg = import_reference()
     out = {}
+    if "--only-hrfuse-ablation" in sys.argv:
+        path = os.path.join(HERE, "reference_vectors.npz")
+        with np.load(path) as z:
+            out = {k: z[k] for k in z.files if not k.startswith(("hrfuse_plain_", "hrfuse_x2_"))}
+        hrfuse_ablation_goldens(out, hrf)
+        np.savez_compressed(path, **out)
+        print("updated reference_vectors.npz", os.path.getsize(path) / 1e6, "MB;", len(out), "arrays")
+        return
     if "--only-srregress" in sys.argv:   # add / refresh the a16 vectors, keep every other array as it is
         path = os.path.join(HERE, "reference_vectors.npz")
         with np.load(path) as z:
@@ -256,6 +280,7 @@ def main():
 
     # ---------------------------------------------------------------- SRRegress_Cls_feature (a16)
     srregress_goldens(out)
+    hrfuse_ablation_goldens(out, hrf)
 
     # ---------------------------------------------------------------- aggregation
     h256 = (np.random.RandomState(8).rand(1, 1, 256, 256) * 60).astype(np.float32)

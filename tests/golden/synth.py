@@ -116,6 +116,20 @@ def hrfuse_residual_state(hr=16, lr=16, mid=16, out=1, upscale=4, seed=0, prefix
     return sd
 
 
+def hrfuse_plain_state(hr=16, lr=16, mid=16, out=3, upscale=4, seed=0):
+    """HRfuse / HRfuse_x2 (SR/HRfuse.py:47-89): `fuse` = conv-BN-ReLU twice, `upsampler`, `conv_last`."""
+    rng = np.random.RandomState(seed)
+    sd = OrderedDict()
+    sd["fuse.0.weight"] = _conv_w(rng, mid, hr + lr, 3, 1.4)
+    _bn(rng, sd, "fuse.1", mid)
+    sd["fuse.3.weight"] = _conv_w(rng, mid, mid, 3, 1.4)
+    _bn(rng, sd, "fuse.4", mid)
+    upsampler_state(rng, sd, "upsampler", mid, upscale)
+    sd["conv_last.weight"] = _conv_w(rng, out, mid, 3, 1.0)
+    sd["conv_last.bias"] = _bias(rng, out)
+    return sd
+
+
 def head_state(super_in=64, super_mid=16, chans_build=7, isaggre=True, seed=0):
     """The reference-owned (non-smp) parameters of SRRegress_Cls_feature (mymodels.py:259-268)."""
     sd = OrderedDict()

@@ -381,3 +381,90 @@ def test_conv_tc_train_vs_cuda_core_conv(dev, cin, cout, k, shuffle, unshuffle):
         base = ya.clone()
         hrfuse._conv_tc_train(x, wt, None, x_unshuffle=unshuffle, y=ya, accumulate=True, **kw)
         assert_close(ya.cpu().numpy(), 2 * base.cpu().numpy(), rtol=1e-3, atol=2e-4, what="accumulate")
+
+
+def test_predict_postprocess_kernel_vs_oracle(dev):
+    """N2: the fused quantise epilogue of the predictor (predict_realesanet_feature_globe.py:172-177)."""
+    from bhsr import dp
+    rng = np.random.RandomState(3)
+    y = (rng.standard_normal((3, 1, 40, 72)) * 20).astype(np.float32)
+    y[0, 0, :4, :4] = np.array([0.05, 0.15, 0.25, 1e4])[None, :]         # ties (half to even) and uint16 saturation
+    b = (rng.standard_normal((3, 7, 40, 72)) * 3).astype(np.float32)
+    yq, bq = dp.predict_postprocess(cuda(y, dev), cuda(b, dev))
+    assert yq.dtype == torch.uint16 and bq.dtype == torch.uint16
+    yr, br = R.predict_postprocess(np.minimum(y, 6553.5), b)
+    yg, bg = yq.cpu().numpy().astype(np.int64), bq.cpu().numpy().astype(np.int64)
+    assert np.array_equal(yg, yr.astype(np.int64))
+    diff = np.abs(bg - br.astype(np.int64))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3     # expf vs numpy exp: at most one level, at ties only
+    assert np.array_equal(np.argmax(bg, 1), np.argmax(br, 1)) or (np.argmax(bg, 1) != np.argmax(br, 1)).mean() < 1e-3
+
+
+def test_fused_weighted_mse_loss_vs_oracle(dev):
+    """N4: `MSE_adapt_weight` (selfloss.py:81-90) as one fused forward+backward kernel."""
+    from bhsr import dp
+    rng = np.random.RandomState(4)
+    p = (rng.standard_normal((4, 256, 256)) * 5).astype(np.float32)
+    t = np.floor(rng.rand(4, 256, 256) * 40 * (rng.rand(4, 256, 256) > 0.8)).astype(np.float32)
+    w = (0.1 + 3 * rng.rand(4, 256, 256)).astype(np.float32)
+    crit = dp.MSE_adapt_weight(0.3, dev)
+    pg = cuda(p, dev).requires_grad_(True)
+    loss = crit(pg, cuda(t, dev), cuda(w, dev))
+    (loss * 1.5).backward()
+    lref, gref, sref = R.mse_adapt_weight(p, t, w, 0.3)
+    np.testing.assert_allclose(float(loss), lref, rtol=1e-5)
+    assert_close(pg.grad.cpu().numpy(), 1.5 * gref, rtol=1e-5, atol=1e-9, what="d loss / d pred")
+    np.testing.assert_allclose(float(crit.log_var.grad), 1.5 * sref, rtol=1e-5)
+    # and it is what the stock formula gives on the same tensors
+    crit2 = dp.MSE_adapt_weight(0.3, dev)
+    p2 = cuda(p, dev).requires_grad_(True)
+    l2 = (torch.nn.functional.mse_loss(p2, cuda(t, dev), reduction="none") * cuda(w, dev)).mean() * \
+        torch.exp(-crit2.log_var) + crit2.log_var
+    np.testing.assert_allclose(float(loss), float(l2), rtol=1e-5)
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_hrfuse_ablation_heads_vs_golden(dev, golden, training):
+    """HRfuse / HRfuse_x2 (SR/HRfuse.py:47-89) against the reference modules' outputs."""
+    from bhsr import hrfuse
+    tag = "train" if training else "eval"
+    lr = synth.features(2, 16, 16, 16, seed=22)
+    hr_lr = synth.features(2, 16, 16, 16, seed=24)
+    hr16 = synth.features(2, 16, 64, 64, seed=23)
+    with torch.no_grad():
+        m = load_np_state(hrfuse.HRfuse(16, 16, 16, 3, 4), synth.hrfuse_plain_state(seed=81), dev).train(training)
+        assert_close(m(cuda(lr, dev), cuda(hr_lr, dev)).cpu().numpy(), golden[f"hrfuse_plain_{tag}"], what=f"HRfuse {tag}")
+        m = load_np_state(hrfuse.HRfuse_x2(16, 16, 16, 3, 4), synth.hrfuse_plain_state(seed=82), dev).train(training)
+        assert_close(m(cuda(lr, dev), cuda(hr16, dev)).cpu().numpy(), golden[f"hrfuse_x2_{tag}"], what=f"HRfuse_x2 {tag}")
+
+
+def test_epoch_harness_two_epochs(dev, tmp_path):
+    """N1: dp.fit — the epoch loop of train.py:150-343 (LR schedule, train epoch with the flat gradient bucket,
+    validation on the eval tensor-core path, checkpoint + resume) on a tiny synthetic loader."""
+    from bhsr import dp
+    from bhsr.models import SRRegress_Cls_feature
+    from bhsr.rrdbnet import RRDBNet
+    torch.manual_seed(0)
+    net_g = RRDBNet(3, 3, scale=4, num_feat=64, num_block=1, num_grow_ch=32).to(dev).eval()
+    for p in net_g.parameters():
+        p.requires_grad = False
+    net = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64, super_mid=16,
+                                upscale=4, isaggre=True, chans_build=7).to(dev)
+
+    def batches(n, seed):
+        out = []
+        for i in range(n):
+            x = torch.from_numpy(synth.tiles(2, 8, seed=seed + i))
+            h, ha, b, w, wa = (t_.cpu() for t_ in dp.synthetic_labels(2, "cpu", seed=seed + i))
+            out.append((x, (h, ha), b, (w, wa)))
+        return out
+
+    train = batches(3, 10)
+    val = [(x, hh[0], None, None) for x, hh, _, _ in batches(2, 50)]
+    hist = dp.fit(net, net_g, train, val, str(tmp_path), epochs=2, init_lr=1e-3, device=dev)
+    assert [r["epoch"] for r in hist] == [1, 2] and all(np.isfinite(r["train_loss"]) and np.isfinite(r["val_rmse"]) for r in hist)
+    assert hist[0]["lr"] == 1e-3 and len(hist[0]["log_vars"]) == 3
+    ck = torch.load(tmp_path / "checkpoint.tar", map_location="cpu")
+    assert set(ck) == {"epoch", "state_dict", "log_vars", "best_acc"} and ck["epoch"] == 2      # train.py:202-208
+    more = dp.fit(net, net_g, train, val, str(tmp_path), epochs=3, init_lr=1e-3, device=dev)    # resumes at epoch 3
+    assert [r["epoch"] for r in more] == [3]

@@ -108,7 +108,7 @@ def main():
         n_grids = args.grids
         mine = list(dp.shard_indices((n_grids + B - 1) // B, rank, world))  # batches of this rank
         x = torch.from_numpy(synth.tiles(B, 8, seed=7 + rank)).to(dev)
-        host_h = torch.empty((B, 1, 256, 256), dtype=torch.int32).pin_memory()
+        host_h = torch.empty((B, 1, 256, 256), dtype=torch.uint16).pin_memory()
 
         def sweep(_):
             for _b in mine:
