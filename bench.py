@@ -138,7 +138,9 @@ def synth_state_torch(num_block):
 def _ncu_traffic():
     """dram bytes per launch of the RDB conv kernels from the committed `ncu --set full` capture
     (profiles/r01_ncu_kernels.json, written by tools/make_profile_summary.py)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")
+    path = os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")
     if not os.path.exists(path):
         return {}
     with open(path) as f:

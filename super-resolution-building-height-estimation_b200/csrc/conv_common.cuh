@@ -154,6 +154,13 @@ __device__ __forceinline__ void finish_slice32(const ConvTcKernelParams& p, floa
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (j < nvalid) o[j * plane] += v[j];
+      } else if (nvalid >= 32) {      // whole slice (conv_hr): no per-channel predicate, pointer walks by one plane
+        float* oo = o;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          __stcs(oo, v[j]);           // streaming store: the 1 GB feature map is not re-read by this kernel
+          oo += plane;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)

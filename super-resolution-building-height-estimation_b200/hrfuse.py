@@ -520,11 +520,16 @@ def _basic_block_tc(blk: "BasicBlock", xin, cin: int):
 
 
 def _to_planes(x: Tensor, ctot: int, choff: int = 0, dst=None):
+    """fp32 NCHW -> channels [choff, choff + C) of (new or given) NHWC hi/lo planes (bhsr_head_to_planes; channel
+    counts that are not multiples of 8 take the scalar round-1 kernel)."""
     x = _prep(x)
     nb, c, h, w = x.shape
     if dst is None:
         dst = _planes(nb, h, w, ctot, x.device)
-    ops.nchw_to_planes(x, dst[0], dst[1], choff)
+    if c % 8 == 0 and choff % 8 == 0:
+        ops.head_to_planes(x, ops.head_xform(x, c, h, w), dst[0], dst[1], choff, c)
+    else:
+        ops.nchw_to_planes(x, dst[0], dst[1], choff)
     return dst
 
 

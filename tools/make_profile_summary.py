@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Build profiles/r01_summary.md from the artefacts a gpurun profile call brought back
+"""Build profiles/<round>_summary.md (round = $BHSR_ROUND, default r02) from the artefacts a gpurun profile call brought back
 (gpurun_out/launches_*.csv, gpurun_out/prof_rdb_*.ncu-rep) plus the saved bench lines."""
 import collections
 import csv
@@ -12,6 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
+ROUND = os.environ.get("BHSR_ROUND", "r02")
 
 
 def launch_table(path):
@@ -51,7 +52,7 @@ def ncu_raw(rep):
 
 
 def main():
-    lines = ["# Round 1 profile summary (B200, sm_100a)", "",
+    lines = [f"# Round {int(ROUND[1:])} profile summary (B200, sm_100a)", "",
              "All numbers below come from `gpurun` calls on a B200; ncu times are cold-cache and serialised "
              "(compare shares, not absolutes); bench lines are CUDA-event timings outside any profiler.", ""]
     for mode in ("exact", "fast"):
@@ -60,7 +61,7 @@ def main():
             continue
         by, tot, seq = launch_table(path)
         lines += [f"## Launch list of one `forward_feature` step, B=64, numerics={mode}",
-                  f"`ncu --metrics gpu__time_duration.sum --clock-control none` on `bench.py --steps 1 --warmup 3 --numerics {mode}`; "
+                  f"`ncu --metrics gpu__time_duration.sum --clock-control none` on `bench.py --steps 1 --warmup 3 --numerics {mode} --no-graph`; "
                   f"{sum(n for n, _ in by.values())} launches, {tot / 1000:.2f} ms total.", "",
                   "| kernel | launches | total us | share | avg us |", "|---|---|---|---|---|"]
         for k, (n, t) in by.items():
@@ -95,18 +96,18 @@ def main():
                     if lay != "?" and lay not in kjson:
                         kjson[lay] = {"dram_bytes": dram, "us_under_ncu": float(g("gpu__time_duration.sum").replace(",", "")),
                                       "tensor_pipe_active_pct": float(g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")),
-                                      "source": f"profiles/r01_summary.md (ncu --set full, {mode}, cold L2 per replay)"}
+                                      "source": f"profiles/{ROUND}_summary.md (ncu --set full, {mode}, cold L2 per replay)"}
                 except ValueError:
                     pass
             lines.append("")
             allk = {}
-            kpath = os.path.join(PROF, "r01_ncu_kernels.json")
+            kpath = os.path.join(PROF, f"{ROUND}_ncu_kernels.json")
             if os.path.exists(kpath):
                 allk = json.load(open(kpath))
             allk[mode] = kjson
             json.dump(allk, open(kpath, "w"), indent=1)
     for name in sorted(os.listdir(PROF)):
-        if name.startswith("r01_bench") and name.endswith(".json"):
+        if name.startswith(f"{ROUND}_bench") and name.endswith(".json"):
             try:
                 d = json.loads(open(os.path.join(PROF, name)).read().strip().split("\n")[0])
             except Exception:
@@ -116,7 +117,7 @@ def main():
                 lines.append(f"* `{name}`: {d.get('config', {}).get('numerics', d.get('impl', ''))} {d['value']:.0f} tiles/s "
                              f"({d.get('ms_per_step', 0):.2f} ms/step, roofline frac {d.get('roofline', {}).get('frac', 0):.3f})"
                              + (f"; {extra.get('numerics')} {extra.get('value', 0):.0f} tiles/s" if extra else ""))
-    open(os.path.join(PROF, "r01_summary.md"), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(PROF, f"{ROUND}_summary.md"), "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:60]))
 
 

@@ -7,10 +7,10 @@ RX='regex:conv_tc_kernel|conv_dx_kernel|conv_pair_kernel|conv3x3_'
 # launch list: 3 warm-up forwards x 356 conv launches are skipped, one whole step is listed
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$RX" \
    -s 1068 -c 356 --csv --log-file gpurun_out/launches_$NUM.csv \
-   python bench.py --steps 1 --warmup 3 --numerics $NUM --no-cpu-baseline --no-secondary > gpurun_out/launches_$NUM.log 2>&1
+   python bench.py --steps 1 --warmup 3 --numerics $NUM --no-cpu-baseline --no-secondary --no-train --no-graph > gpurun_out/launches_$NUM.log 2>&1
 echo "launch list rc=$?"
 # full capture of 10 consecutive trunk convs (two RDBs' worth: conv1..conv5 appear in order)
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:conv_tc_kernel|conv_dx_kernel|conv_pair_kernel" -s 1100 -c 10 \
-   -f -o gpurun_out/prof_rdb_$NUM python bench.py --steps 1 --warmup 3 --numerics $NUM --no-cpu-baseline --no-secondary > gpurun_out/prof_rdb_$NUM.log 2>&1
+   -f -o gpurun_out/prof_rdb_$NUM python bench.py --steps 1 --warmup 3 --numerics $NUM --no-cpu-baseline --no-secondary --no-train --no-graph > gpurun_out/prof_rdb_$NUM.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches_*.csv
