@@ -56,6 +56,9 @@ struct ConvTcKernelParams {
   // twice as many SMs share them (item index split_round, CTAs [0, split_items)); -1 = off
   int split_round, split_items, split_tile0;
   long long* dbg;  // optional [grid][8] cycle counters of the MMA warp (BHSR_DEBUG_TIMING)
+  // plane format (conv_dxs.cuh): lo = fp16((v - hi) * lo_mul), lo_mul = 2^11 (format 0) or 1 (format 1);
+  // out_mul = 2^-8 when the packed weights carry the format-1 pre-scale, else 1
+  float lo_mul, out_mul;
 };
 
 // CH = input channels per shared-memory chunk: 64 (128-byte pixel rows, SWIZZLE_128B) in fast
@@ -312,6 +315,7 @@ __device__ __forceinline__ void finish_planes32_rolled(const ConvTcKernelParams&
   }
   const bool chan_ok = cg * 8 < p.cout_valid;
   const int epi = p.epilogue;
+  const float lo_mul = p.lo_mul;
   __syncwarp();
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
@@ -347,7 +351,7 @@ __device__ __forceinline__ void finish_planes32_rolled(const ConvTcKernelParams&
         const __half2 h2 = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
         const float2 back = __half22float2(h2);
         hh[j] = h2;
-        ll[j] = __floats2half2_rn((x[2 * j] - back.x) * 2048.f, (x[2 * j + 1] - back.y) * 2048.f);
+        ll[j] = __floats2half2_rn((x[2 * j] - back.x) * lo_mul, (x[2 * j + 1] - back.y) * lo_mul);
       }
       const size_t off = static_cast<size_t>(op) * p.out_ctot + p.out_choff + cg * 8;
       *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hh);

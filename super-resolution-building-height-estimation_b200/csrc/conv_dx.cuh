@@ -499,6 +499,13 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         t_epi_wait += clock64() - tw0;
 #endif
         tc_fence_after();
+#ifdef BHSR_TIMING
+        if (p.nomma == 9) {   // diagnostic: the accumulator is released without being read (no tcgen05.ld at all)
+          tc_fence_before();
+          mbar_arrive(bar(B_TEMPTY + slot));
+          continue;
+        }
+#endif
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * COLS;
         // drain the three dx groups (main + 2^-11 * correction) and free the block at once
         float v0[32], v1[32], v2[32];

@@ -1,0 +1,601 @@
+// conv_dxs.cuh — round-2 successor of the dx-in-N kernel: ONE accumulator per block, tall tiles.
+#pragma once
+#include "conv_common.cuh"
+#include "conv_dx.cuh"
+
+namespace bhsr {
+
+// ======================================================================================
+// conv_dxs_kernel — dx-in-N conv for the 32-output 3x3 layers (SR/rrdbnet_arch.py:137-140) with
+// 96 TMEM columns per 128-row block, so that a tile is MB = 3 or 4 blocks tall.
+//
+// Why (profiles/r02_dx_layer_model.md): conv2..conv5 of a ResidualDenseBlock run at the rate the
+// L2 -> SM fabric delivers their operands (~30 B/clk/SM, 7 TB/s over the chip), and a 2-block
+// tile loads 7 image rows for 3.8 rows of outputs (1.83x) and re-streams the layer's weights for
+// every 252 pixels.  The 2-block limit came from TMEM: exact numerics kept TWO accumulators per
+// block (hi*hi and the 2^-11 cross terms; 192 columns).  Here all three split products of a
+// k-step go into the SAME 96 columns:
+//     D += A_hi * W_hi^T      D += A_hi * W_lo^T      D += A_lo * W_hi^T
+// which needs operands whose cross terms carry the same scale as the main term: plane format 1
+// (BHSR_PLANES_UNSCALED_LO: lo = fp16(v - hi), not multiplied by 2^11; fp16 subnormals keep
+// 2^-25 absolute) and weights pre-scaled by 2^8 before their own unscaled split (the epilogue
+// multiplies by 2^-8).  CPU emulation of the 23-block trunk: max err/tol 0.042 (random init) /
+// 0.055 (x4plus), identical to the two-accumulator split (tools/numerics_probe_single_acc.py).
+// Fast numerics is the same kernel with one product per k-step.
+//
+// Tile geometry: blocks advance by 126 flat pixels (rows 0 / 127 of a block have no neighbour for
+// the lane-shift combine); a tile of MB blocks needs ceil((326 + 126 (MB-1)) / 66) image rows of
+// the pitch-66 halo strip: 9 rows for 5.7 rows of outputs (MB = 3, 1.57x) or 11 for 7.6 (MB = 4,
+// 1.44x), and the weights are streamed once per 378 / 504 pixels.  Five accumulator slots rotate
+// (slot = running block index % 5), so with MB = 4 the first block of the next tile always finds a
+// slot that was drained a whole tile ago.  The last tile of a strip only runs its valid blocks.
+//
+// Issue order.  Inside a chunk the MMAs go window-row-major (one asm block per dy covers every block
+// of the tile: MB x KST (x2) MMAs and two barrier probes); around the accumulator hand-over — the
+// first chunk's first phase, the last chunk's last phase — and for ragged tiles they go
+// block-major, so block b's drain overlaps the MMAs of blocks b+1.. and the next tile's first
+// blocks start while this tile's last blocks are still being drained.
+constexpr int kDxsSlots = 5;
+constexpr int kDxsBars = 4 * kMaxAStages + 2 * kDxsSlots + 2 * kMaxWSlots;
+constexpr int kDxsTailBytes = kDxsBars * 8 + 16 + 2 * 64 * 4 + 64 + kDxStageBytes + kDxXchgFloats * 4;
+
+template <int MB>
+struct DxsRows { static constexpr int value = (326 + 126 * (MB - 1) + kPitch - 1) / kPitch; };
+
+// ---- issue blocks: NB blocks x KST k-steps (x2 when DUAL: W_hi rows, then the W_lo rows BOFF16 further)
+// operands: %0 %1 probe results | %2 a_lo %3 b_lo %4 desc_hi %5..%8 accumulators %9 idesc %10 acc_first
+//           %11 %12 probe 1 (barrier, parity) %13 %14 probe 2 | %15 A step to the next block minus the k advance,
+//           %16 k advance, %17 W_hi -> W_lo distance (descriptor units)
+#define BHSR_DXS_PRE                                                                   \
+  "{\n.reg .pred pacc, ptrue, pw1, pw2, pen;\n.reg .b32 alo, blo, bl2;\n.reg .b64 da, db;\n" \
+  "setp.ne.b32 pacc, %10, 0;\nsetp.eq.b32 ptrue, 0, 0;\n"                              \
+  "setp.ne.b32 pen, %11, 0;\nsetp.ne.b32 pw1, 0, 0;\nsetp.ne.b32 pw2, 0, 0;\n"          \
+  "@pen mbarrier.test_wait.parity.shared::cta.b64 pw1, [%11], %12;\n"                   \
+  "@pen mbarrier.test_wait.parity.shared::cta.b64 pw2, [%13], %14;\n"                   \
+  "mov.b32 alo, %2;\nmov.b32 blo, %3;\n"
+#define BHSR_DXS_S(D, ACC)                                                             \
+  "mov.b64 da, {alo, %4};\nmov.b64 db, {blo, %4};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %9, " ACC ";\n"                 \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_DXS_D(D, ACC)                                                             \
+  "mov.b64 da, {alo, %4};\nmov.b64 db, {blo, %4};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %9, " ACC ";\n"                 \
+  "add.u32 bl2, blo, %17;\nmov.b64 db, {bl2, %4};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %9, ptrue;\n"                   \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_DXS_NEXT "add.u32 alo, alo, %15;\nsub.u32 blo, blo, %16;\n"
+#define BHSR_DXS_POST "selp.u32 %0, 1, 0, pw1;\nselp.u32 %1, 1, 0, pw2;\n}\n"
+#define BHSR_DXS_K1(S, D) S(D, "pacc")
+#define BHSR_DXS_K2(S, D) S(D, "pacc") S(D, "ptrue")
+#define BHSR_DXS_K4(S, D) S(D, "pacc") S(D, "ptrue") S(D, "ptrue") S(D, "ptrue")
+#define BHSR_DXS_N1(K, S) K(S, "%5")
+#define BHSR_DXS_N2(K, S) K(S, "%5") BHSR_DXS_NEXT K(S, "%6")
+#define BHSR_DXS_N3(K, S) K(S, "%5") BHSR_DXS_NEXT K(S, "%6") BHSR_DXS_NEXT K(S, "%7")
+#define BHSR_DXS_N4(K, S) K(S, "%5") BHSR_DXS_NEXT K(S, "%6") BHSR_DXS_NEXT K(S, "%7") BHSR_DXS_NEXT K(S, "%8")
+#define BHSR_DXS_ASM(BODY)                                                             \
+  asm volatile(BHSR_DXS_PRE BODY BHSR_DXS_POST                                         \
+               : "=r"(ok1), "=r"(ok2)                                                  \
+               : "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(idesc),   \
+                 "r"(acc_first), "r"(bar1), "r"(par1), "r"(bar2), "r"(par2), "n"(ASTEP16 - 2 * KST),   \
+                 "n"(2 * KST), "n"(BOFF16)                                             \
+               : "memory")
+#define BHSR_DXS_PICK_K(NMAC, S)                                                       \
+  if constexpr (KST == 4) BHSR_DXS_ASM(NMAC(BHSR_DXS_K4, S));                          \
+  else if constexpr (KST == 2) BHSR_DXS_ASM(NMAC(BHSR_DXS_K2, S));                     \
+  else BHSR_DXS_ASM(NMAC(BHSR_DXS_K1, S))
+#define BHSR_DXS_PICK_N(S)                                                             \
+  if constexpr (NB == 1) { BHSR_DXS_PICK_K(BHSR_DXS_N1, S); }                          \
+  else if constexpr (NB == 2) { BHSR_DXS_PICK_K(BHSR_DXS_N2, S); }                     \
+  else if constexpr (NB == 3) { BHSR_DXS_PICK_K(BHSR_DXS_N3, S); }                     \
+  else { BHSR_DXS_PICK_K(BHSR_DXS_N4, S); }
+
+template <int KST, int NB, int ASTEP16, bool DUAL, int BOFF16>
+__device__ __forceinline__ uint32_t issue_dxs(uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t d0, uint32_t d1,
+                                              uint32_t d2, uint32_t d3, uint32_t idesc, uint32_t acc_first,
+                                              uint32_t bar1, uint32_t par1, uint32_t bar2, uint32_t par2) {
+  static_assert(KST == 1 || KST == 2 || KST == 4, "k-steps per chunk");
+  static_assert(NB >= 1 && NB <= 4, "blocks per issue block");
+  uint32_t ok1, ok2;
+  if constexpr (DUAL) { BHSR_DXS_PICK_N(BHSR_DXS_D) } else { BHSR_DXS_PICK_N(BHSR_DXS_S) }
+  return ok1 | (ok2 << 1);
+}
+
+template <bool EXACT, int MB, int CH, bool WRES>
+__global__ void __launch_bounds__(kDxThreads, 1)
+conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+                const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w, const ConvTcKernelParams p) {
+  static_assert(MB >= 2 && MB <= 4, "blocks per tile");
+  static_assert(CH == 32 || CH == 64, "channels per chunk");
+  constexpr int PACK_CH = EXACT ? 32 : 64;         // channels per chunk of the packed weight blob
+  static_assert(PACK_CH % CH == 0, "chunk must divide the packed chunk");
+  constexpr int SUB = PACK_CH / CH;
+  constexpr int RB = CH * 2;
+  constexpr int RB16 = RB / 16;
+  constexpr int KSTEPS = CH / 16;
+  constexpr int NPART = EXACT ? 2 : 1;
+  constexpr int COLS = 96;                          // TMEM columns per block (one accumulator)
+  constexpr int NSLOT = kDxsSlots;
+  constexpr int W_SLAB = 96 * NPART * RB;           // one (chunk, dy): [part][dx][cout] rows
+  constexpr int W_LO16 = (96 * RB) >> 4;            // W_hi rows -> W_lo rows
+  constexpr int ROWS = DxsRows<MB>::value;
+  constexpr int A_TX = ROWS * kPitch * RB;
+  constexpr int TILE = (A_TX + 1023) / 1024 * 1024;
+  constexpr int S_OUT = kDxBlk * MB;
+  constexpr uint32_t IDESC = make_idesc_f16(96, 128);
+  constexpr uint32_t ASTEP = kDxBlk * RB16;         // descriptor units between consecutive blocks
+  static_assert(NSLOT * COLS <= 512, "TMEM overflow");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_base = smem_u32(smem);
+  const int NS = p.astages;
+  const uint32_t ah_base = smem_base;
+  const uint32_t al_base = ah_base + NS * TILE;
+  const uint32_t w_base = ah_base + NPART * NS * TILE;
+  uint8_t* tail = smem + NPART * NS * TILE + p.wslots * W_SLAB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  auto bar = [&](int i) { return smem_u32(bars + i); };
+  constexpr int B_HFULL = 0, B_HEMPTY = kMaxAStages, B_LFULL = 2 * kMaxAStages, B_LEMPTY = 3 * kMaxAStages,
+                B_TFULL = 4 * kMaxAStages, B_TEMPTY = B_TFULL + NSLOT, B_WFULL = B_TEMPTY + NSLOT;
+  const int B_WEMPTY = B_WFULL + kMaxWSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kDxsBars);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_scale = s_bias + 64;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_scale + 64);
+  float* s_xchg = reinterpret_cast<float*>(s_stage + kDxStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+#ifdef BHSR_TIMING
+  const long long t_entry = clock64();
+#endif
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4 * kMaxAStages; ++i) mbar_init(bar(i), 1);
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(bar(B_TFULL + i), 1);
+      mbar_init(bar(B_TEMPTY + i), 128);
+    }
+    for (int i = 0; i < p.wslots; ++i) {
+      mbar_init(bar(B_WFULL + i), 1);
+      mbar_init(bar(B_WEMPTY + i), 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_a_hi);
+    if (EXACT) tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (threadIdx.x < 32) {
+    s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    s_scale[threadIdx.x] = (p.scale ? p.scale[threadIdx.x] : 1.f) * p.out_mul;   // 2^-8 of the weight pre-scale
+  }
+  if (warp == kDxWarpMma) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (p.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp != kDxWarpProdW) asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+
+  const int grid = static_cast<int>(gridDim.x);
+  const int flat_end = p.h * kPitch;                 // flat outputs of a strip
+  // blocks of tile-in-strip t that hold at least one valid output
+  auto blocks_of = [&](int t) {
+    const int n = (flat_end - t * S_OUT + kDxBlk - 1) / kDxBlk;
+    return n < MB ? n : MB;
+  };
+
+  if (warp == kDxWarpProdA) {
+    // ------------------------------------------------ activation producer (hi ring, lo ring)
+    if (lane == 0) {
+      int sh = 0, ph_h = 1, sl = 0, ph_l = 1;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
+        const int t = tile % p.tiles_per_strip;
+        const int sn = tile / p.tiles_per_strip;
+        const int s = sn % p.n_strips;
+        const int n = sn / p.n_strips;
+        const int r0 = (t * S_OUT + kPitch - 1) / kPitch - 2;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          mbar_wait(bar(B_HEMPTY + sh), ph_h);
+          mbar_expect_tx(bar(B_HFULL + sh), A_TX);
+          tma_load_4d(ah_base + sh * TILE, &tm_a_hi, bar(B_HFULL + sh), p.in_choff + c * CH, s * kStrip - 1, r0, n);
+          if (++sh == NS) { sh = 0; ph_h ^= 1; }
+          if (EXACT) {
+            mbar_wait(bar(B_LEMPTY + sl), ph_l);
+            mbar_expect_tx(bar(B_LFULL + sl), A_TX);
+            tma_load_4d(al_base + sl * TILE, &tm_a_lo, bar(B_LFULL + sl), p.in_choff + c * CH, s * kStrip - 1, r0, n);
+            if (++sl == NS) { sl = 0; ph_l ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kDxWarpProdW) {
+    // ------------------------------------------------ weight producer (one slab per (chunk, dy))
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
+        for (int c = 0; c < p.n_chunks; ++c) {
+#pragma unroll 1
+          for (int g = 0; g < 3; ++g, ++it) {
+            const int ws = WRES ? c * 3 + g : static_cast<int>(it % p.wslots);
+            if (!WRES) mbar_wait(bar(B_WEMPTY + ws), ((it / p.wslots) & 1) ^ 1);
+            mbar_expect_tx(bar(B_WFULL + ws), W_SLAB);
+            tma_load_5d(w_base + ws * W_SLAB, &tm_w, bar(B_WFULL + ws), (c % SUB) * CH, 0, 0, 0, (c / SUB) * 3 + g);
+          }
+        }
+        if (WRES) break;
+      }
+    }
+  } else if (warp == kDxWarpMma) {
+    // ------------------------------------------------ MMA issuer
+    const uint64_t desc0 = make_kmajor_desc<RB>(0);
+    const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+    const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
+#ifdef BHSR_TIMING
+    long long t_tempty = 0, t_afull = 0, t_wfull = 0, t_total = clock64(), tq = 0, t_issue = 0, ti = 0;
+    const bool dbg = p.dbg != nullptr;
+    const long long t_loop0 = t_total;
+    int n_tiles = 0;
+#else
+    long long t_tempty = 0, t_afull = 0, t_wfull = 0, tq = 0, t_issue = 0, ti = 0;
+    constexpr bool dbg = false;
+#endif
+    uint32_t ok_h = 0, ok_l = 0, ok_w = 0;
+    const int n_chunks = p.n_chunks, cin = p.cin, wslots = p.wslots;
+    int sh = 0, h_ph = 0, sl = 0, l_ph = 0;
+    int ws_r = 0, w_ph = 0;
+    uint32_t blk = 0;                                   // running block index (slot = blk % NSLOT)
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
+      const int t = tile % p.tiles_per_strip;
+      const int f0 = t * S_OUT;
+      const int r0 = (f0 + kPitch - 1) / kPitch - 2;
+      const int base_flat = f0 - r0 * kPitch;
+      const int nblk = blocks_of(t);
+      const bool full = nblk == MB;
+      const bool more_tiles = tile + grid < p.total_tiles;
+      uint32_t dacc[4], tbar_e[4], tbar_f[4], tpar[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t bi = blk + b;
+        const uint32_t slot = bi % NSLOT;
+        dacc[b] = tmem_base + slot * COLS;
+        tbar_e[b] = bar(B_TEMPTY + slot);
+        tbar_f[b] = bar(B_TFULL + slot);
+        tpar[b] = (bi / NSLOT) & 1;
+      }
+      for (int c = 0; c < n_chunks; ++c) {
+        int wsl[3];
+        uint32_t nbar[3], npar[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          if (WRES) {
+            wsl[g] = c * 3 + g;
+            if (first_tile) mbar_wait(bar(B_WFULL + wsl[g]), 0);
+          } else {
+            wsl[g] = ws_r;
+            if (!((ok_w >> g) & 1u)) {
+              if (dbg) tq = clock64();
+              mbar_wait(bar(B_WFULL + ws_r), w_ph);
+              if (dbg) t_wfull += clock64() - tq;
+            }
+            if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }
+          }
+        }
+        ok_w = 0;
+        {
+          int r = ws_r, ph = w_ph;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            nbar[g] = bar(B_WFULL + (WRES ? wsl[g] : r));
+            npar[g] = WRES ? 0u : static_cast<uint32_t>(ph);
+            if (++r == wslots) { r = 0; ph ^= 1; }
+          }
+        }
+        if (!ok_h) {
+          if (dbg) tq = clock64();
+          mbar_wait(bar(B_HFULL + sh), h_ph);
+          if (dbg) t_afull += clock64() - tq;
+        }
+        ok_h = 0;
+        tc_fence_after();
+        int sh_next = sh + 1, h_ph_next = h_ph;
+        if (sh_next == NS) { sh_next = 0; h_ph_next ^= 1; }
+        const uint32_t bar_h_next = bar(B_HFULL + sh_next);
+        const uint32_t bar_l_cur = bar(B_LFULL + sl);
+        const uint32_t row0 = (base_flat - kPitch) * RB16;
+        const uint32_t a_h0 = desc_lo0 + (((ah_base + sh * TILE) >> 4) & 0x3FFF) + row0;
+        const uint32_t a_l0 = desc_lo0 + (((al_base + sl * TILE) >> 4) & 0x3FFF) + row0;
+        const uint32_t b0 = desc_lo0 + ((w_base >> 4) & 0x3FFF);
+        const int rem = cin - c * CH;
+        const bool first_chunk = (c == 0);
+        const bool last_chunk = (c + 1 == n_chunks);
+        auto issue_chunk = [&](auto ksteps_tag) {
+          constexpr int KST = decltype(ksteps_tag)::value;
+          uint32_t okbits = 0;
+          // ================= phase H: hi activations x W_hi (exact: and x W_lo), fast: the only phase
+          // probe 1 = what the issuer waits for next (exact: this chunk's lo stage; fast: next hi stage),
+          // probe 2 = (fast) next chunk's weight slab of the same window row
+#ifdef BHSR_TIMING
+          const bool probes = p.nomma != 3;     // diagnostic 3: no barrier probes in the issue blocks
+#else
+          constexpr bool probes = true;
+#endif
+          const uint32_t hb1 = !probes ? 0u : EXACT ? bar_l_cur : bar_h_next;
+          const uint32_t hp1 = static_cast<uint32_t>(EXACT ? l_ph : h_ph_next);
+          const bool h_is_last = !EXACT && last_chunk;
+          if (first_chunk || h_is_last || !full) {
+            // block-major: accumulator hand-over (wait for the drained slot / publish as soon as done)
+#pragma unroll
+            for (int b = 0; b < MB; ++b) {
+              if (b >= nblk) break;
+              if (first_chunk) {
+                if (dbg) tq = clock64();
+                mbar_wait(tbar_e[b], tpar[b] ^ 1);
+                if (dbg) t_tempty += clock64() - tq;
+                tc_fence_after();
+              }
+              if (dbg) ti = clock64();
+              if (elect_one()) {
+#ifdef BHSR_TIMING
+                if (p.nomma != 1)
+#endif
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                  const uint32_t r = issue_dxs<KST, 1, 0, EXACT, W_LO16>(
+                      a_h0 + (g * kPitch + b * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, dacc[b], 0, 0, 0,
+                      IDESC, (c > 0 || g > 0) ? 1u : 0u, hb1, hp1, EXACT ? hb1 : nbar[g], EXACT ? hp1 : npar[g]);
+                  if (b == nblk - 1) okbits |= (r & 1u) | ((r >> 1) << (1 + g));
+                }
+                if (h_is_last) umma_commit(tbar_f[b]);
+              }
+              __syncwarp();
+              if (dbg) t_issue += clock64() - ti;
+            }
+          } else {
+            if (dbg) ti = clock64();
+            if (elect_one()) {
+#ifdef BHSR_TIMING
+              if (p.nomma != 1)
+#endif
+#pragma unroll
+              for (int g = 0; g < 3; ++g) {
+                const uint32_t r = issue_dxs<KST, MB, ASTEP, EXACT, W_LO16>(
+                    a_h0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, dacc[0], dacc[1], dacc[2], dacc[3],
+                    IDESC, 1u, hb1, hp1, EXACT ? hb1 : nbar[g], EXACT ? hp1 : npar[g]);
+                okbits |= (r & 1u) | ((r >> 1) << (1 + g));
+              }
+            }
+            __syncwarp();
+            if (dbg) t_issue += clock64() - ti;
+          }
+          if (dbg) tq = clock64();
+          if (elect_one()) {
+            umma_commit(bar(B_HEMPTY + sh));
+            if (!EXACT && !WRES) {
+#pragma unroll
+              for (int g = 0; g < 3; ++g) umma_commit(bar(B_WEMPTY + wsl[g]));
+            }
+          }
+          __syncwarp();
+          okbits = __reduce_or_sync(0xffffffffu, okbits);
+          if (dbg) t_wfull += clock64() - tq;   // timing builds: commit + probe-result reduction ("post" cycles)
+          if (EXACT) {
+            ok_l = okbits & 1u;
+          } else {
+            if (!last_chunk || more_tiles) ok_h = okbits & 1u;
+            if (!WRES) ok_w = (okbits >> 1) & 7u;
+          }
+          if (EXACT) {
+            // ================= phase L: lo activations x W_hi into the same accumulators
+            if (!ok_l) {
+              if (dbg) tq = clock64();
+              mbar_wait(bar(B_LFULL + sl), l_ph);
+              if (dbg) t_afull += clock64() - tq;
+            }
+            ok_l = 0;
+            tc_fence_after();
+            okbits = 0;
+            if (last_chunk || !full) {
+#pragma unroll
+              for (int b = 0; b < MB; ++b) {
+                if (b >= nblk) break;
+                if (dbg) ti = clock64();
+                if (elect_one()) {
+#ifdef BHSR_TIMING
+                  if (p.nomma != 1)
+#endif
+#pragma unroll
+                  for (int g = 0; g < 3; ++g) {
+                    const uint32_t r = issue_dxs<KST, 1, 0, false, 0>(
+                        a_l0 + (g * kPitch + b * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, dacc[b], 0, 0, 0,
+                        IDESC, 1u, probes ? bar_h_next : 0u, static_cast<uint32_t>(h_ph_next), nbar[g], npar[g]);
+                    if (b == nblk - 1) okbits |= (r & 1u) | ((r >> 1) << (1 + g));
+                  }
+                  if (last_chunk) umma_commit(tbar_f[b]);
+                }
+                __syncwarp();
+                if (dbg) t_issue += clock64() - ti;
+              }
+            } else {
+              if (dbg) ti = clock64();
+              if (elect_one()) {
+#ifdef BHSR_TIMING
+                if (p.nomma != 1)
+#endif
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                  const uint32_t r = issue_dxs<KST, MB, ASTEP, false, 0>(
+                      a_l0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4), desc_hi, dacc[0], dacc[1], dacc[2], dacc[3],
+                      IDESC, 1u, probes ? bar_h_next : 0u, static_cast<uint32_t>(h_ph_next), nbar[g], npar[g]);
+                  okbits |= (r & 1u) | ((r >> 1) << (1 + g));
+                }
+              }
+              __syncwarp();
+              if (dbg) t_issue += clock64() - ti;
+            }
+            if (elect_one()) {
+              if (!WRES) {
+#pragma unroll
+                for (int g = 0; g < 3; ++g) umma_commit(bar(B_WEMPTY + wsl[g]));
+              }
+              umma_commit(bar(B_LEMPTY + sl));
+            }
+            __syncwarp();
+            okbits = __reduce_or_sync(0xffffffffu, okbits);
+            if (!last_chunk || more_tiles) ok_h = okbits & 1u;
+            if (!WRES) ok_w = (okbits >> 1) & 7u;
+          }
+        };
+        if (rem >= CH) issue_chunk(std::integral_constant<int, KSTEPS>{});
+        else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
+        sh = sh_next;
+        h_ph = h_ph_next;
+        if (EXACT) {
+          if (++sl == NS) { sl = 0; l_ph ^= 1; }
+        }
+      }
+      blk += nblk;
+      first_tile = false;
+#ifdef BHSR_TIMING
+      ++n_tiles;
+#endif
+    }
+#ifdef BHSR_TIMING
+    if (dbg && lane == 0) {
+      long long* o = p.dbg + blockIdx.x * 8;
+      o[0] = clock64() - t_total; o[1] = t_tempty; o[2] = t_afull; o[3] = t_wfull; o[4] = n_tiles;
+      o[5] = t_issue;   // cycles inside the issue regions (probe_conv_tc.py prints it as prologue_cycles)
+      (void)t_loop0;
+    }
+#endif
+    (void)t_tempty; (void)t_afull; (void)t_wfull; (void)tq; (void)t_issue; (void)ti;
+  } else {
+    // ------------------------------------------------ epilogue (two groups of four warps)
+    const int grp = warp >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t blk = 0;
+    uint32_t xpar = 0;
+#ifdef BHSR_TIMING
+    long long t_epi_wait = 0;
+#endif
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
+      const int t = tile % p.tiles_per_strip;
+      const int sn = tile / p.tiles_per_strip;
+      const int s = sn % p.n_strips;
+      const int n = sn / p.n_strips;
+      const int nblk = blocks_of(t);
+#pragma unroll 1
+      for (int mb = 0; mb < nblk; ++mb) {
+        const uint32_t bi = blk + mb;
+        if (static_cast<int>(bi & 1u) != grp) continue;
+        const uint32_t slot = bi % NSLOT;
+#ifdef BHSR_TIMING
+        const long long tw0 = clock64();
+#endif
+        mbar_wait(bar(B_TFULL + slot), (bi / NSLOT) & 1);
+#ifdef BHSR_TIMING
+        t_epi_wait += clock64() - tw0;
+#endif
+        tc_fence_after();
+#ifdef BHSR_TIMING
+        if (p.nomma == 9) {   // diagnostic: the accumulator is released without being read (no tcgen05.ld at all)
+          tc_fence_before();
+          mbar_arrive(bar(B_TEMPTY + slot));
+          continue;
+        }
+#endif
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * COLS;
+        float v0[32], v1[32], v2[32];
+        {
+          uint32_t r0_[32], r1_[32], r2_[32];
+          tmem_ld_32x32(t_row, r0_);
+          tmem_ld_32x32(t_row + 32, r1_);
+          tmem_ld_32x32(t_row + 64, r2_);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            v0[jj] = __uint_as_float(r0_[jj]);
+            v1[jj] = __uint_as_float(r1_[jj]);
+            v2[jj] = __uint_as_float(r2_[jj]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar(B_TEMPTY + slot));
+#ifdef BHSR_TIMING
+        if (p.nomma == 4) continue;
+#endif
+        // out[row] = g0[row-1] + g1[row] + g2[row+1]: lane shifts inside the warp, smem across warps
+        float* xb = s_xchg + ((grp * 2 + xpar) * 4) * 64;
+        if (lane == 31) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4)
+            *reinterpret_cast<float4*>(xb + q * 64 + jj) = make_float4(v0[jj], v0[jj + 1], v0[jj + 2], v0[jj + 3]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4)
+            *reinterpret_cast<float4*>(xb + q * 64 + 32 + jj) = make_float4(v2[jj], v2[jj + 1], v2[jj + 2], v2[jj + 3]);
+        }
+        if (grp == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
+        xpar ^= 1;
+        float v[32];
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float up = __shfl_up_sync(0xffffffffu, v0[jj], 1);
+          const float dn = __shfl_down_sync(0xffffffffu, v2[jj], 1);
+          v0[jj] = up;
+          v2[jj] = dn;
+        }
+        if (lane == 0 && q > 0) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xb + (q - 1) * 64 + jj);
+            v0[jj] = x.x; v0[jj + 1] = x.y; v0[jj + 2] = x.z; v0[jj + 3] = x.w;
+          }
+        }
+        if (lane == 31 && q < 3) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xb + (q + 1) * 64 + 32 + jj);
+            v2[jj] = x.x; v2[jj + 1] = x.y; v2[jj + 2] = x.z; v2[jj + 3] = x.w;
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] = (v0[jj] + v1[jj]) + v2[jj];
+
+        const int f = (t * MB + mb) * kDxBlk - 1 + row;
+        const int py = f / kPitch;
+        const int pc = f - py * kPitch;
+        const int px = s * kStrip + pc;
+        const bool valid = (row >= 1) && (row <= kDxBlk) && (pc < kStrip) && (py < p.h) && (px < p.w);
+        const size_t in_pix = (static_cast<size_t>(n) * p.h + py) * p.w + px;
+        const int oy = py * p.out_scale + p.out_oy;
+        const int ox = px * p.out_scale + p.out_ox;
+        const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
+        finish_planes32_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
+      }
+      blk += nblk;
+    }
+#ifdef BHSR_TIMING
+    if (p.dbg != nullptr && threadIdx.x == 0) {
+      long long* o = p.dbg + blockIdx.x * 8;
+      o[6] = t_epi_wait;
+      o[7] = clock64() - t_entry;
+    }
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kDxWarpMma) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace bhsr

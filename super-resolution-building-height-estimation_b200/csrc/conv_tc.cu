@@ -40,6 +40,7 @@
 #include "conv_common.cuh"
 #include "conv_tap.cuh"
 #include "conv_dx.cuh"
+#include "conv_dxs.cuh"
 
 namespace bhsr {
 
@@ -223,18 +224,19 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
 // 5-D view of the packed weight blob [chunk][tap = dy*3+dx][part][32 couts][CH] that lands one
 // (chunk, dy) slab in shared memory as [part][dx][cout][CH] rows (see conv_dx_kernel).
 static int make_weight_map_dx(CUtensorMap* tm, const void* base, int n_chunks, int nparts, int ch,
-                              int box_couts = 32, int box_parts = -1) {
+                              int box_couts = 32, int box_parts = -1, int box_ch = -1) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return BHSR_ECUDA;
   const cuuint64_t rb = (cuuint64_t)ch * 2;
   const cuuint64_t tap_bytes = (cuuint64_t)nparts * 32 * rb;
   cuuint64_t dims[5] = {(cuuint64_t)ch, 32, 3, (cuuint64_t)nparts, (cuuint64_t)n_chunks * 3};
   cuuint64_t strides[4] = {rb, tap_bytes, 32 * rb, 3 * tap_bytes};
-  cuuint32_t box[5] = {(cuuint32_t)ch, (cuuint32_t)box_couts, 3, (cuuint32_t)(box_parts < 0 ? nparts : box_parts), 1};
+  if (box_ch < 0) box_ch = ch;   // conv_dxs: 32-channel boxes out of the fast blob's 64-channel chunks
+  cuuint32_t box[5] = {(cuuint32_t)box_ch, (cuuint32_t)box_couts, 3, (cuuint32_t)(box_parts < 0 ? nparts : box_parts), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   box_ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(w, dx) -> %d", (int)r);
   return 0;
@@ -320,6 +322,89 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   if (p.w_resident) return launch_dx_kernel<EXACT, MB, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
   return launch_dx_kernel<EXACT, MB, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+}
+
+// Single-accumulator dx-in-N launch (conv_dxs.cuh): MB = 2..4 blocks per tile, CH channels per chunk.
+template <bool EXACT, int MB, int CH, bool WRES>
+static int launch_dxs_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
+                             const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
+  auto kern = conv_dxs_kernel<EXACT, MB, CH, WRES>;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
+    BHSR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kDxThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  BHSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));
+  return 0;
+}
+
+template <bool EXACT, int MB, int CH>
+static int launch_dxs(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream) {
+  constexpr int PACK_CH = EXACT ? 32 : 64;
+  constexpr int NPART = EXACT ? 2 : 1;
+  constexpr int RB = CH * 2;
+  constexpr int ROWS = DxsRows<MB>::value;
+  constexpr int TILE = (ROWS * kPitch * RB + 1023) / 1024 * 1024;
+  constexpr int A_STAGE = TILE * NPART;
+  constexpr int W_SLAB = 96 * NPART * RB;
+  constexpr int S_OUT = kDxBlk * MB;
+  p.n_chunks = (d.cin + CH - 1) / CH;
+  p.tiles_per_strip = (d.h * kPitch + S_OUT - 1) / S_OUT;
+  p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;
+  p.split_round = -1;
+  const int slabs = p.n_chunks * 3;
+  auto slots_for = [&](int ns) {
+    const int avail = kSmemLimit - 1024 - ns * A_STAGE - kDxsTailBytes;
+    return avail < 0 ? 0 : avail / W_SLAB;
+  };
+  int astages = 2, wslots = slots_for(2);
+  bool picked = false;
+  for (int ns = kMaxAStages; ns >= 2 && !picked; --ns)   // whole layer resident, deepest ring
+    if (slots_for(ns) >= slabs) { astages = ns; wslots = slots_for(ns); picked = true; }
+  for (int ns = kMaxAStages; ns >= 2 && !picked; --ns)   // else a weight ring of >= 6 slabs (two chunks)
+    if (slots_for(ns) >= 6) { astages = ns; wslots = slots_for(ns); picked = true; }
+  {
+    static const char* force_ns = getenv("BHSR_ASTAGES");
+    if (force_ns && force_ns[0] >= '2' && force_ns[0] <= '4' && slots_for(force_ns[0] - '0') >= 3) {
+      astages = force_ns[0] - '0';
+      wslots = slots_for(astages);
+    }
+  }
+  if (wslots > kMaxWSlots) wslots = kMaxWSlots;
+  if (wslots < 3) return set_error(BHSR_EINVAL, "conv_tc(dxs): no room for the weight ring (MB %d, CH %d)", MB, CH);
+  p.w_resident = slabs <= wslots ? 1 : 0;
+  {
+    static const char* force = getenv("BHSR_DEBUG_FORCE_STREAM");
+    if (force && force[0] == '1') { p.w_resident = 0; if (wslots > 6) wslots = 6; }
+  }
+  if (p.w_resident) wslots = slabs;
+  p.wslots = wslots;
+  p.astages = astages;
+  const int smem_bytes = 1024 + astages * A_STAGE + wslots * W_SLAB + kDxsTailBytes;
+
+  CUtensorMap tm_hi, tm_lo, tm_w;
+  int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, ROWS, CH);
+  if (rc) return rc;
+  rc = make_act_map(&tm_lo, EXACT ? d.in_lo : d.in_hi, d.nb, d.h, d.w, d.in_ctot, ROWS, CH);
+  if (rc) return rc;
+  rc = make_weight_map_dx(&tm_w, d.w_packed, (d.cin + PACK_CH - 1) / PACK_CH, NPART, PACK_CH, 32, -1, CH);
+  if (rc) return rc;
+  int sms = device_sm_count();
+  if (sms <= 0) return set_error(BHSR_ENOGPU, "no CUDA device");
+  int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
+  static const char* no_pdl = getenv("BHSR_NO_PDL");
+  p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
+  if (p.w_resident) return launch_dxs_kernel<EXACT, MB, CH, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  return launch_dxs_kernel<EXACT, MB, CH, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
 }
 
 // CTA-pair launch for the 64-output exact 3x3 layers (even batch, plane or NCHW output).
@@ -503,7 +588,9 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
 
   int mb = d.mblocks;
   if (mb == 0) mb = 2;
-  BHSR_REQUIRE(mb == 1 || mb == 2, "conv_tc: mblocks must be 1 or 2");
+  BHSR_REQUIRE(mb >= 1 && mb <= 4, "conv_tc: mblocks must be 1..4");
+  const int mb_tall = mb;        // 3 / 4: tall tiles of the single-accumulator dx kernel (32-output 3x3 plane layers)
+  if (mb > 2) mb = 2;            // every other kernel: two blocks per tile
 
   ConvTcKernelParams p{};
   p.split_round = -1;
@@ -537,6 +624,8 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   p.res2_lo = static_cast<const __half*>(d.res2_lo);
   p.res2_ctot = d.res2_ctot; p.res2_choff = d.res2_choff;
   p.desc_mode = d.desc_mode;
+  p.lo_mul = 2048.f;
+  p.out_mul = 1.f;
   {
     static const char* want = getenv("BHSR_DEBUG_TIMING");  // debug only: MMA-warp wait cycles
     if (want && want[0] == '1') {
@@ -552,6 +641,15 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
     static const char* dxn = getenv("BHSR_DXN");
     const bool use_dx = !(dxn && dxn[0] == '0') && !(d.desc_mode & 0x100);  // desc_mode bit 8: per-tap kernel
     if (use_dx && d.cout == 32 && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2)) {
+      // tall tiles on the single-accumulator kernel (fast numerics; exact needs plane format 1)
+      static const char* dxs = getenv("BHSR_DXS_MB");
+      int tall = mb_tall > 2 ? mb_tall : 0;
+      if (dxs && dxs[0] >= '2' && dxs[0] <= '4') tall = dxs[0] - '0';
+      if (!exact && tall >= 2 && d.cin % 32 == 0 && d.in_ctot % 32 == 0 && d.in_choff % 32 == 0) {
+        if (tall == 4) return launch_dxs<false, 4, 32>(d, p, stream);
+        if (tall == 3) return launch_dxs<false, 3, 32>(d, p, stream);
+        return launch_dxs<false, 2, 32>(d, p, stream);
+      }
       if (exact && mb == 2 && d.nb % 2 == 0 && d.cin % 32 == 0) {
         // CTA pairs for the dx kernel are correct but not faster (these layers are bound by their OWN
         // activation supply, and the leader waits for the slower of two loads:

@@ -486,6 +486,159 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ g_out, int g_ctot,
   }
 }
 
+// ---------------------------------------------------------------- float4 variants (hw % 4 == 0, 16-byte aligned views)
+// The scalar kernels above pay two 64-bit divisions per element; here a block row owns one (image, channel) plane
+// (blockIdx.y = n*c + ch), a thread moves four independent float4 per tensor, and the per-channel constants are
+// loaded once: the three BasicBlock element-wise passes run at the HBM rate instead of at the integer-divide rate.
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+
+constexpr int kEwUnroll = 4;
+
+__global__ void __launch_bounds__(256)
+affine_add_relu_v4_kernel(const float* __restrict__ a, const float* __restrict__ sa, const float* __restrict__ ta,
+                          const float* __restrict__ b, int b_ctot, int b_choff, const float* __restrict__ sb,
+                          const float* __restrict__ tb, int c, int hw4, float* __restrict__ out, int o_ctot,
+                          int o_choff) {
+  const int n = blockIdx.y / c, ch = blockIdx.y - n * c;
+  const size_t hw = static_cast<size_t>(hw4) * 4;
+  const float* ap = a + (static_cast<size_t>(n) * c + ch) * hw;
+  const float* bp = b + (static_cast<size_t>(n) * b_ctot + b_choff + ch) * hw;
+  float* op = out + (static_cast<size_t>(n) * o_ctot + o_choff + ch) * hw;
+  const float s_a = sa[ch], t_a = ta[ch];
+  const float s_b = sb ? sb[ch] : 1.f, t_b = sb ? tb[ch] : 0.f;
+  for (int v0 = (blockIdx.x * kEwUnroll) * blockDim.x + threadIdx.x; v0 < hw4; v0 += gridDim.x * kEwUnroll * blockDim.x) {
+    float4 av[kEwUnroll], bv[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const int v = v0 + u * blockDim.x;
+      if (v < hw4) { av[u] = ld4s(ap + 4 * static_cast<size_t>(v)); bv[u] = ld4s(bp + 4 * static_cast<size_t>(v)); }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const int v = v0 + u * blockDim.x;
+      if (v >= hw4) break;
+      float4 r;
+      r.x = fmaxf(fmaf(av[u].x, s_a, t_a) + fmaf(bv[u].x, s_b, t_b), 0.f);
+      r.y = fmaxf(fmaf(av[u].y, s_a, t_a) + fmaf(bv[u].y, s_b, t_b), 0.f);
+      r.z = fmaxf(fmaf(av[u].z, s_a, t_a) + fmaf(bv[u].z, s_b, t_b), 0.f);
+      r.w = fmaxf(fmaf(av[u].w, s_a, t_a) + fmaf(bv[u].w, s_b, t_b), 0.f);
+      *reinterpret_cast<float4*>(op + 4 * static_cast<size_t>(v)) = r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_v4_kernel(const float* __restrict__ g_out, int g_ctot, int g_choff, const float* __restrict__ out,
+                        int o_ctot, int o_choff, const float* __restrict__ a, const float* __restrict__ sa,
+                        const float* __restrict__ ta, const float* __restrict__ b, int b_ctot, int b_choff, int nb,
+                        int c, int hw4, double* sums) {
+  const int ch = blockIdx.y;
+  const size_t hw = static_cast<size_t>(hw4) * 4;
+  const float s_a = out ? 0.f : sa[ch], t_a = out ? 0.f : ta[ch];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const int total = nb * hw4;                         // float4 groups of this channel (< 2^31 for any real batch)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / hw4, v = i - n * hw4;
+    const float4 av = ld4(a + (static_cast<size_t>(n) * c + ch) * hw + 4 * static_cast<size_t>(v));
+    float4 g = ld4(g_out + (static_cast<size_t>(n) * g_ctot + g_choff + ch) * hw + 4 * static_cast<size_t>(v));
+    float4 m;
+    if (out) m = ld4(out + (static_cast<size_t>(n) * o_ctot + o_choff + ch) * hw + 4 * static_cast<size_t>(v));
+    else m = make_float4(fmaf(av.x, s_a, t_a), fmaf(av.y, s_a, t_a), fmaf(av.z, s_a, t_a), fmaf(av.w, s_a, t_a));
+    if (!(m.x > 0.f)) g.x = 0.f;
+    if (!(m.y > 0.f)) g.y = 0.f;
+    if (!(m.z > 0.f)) g.z = 0.f;
+    if (!(m.w > 0.f)) g.w = 0.f;
+    s0 += (g.x + g.y) + (g.z + g.w);
+    s1 = fmaf(g.x, av.x, fmaf(g.y, av.y, fmaf(g.z, av.z, fmaf(g.w, av.w, s1))));
+    if (b) {
+      const float4 bv = ld4(b + (static_cast<size_t>(n) * b_ctot + b_choff + ch) * hw + 4 * static_cast<size_t>(v));
+      s2 = fmaf(g.x, bv.x, fmaf(g.y, bv.y, fmaf(g.z, bv.z, fmaf(g.w, bv.w, s2))));
+    }
+  }
+  __shared__ float red[3][32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = s0; red[1][wid] = s1; red[2][wid] = s2; }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = blockDim.x >> 5;
+    double d0 = lane < nw ? red[0][lane] : 0.f, d1 = lane < nw ? red[1][lane] : 0.f, d2 = lane < nw ? red[2][lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    if (lane == 0) {
+      atomicAdd(sums + ch, d0);
+      atomicAdd(sums + c + ch, d1);
+      atomicAdd(sums + 2 * c + ch, d2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v4_kernel(const float* __restrict__ g_out, int g_ctot, int g_choff, const float* __restrict__ out,
+                       int o_ctot, int o_choff, const float* __restrict__ a, const float* __restrict__ sa,
+                       const float* __restrict__ ta, const float* __restrict__ k1, const float* __restrict__ k2,
+                       const float* __restrict__ k3, float* __restrict__ g_a, const float* __restrict__ b, int b_ctot,
+                       int b_choff, const float* __restrict__ kb1, const float* __restrict__ kb2,
+                       const float* __restrict__ kb3, float* __restrict__ g_b, int gb_ctot, int gb_choff,
+                       int gb_accumulate, int c, int hw4) {
+  const int n = blockIdx.y / c, ch = blockIdx.y - n * c;
+  const size_t hw = static_cast<size_t>(hw4) * 4;
+  const float* ap = a + (static_cast<size_t>(n) * c + ch) * hw;
+  const float* gp = g_out + (static_cast<size_t>(n) * g_ctot + g_choff + ch) * hw;
+  const float* op = out ? out + (static_cast<size_t>(n) * o_ctot + o_choff + ch) * hw : nullptr;
+  const float* bp = (g_b && kb1) ? b + (static_cast<size_t>(n) * b_ctot + b_choff + ch) * hw : nullptr;
+  float* gap = g_a + (static_cast<size_t>(n) * c + ch) * hw;
+  float* gbp = g_b ? g_b + (static_cast<size_t>(n) * gb_ctot + gb_choff + ch) * hw : nullptr;
+  const float s_a = out ? 0.f : sa[ch], t_a = out ? 0.f : ta[ch];
+  const float c1 = k1[ch], c2 = k2[ch], c3 = k3[ch];
+  const float d1 = bp ? kb1[ch] : 1.f, d2 = bp ? kb2[ch] : 0.f, d3 = bp ? kb3[ch] : 0.f;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw4; v += gridDim.x * blockDim.x) {
+    const size_t e = 4 * static_cast<size_t>(v);
+    const float4 av = ld4(ap + e);
+    float4 g = ld4s(gp + e);
+    float4 m;
+    if (op) m = ld4(op + e);
+    else m = make_float4(fmaf(av.x, s_a, t_a), fmaf(av.y, s_a, t_a), fmaf(av.z, s_a, t_a), fmaf(av.w, s_a, t_a));
+    if (!(m.x > 0.f)) g.x = 0.f;
+    if (!(m.y > 0.f)) g.y = 0.f;
+    if (!(m.z > 0.f)) g.z = 0.f;
+    if (!(m.w > 0.f)) g.w = 0.f;
+    float4 r;
+    r.x = fmaf(c1, g.x, fmaf(c2, av.x, c3));
+    r.y = fmaf(c1, g.y, fmaf(c2, av.y, c3));
+    r.z = fmaf(c1, g.z, fmaf(c2, av.z, c3));
+    r.w = fmaf(c1, g.w, fmaf(c2, av.w, c3));
+    *reinterpret_cast<float4*>(gap + e) = r;
+    if (gbp) {
+      float4 gb = g;
+      if (bp) {
+        const float4 bv = ld4(bp + e);
+        gb.x = fmaf(d1, g.x, fmaf(d2, bv.x, d3));
+        gb.y = fmaf(d1, g.y, fmaf(d2, bv.y, d3));
+        gb.z = fmaf(d1, g.z, fmaf(d2, bv.z, d3));
+        gb.w = fmaf(d1, g.w, fmaf(d2, bv.w, d3));
+      }
+      if (gb_accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(gbp + e);
+        gb.x += old.x; gb.y += old.y; gb.z += old.z; gb.w += old.w;
+      }
+      *reinterpret_cast<float4*>(gbp + e) = gb;
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // 4x4 (scale x scale) block aggregation, aggregate_utils.py:29-59:
 //   out = sum(x) / (count(x > thr | x >= thr) + 1e-10)
 __global__ void aggregate_kernel(const float* __restrict__ x, int nimg, int h, int w, int step,
@@ -616,6 +769,14 @@ extern "C" int bhsr_affine_add_relu(const float* a, const float* sa, const float
                                     void* stream) {
   BHSR_REQUIRE(a && sa && ta && b && out, "affine_add_relu: null pointer");
   const size_t total = static_cast<size_t>(nb) * c * hw;
+  if (hw % 4 == 0 && aligned16(a) && aligned16(b) && aligned16(out) && static_cast<size_t>(nb) * c <= 65535) {
+    const int hw4 = hw / 4;
+    unsigned bx = static_cast<unsigned>((hw4 + 256 * kEwUnroll - 1) / (256 * kEwUnroll));
+    affine_add_relu_v4_kernel<<<dim3(bx, nb * c), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        a, sa, ta, b, b_ctot, b_choff, sb, tb, c, hw4, out, o_ctot, o_choff);
+    BHSR_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   affine_add_relu_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       a, sa, ta, b, b_ctot, b_choff, sb, tb, nb, c, hw, out, o_ctot, o_choff);
   BHSR_CUDA_CHECK(cudaGetLastError());
@@ -631,6 +792,19 @@ extern "C" int bhsr_bn_bwd_reduce(const float* g_out, int32_t g_ctot, int32_t g_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BHSR_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * c, st));
   const size_t per = static_cast<size_t>(nb) * hw;
+  if (hw % 4 == 0 && aligned16(a) && aligned16(g_out) && (!out || aligned16(out)) && (!b || aligned16(b)) &&
+      per / 4 < (1u << 30)) {
+    const int hw4 = hw / 4;
+    unsigned bxv = static_cast<unsigned>((per / 4 + 255) / 256);
+    int sms = device_sm_count();
+    const unsigned cap = static_cast<unsigned>(((sms > 0 ? sms : 148) * 8 + c - 1) / c);   // ~8 blocks per SM in total
+    if (bxv > cap) bxv = cap;
+    if (bxv < 1) bxv = 1;
+    bn_bwd_reduce_v4_kernel<<<dim3(bxv, c), 256, 0, st>>>(g_out, g_ctot, g_choff, out, o_ctot, o_choff, a, sa, ta, b,
+                                                          b_ctot, b_choff, nb, c, hw4, sums);
+    BHSR_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   unsigned bx = static_cast<unsigned>((per + 255) / 256);
   if (bx > 256) bx = 256;
   bn_bwd_reduce_kernel<<<dim3(bx, c), 256, 0, st>>>(g_out, g_ctot, g_choff, out, o_ctot, o_choff, a,
@@ -661,6 +835,17 @@ extern "C" int bhsr_bn_bwd_apply(const float* g_out, int32_t g_ctot, int32_t g_c
                                  void* stream) {
   BHSR_REQUIRE(g_out && a && k1 && k2 && k3 && g_a && (out || (sa && ta)), "bn_bwd_apply: null pointer");
   const size_t total = static_cast<size_t>(nb) * c * hw;
+  if (hw % 4 == 0 && aligned16(a) && aligned16(g_out) && aligned16(g_a) && (!out || aligned16(out)) &&
+      (!b || aligned16(b)) && (!g_b || aligned16(g_b)) && static_cast<size_t>(nb) * c <= 65535) {
+    const int hw4 = hw / 4;
+    unsigned bx = static_cast<unsigned>((hw4 + 255) / 256);
+    if (bx > 16) bx = 16;
+    bn_bwd_apply_v4_kernel<<<dim3(bx, nb * c), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        g_out, g_ctot, g_choff, out, o_ctot, o_choff, a, sa, ta, k1, k2, k3, g_a, b, b_ctot, b_choff, kb1, kb2, kb3,
+        g_b, gb_ctot, gb_choff, gb_accumulate, c, hw4);
+    BHSR_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   bn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       g_out, g_ctot, g_choff, out, o_ctot, o_choff, a, sa, ta, k1, k2, k3, g_a, b, b_ctot, b_choff,
       kb1, kb2, kb3, g_b, gb_ctot, gb_choff, gb_accumulate, nb, c, hw);

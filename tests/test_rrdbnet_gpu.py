@@ -110,6 +110,40 @@ def test_conv_dx_kernel_vs_per_tap_and_oracle(dev, numerics, rtol, atol, cin, h,
         assert_close(outs[2], outs[0], 1e-5, 1e-6, "dx pair vs dx single")
 
 
+@pytest.mark.parametrize("mb", [3, 4])
+@pytest.mark.parametrize("cin,h,w,nb,max_ctas", [(64, 64, 64, 3, 0), (160, 64, 64, 3, 5), (96, 23, 130, 2, 3),
+                                                  (32, 2, 64, 1, 0), (128, 64, 64, 5, 40)])
+def test_conv_dxs_tall_tiles_vs_two_block_kernel_and_oracle(dev, mb, cin, h, w, nb, max_ctas):
+    """conv_dxs_kernel (csrc/conv_dxs.cuh: one accumulator of 96 TMEM columns per block, 3 or 4 blocks per tile, five
+    rotating accumulator slots, ragged last tile of a strip) in fast numerics against the two-block dx kernel and the
+    oracle, with the scale / residual / ReLU epilogue, few CTAs, several strips and images shorter than one block."""
+    from bhsr import ops
+    from bhsr._lib import NUMERICS
+    rng = np.random.RandomState(cin + h + w + mb)
+    x = (rng.rand(nb, cin, h, w) * 2 - 0.5).astype(np.float32)
+    wt = (rng.standard_normal((32, cin, 3, 3)) * (0.5 / np.sqrt(cin * 9))).astype(np.float32)
+    b = (rng.standard_normal(32) * 0.1).astype(np.float32)
+    sc = (rng.rand(32) + 0.5).astype(np.float32)
+    r1 = rng.standard_normal((nb, 32, h, w)).astype(np.float32)
+    conv = R.conv2d(x, wt, None, padding=1, acc_dtype=np.float64)
+    ref = np.maximum((conv * sc[None, :, None, None] + b[None, :, None, None]) * 0.5 + r1, 0.0)
+    num = NUMERICS["fast"]
+    hi, lo = _planes(x, 192, dev)
+    rhi, rlo = _planes(r1, 32, dev)
+    wp = ops.pack_conv_weights(cuda(wt, dev), num)
+    outs = []
+    for m in (2, mb):
+        out_hi = torch.zeros((nb, h, w, 64), dtype=torch.float16, device=dev)
+        out_lo = torch.zeros_like(out_hi)
+        ops.conv_tc(hi, lo, 0, cin, wp, 32, cuda(b, dev), ops.PLAIN_TAPS, out_hi, out_lo, out_choff=32,
+                    scale=cuda(sc, dev), res1=(rhi, rlo, 0), alpha1=0.5, relu=True, numerics=num,
+                    mblocks=m, max_ctas=max_ctas)
+        assert float(out_hi[..., :32].abs().max()) == 0.0
+        outs.append(ops.planes_to_nchw(out_hi, out_lo, 32, 32).cpu().numpy())
+    assert_close(outs[1], ref, 2e-2, 2e-2, f"dxs kernel {cin}->32 fast mb{mb}")
+    assert_close(outs[1], outs[0], 1e-4, 1e-5, "dxs (tall tiles) vs two-block dx kernel")
+
+
 @pytest.mark.parametrize("cin,nb,h,w,max_ctas,nchw", [(192, 6, 64, 64, 80, False), (64, 2, 40, 130, 0, False),
                                                        (192, 4, 64, 64, 6, False), (64, 2, 128, 128, 0, True)])
 def test_conv_pair_kernel_vs_per_tap_and_oracle(dev, cin, nb, h, w, max_ctas, nchw):

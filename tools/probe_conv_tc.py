@@ -91,6 +91,15 @@ def run_case(name, desc_mode):
     cases["exact32_c160_mb2_nb4"] = dict(cin=160, exact=True, mb=2, nb=4)
     cases["exact32_c160_mb2_nb6s"] = dict(cin=160, exact=True, mb=2, nb=6, max_ctas=80)
     cases["exact32_c96_w130_nb2"] = dict(cin=96, exact=True, mb=2, nb=2, h=23, w=130)
+    for mbv in (3, 4):   # tall tiles of the single-accumulator dx kernel (conv_dxs.cuh)
+        cases[f"fast32_mb{mbv}"] = dict(mb=mbv)
+        cases[f"fast32_c160_mb{mbv}"] = dict(cin=160, mb=mbv, nb=3, max_ctas=5)
+        cases[f"fast32_c96_w130_mb{mbv}"] = dict(cin=96, mb=mbv, nb=2, h=23, w=130)
+        cases[f"fast32_c32_h7_mb{mbv}"] = dict(cin=32, ctot=32, mb=mbv, nb=5, h=7, w=40, max_ctas=3)
+        for cc in (64, 96, 128, 160):
+            cases[f"time_fast32_c{cc}_mb{mbv}"] = dict(nb=64, cin=cc, mb=mbv, time=True)
+    cases["time_fast32_c96_mb2"] = dict(nb=64, cin=96, mb=2, time=True)
+    cases["time_fast32_c128_mb2"] = dict(nb=64, cin=128, mb=2, time=True)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
