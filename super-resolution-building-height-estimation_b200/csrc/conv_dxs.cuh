@@ -100,7 +100,59 @@ __device__ __forceinline__ uint32_t issue_dxs(uint32_t a_lo, uint32_t b_lo, uint
   return ok1 | (ok2 << 1);
 }
 
-template <bool EXACT, int MB, int CH, bool WRES>
+// ---- lean issue: ALL MMAs of one phase of a chunk (3 window rows x NB blocks x KST k-steps, x2 when DUAL) as one asm
+// block with no barrier probes.  Round 2 measured (profiles/r02_mma_issue_gaps.md) that the MMA warp spends ~45 % of a
+// tile OUTSIDE its issue blocks — probe bookkeeping, per-window-row slab indices, vote / reduce — while the tensor
+// queue (a few MMAs deep) runs dry; with resident weights the three slabs of a chunk are consecutive, so a phase needs
+// one wait, one asm block and one commit.
+// extra operands: %18 A step to the next window row (minus what the block sequence advanced), %19 B step likewise
+#define BHSR_DXL_PRE                                                                   \
+  "{\n.reg .pred pacc, ptrue;\n.reg .b32 alo, blo, bl2;\n.reg .b64 da, db;\n"          \
+  "setp.ne.b32 pacc, %8, 0;\nsetp.eq.b32 ptrue, 0, 0;\n"                               \
+  "mov.b32 alo, %0;\nmov.b32 blo, %1;\n"
+#define BHSR_DXL_S(D, ACC)                                                             \
+  "mov.b64 da, {alo, %2};\nmov.b64 db, {blo, %2};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %7, " ACC ";\n"                 \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_DXL_D(D, ACC)                                                             \
+  "mov.b64 da, {alo, %2};\nmov.b64 db, {blo, %2};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %7, " ACC ";\n"                 \
+  "add.u32 bl2, blo, %11;\nmov.b64 db, {bl2, %2};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %7, ptrue;\n"                   \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_DXL_NEXT "add.u32 alo, alo, %9;\nsub.u32 blo, blo, %10;\n"
+#define BHSR_DXL_NEXTDY "add.u32 alo, alo, %12;\nadd.u32 blo, blo, %13;\n"
+#define BHSR_DXL_K1(S, D, A0) S(D, A0)
+#define BHSR_DXL_K2(S, D, A0) S(D, A0) S(D, "ptrue")
+#define BHSR_DXL_K4(S, D, A0) S(D, A0) S(D, "ptrue") S(D, "ptrue") S(D, "ptrue")
+#define BHSR_DXL_N2(K, S, A0) K(S, "%3", A0) BHSR_DXL_NEXT K(S, "%4", A0)
+#define BHSR_DXL_N3(K, S, A0) K(S, "%3", A0) BHSR_DXL_NEXT K(S, "%4", A0) BHSR_DXL_NEXT K(S, "%5", A0)
+#define BHSR_DXL_N4(K, S, A0) K(S, "%3", A0) BHSR_DXL_NEXT K(S, "%4", A0) BHSR_DXL_NEXT K(S, "%5", A0) BHSR_DXL_NEXT K(S, "%6", A0)
+#define BHSR_DXL_PHASE(NMAC, K, S) NMAC(K, S, "pacc") BHSR_DXL_NEXTDY NMAC(K, S, "ptrue") BHSR_DXL_NEXTDY NMAC(K, S, "ptrue")
+#define BHSR_DXL_ASM(BODY)                                                             \
+  asm volatile(BHSR_DXL_PRE BODY "}\n"                                                 \
+               :: "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(idesc),  \
+                  "r"(acc_first), "n"(ASTEP16 - 2 * KST), "n"(2 * KST), "n"(BOFF16),                     \
+                  "n"(DYA16 - (NB - 1) * ASTEP16 - 2 * KST), "n"(DYB16 - 2 * KST)                        \
+               : "memory")
+#define BHSR_DXL_PICK_K(NMAC, S)                                                       \
+  if constexpr (KST == 4) BHSR_DXL_ASM(BHSR_DXL_PHASE(NMAC, BHSR_DXL_K4, S));         \
+  else if constexpr (KST == 2) BHSR_DXL_ASM(BHSR_DXL_PHASE(NMAC, BHSR_DXL_K2, S));    \
+  else BHSR_DXL_ASM(BHSR_DXL_PHASE(NMAC, BHSR_DXL_K1, S))
+#define BHSR_DXL_PICK_N(S)                                                             \
+  if constexpr (NB == 2) { BHSR_DXL_PICK_K(BHSR_DXL_N2, S); }                          \
+  else if constexpr (NB == 3) { BHSR_DXL_PICK_K(BHSR_DXL_N3, S); }                     \
+  else { BHSR_DXL_PICK_K(BHSR_DXL_N4, S); }
+
+template <int KST, int NB, int ASTEP16, bool DUAL, int BOFF16, int DYA16, int DYB16>
+__device__ __forceinline__ void issue_phase(uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t d0, uint32_t d1,
+                                            uint32_t d2, uint32_t d3, uint32_t idesc, uint32_t acc_first) {
+  static_assert(KST == 1 || KST == 2 || KST == 4, "k-steps per chunk");
+  static_assert(NB >= 2 && NB <= 4, "blocks per tile");
+  if constexpr (DUAL) { BHSR_DXL_PICK_N(BHSR_DXL_D) } else { BHSR_DXL_PICK_N(BHSR_DXL_S) }
+}
+
+template <bool EXACT, int MB, int CH, bool WRES, bool LEAN = false>
 __global__ void __launch_bounds__(kDxThreads, 1)
 conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 const __grid_constant__ CUtensorMap tm_a_lo,
@@ -184,9 +236,11 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   const int flat_end = p.h * kPitch;                 // flat outputs of a strip
   // blocks of tile-in-strip t that hold at least one valid output
   auto blocks_of = [&](int t) {
+    if (LEAN) return MB;   // lean issue: ragged tiles run all blocks (rows past the image are discarded by the epilogue)
     const int n = (flat_end - t * S_OUT + kDxBlk - 1) / kDxBlk;
     return n < MB ? n : MB;
   };
+  static_assert(!LEAN || WRES, "lean issue needs resident weights (consecutive slabs)");
 
   if (warp == kDxWarpProdA) {
     // ------------------------------------------------ activation producer (hi ring, lo ring)
@@ -229,6 +283,110 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         if (WRES) break;
       }
     }
+  } else if (LEAN && warp == kDxWarpMma) {
+    // ------------------------------------------------ MMA issuer, lean form: per chunk and phase one wait, one asm
+    // block, one commit; accumulator slots rotate so a tile's slots were drained two tiles ago
+    const uint64_t desc0 = make_kmajor_desc<RB>(0);
+    const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+    const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
+    const uint32_t b_base16 = desc_lo0 + ((w_base >> 4) & 0x3FFF);
+    const int n_chunks = p.n_chunks, cin = p.cin;
+    constexpr int DYA = kPitch * RB16, DYB = W_SLAB >> 4;
+#ifdef BHSR_TIMING
+    long long t_tempty = 0, t_afull = 0, t_total = clock64(), tq = 0;
+    const bool dbg = p.dbg != nullptr;
+    int n_tiles = 0;
+#endif
+    int sh = 0, h_ph = 0, sl = 0, l_ph = 0;
+    uint32_t blk = 0;
+    for (int i = 0; i < n_chunks * 3; ++i) mbar_wait(bar(B_WFULL + i), 0);     // resident weights: once
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, blk += MB) {
+      const int t = tile % p.tiles_per_strip;
+      const int f0 = t * S_OUT;
+      const int r0 = (f0 + kPitch - 1) / kPitch - 2;
+      const uint32_t row0 = (f0 - r0 * kPitch - kPitch) * RB16;
+      uint32_t dacc[4], tslot[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        tslot[b] = (blk + b) % NSLOT;
+        dacc[b] = tmem_base + tslot[b] * COLS;
+      }
+#ifdef BHSR_TIMING
+      if (dbg) tq = clock64();
+#endif
+#pragma unroll
+      for (int b = 0; b < MB; ++b) mbar_wait(bar(B_TEMPTY + tslot[b]), (((blk + b) / NSLOT) & 1) ^ 1);
+#ifdef BHSR_TIMING
+      if (dbg) t_tempty += clock64() - tq;
+#endif
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t b0 = b_base16 + c * 3 * DYB;
+        const bool half = cin - c * CH < CH;
+#ifdef BHSR_TIMING
+        if (dbg) tq = clock64();
+#endif
+        mbar_wait(bar(B_HFULL + sh), h_ph);
+#ifdef BHSR_TIMING
+        if (dbg) t_afull += clock64() - tq;
+#endif
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = desc_lo0 + (((ah_base + sh * TILE) >> 4) & 0x3FFF) + row0;
+#ifdef BHSR_TIMING
+          if (p.nomma != 1) {
+#endif
+          if (!half) issue_phase<KSTEPS, MB, ASTEP, EXACT, W_LO16, DYA, DYB>(a0, b0, desc_hi, dacc[0], dacc[1], dacc[2], dacc[3], IDESC, c > 0 ? 1u : 0u);
+          else issue_phase<(KSTEPS > 1 ? KSTEPS / 2 : 1), MB, ASTEP, EXACT, W_LO16, DYA, DYB>(a0, b0, desc_hi, dacc[0], dacc[1], dacc[2], dacc[3], IDESC, c > 0 ? 1u : 0u);
+#ifdef BHSR_TIMING
+          }
+#endif
+          umma_commit(bar(B_HEMPTY + sh));
+          if (!EXACT && c + 1 == n_chunks) {
+#pragma unroll
+            for (int b = 0; b < MB; ++b) umma_commit(bar(B_TFULL + tslot[b]));
+          }
+        }
+        __syncwarp();
+        if (++sh == NS) { sh = 0; h_ph ^= 1; }
+        if (EXACT) {
+#ifdef BHSR_TIMING
+          if (dbg) tq = clock64();
+#endif
+          mbar_wait(bar(B_LFULL + sl), l_ph);
+#ifdef BHSR_TIMING
+          if (dbg) t_afull += clock64() - tq;
+#endif
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a0 = desc_lo0 + (((al_base + sl * TILE) >> 4) & 0x3FFF) + row0;
+#ifdef BHSR_TIMING
+            if (p.nomma != 1) {
+#endif
+            if (!half) issue_phase<KSTEPS, MB, ASTEP, false, 0, DYA, DYB>(a0, b0, desc_hi, dacc[0], dacc[1], dacc[2], dacc[3], IDESC, 1u);
+            else issue_phase<(KSTEPS > 1 ? KSTEPS / 2 : 1), MB, ASTEP, false, 0, DYA, DYB>(a0, b0, desc_hi, dacc[0], dacc[1], dacc[2], dacc[3], IDESC, 1u);
+#ifdef BHSR_TIMING
+            }
+#endif
+            umma_commit(bar(B_LEMPTY + sl));
+            if (c + 1 == n_chunks) {
+#pragma unroll
+              for (int b = 0; b < MB; ++b) umma_commit(bar(B_TFULL + tslot[b]));
+            }
+          }
+          __syncwarp();
+          if (++sl == NS) { sl = 0; l_ph ^= 1; }
+        }
+      }
+#ifdef BHSR_TIMING
+      ++n_tiles;
+#endif
+    }
+#ifdef BHSR_TIMING
+    if (dbg && lane == 0 && p.nomma != 6) {
+      long long* o = p.dbg + blockIdx.x * 8;
+      o[0] = clock64() - t_total; o[1] = t_tempty; o[2] = t_afull; o[3] = 0; o[4] = n_tiles; o[5] = 0;
+    }
+#endif
   } else if (warp == kDxWarpMma) {
     // ------------------------------------------------ MMA issuer
     const uint64_t desc0 = make_kmajor_desc<RB>(0);
@@ -465,7 +623,7 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #endif
     }
 #ifdef BHSR_TIMING
-    if (dbg && lane == 0) {
+    if (dbg && lane == 0 && p.nomma != 6) {
       long long* o = p.dbg + blockIdx.x * 8;
       o[0] = clock64() - t_total; o[1] = t_tempty; o[2] = t_afull; o[3] = t_wfull; o[4] = n_tiles;
       o[5] = t_issue;   // cycles inside the issue regions (probe_conv_tc.py prints it as prologue_cycles)
@@ -481,7 +639,7 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     uint32_t blk = 0;
     uint32_t xpar = 0;
 #ifdef BHSR_TIMING
-    long long t_epi_wait = 0;
+    long long t_epi_wait = 0, e_drain = 0, e_bar = 0, e_comb = 0, e_fin = 0, es = 0;
 #endif
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid) {
       const int t = tile % p.tiles_per_strip;
@@ -503,6 +661,7 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #endif
         tc_fence_after();
 #ifdef BHSR_TIMING
+        es = clock64();
         if (p.nomma == 9) {   // diagnostic: the accumulator is released without being read (no tcgen05.ld at all)
           tc_fence_before();
           mbar_arrive(bar(B_TEMPTY + slot));
@@ -528,6 +687,7 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         mbar_arrive(bar(B_TEMPTY + slot));
 #ifdef BHSR_TIMING
         if (p.nomma == 4) continue;
+        { const long long tn = clock64(); e_drain += tn - es; es = tn; }
 #endif
         // out[row] = g0[row-1] + g1[row] + g2[row+1]: lane shifts inside the warp, smem across warps
         float* xb = s_xchg + ((grp * 2 + xpar) * 4) * 64;
@@ -543,6 +703,9 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         }
         if (grp == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
         xpar ^= 1;
+#ifdef BHSR_TIMING
+        { const long long tn = clock64(); e_bar += tn - es; es = tn; }
+#endif
         float v[32];
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
@@ -568,6 +731,9 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) v[jj] = (v0[jj] + v1[jj]) + v2[jj];
 
+#ifdef BHSR_TIMING
+        { const long long tn = clock64(); e_comb += tn - es; es = tn; }
+#endif
         const int f = (t * MB + mb) * kDxBlk - 1 + row;
         const int py = f / kPitch;
         const int pc = f - py * kPitch;
@@ -578,6 +744,9 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int ox = px * p.out_scale + p.out_ox;
         const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
         finish_planes32_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
+#ifdef BHSR_TIMING
+        { const long long tn = clock64(); e_fin += tn - es; es = tn; }
+#endif
       }
       blk += nblk;
     }
@@ -586,6 +755,7 @@ conv_dxs_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       long long* o = p.dbg + blockIdx.x * 8;
       o[6] = t_epi_wait;
       o[7] = clock64() - t_entry;
+      if (p.nomma == 6) { o[1] = e_drain; o[2] = e_bar; o[3] = e_comb; o[5] = e_fin; }   // diagnostic 6: epilogue stages
     }
 #endif
   }

@@ -325,10 +325,10 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
 }
 
 // Single-accumulator dx-in-N launch (conv_dxs.cuh): MB = 2..4 blocks per tile, CH channels per chunk.
-template <bool EXACT, int MB, int CH, bool WRES>
+template <bool EXACT, int MB, int CH, bool WRES, bool LEAN = false>
 static int launch_dxs_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
                              const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
-  auto kern = conv_dxs_kernel<EXACT, MB, CH, WRES>;
+  auto kern = conv_dxs_kernel<EXACT, MB, CH, WRES, LEAN>;
   static PerDeviceOnce attr_once;
   if (attr_once.first())
     BHSR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -403,6 +403,12 @@ static int launch_dxs(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
   static const char* no_pdl = getenv("BHSR_NO_PDL");
   p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
+  static const char* lean_env = getenv("BHSR_DXS_LEAN");   // 1 = lean issuer (one wait / asm block / commit per phase) when the weights are resident
+  const bool lean = lean_env && lean_env[0] == '1';   // opt-in: measured no faster (the epilogue / the 2-stage ring bound the resident layers)
+  if (p.w_resident && lean) {
+    // lean issue treats the ragged last tile of a strip as a full tile
+    return launch_dxs_kernel<EXACT, MB, CH, true, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  }
   if (p.w_resident) return launch_dxs_kernel<EXACT, MB, CH, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
   return launch_dxs_kernel<EXACT, MB, CH, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
 }
