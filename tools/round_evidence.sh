@@ -1,5 +1,5 @@
 #!/bin/bash
-# Final round-1 evidence: gpu tests, smoke, bench (both arms), launch list + ncu capture.
+# Final round evidence: gpu tests, smoke, bench (both arms), launch list + ncu capture.
 mkdir -p gpurun_out
 python -c "import torch; torch.zeros(1).cuda()" > /dev/null 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_final.log; tail -4 gpurun_out/pytest_gpu_final.log
