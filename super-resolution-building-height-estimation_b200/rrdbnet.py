@@ -70,9 +70,8 @@ def _default_numerics() -> str:
 def _no_autograd(name: str, *tensors) -> None:
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            f"{name}: backward through RRDBNet is not built (the height pipeline runs it frozen under "
-            "torch.no_grad(), train.py:139-140,243-244); call under torch.no_grad() / detach inputs "
-            "and set requires_grad=False on its parameters")
+            f"{name}: backward through a stand-alone block is not built (RRDBNet.forward / forward_feature have one, "
+            "rrdbnet_train.py); call under torch.no_grad() / detach inputs and set requires_grad=False on its parameters")
 
 
 # ------------------------------------------------------------------ blocks (parameter containers)
@@ -244,6 +243,8 @@ class _RRDBNetBase(_lib.CacheMixin, nn.Module):
         overwritten by the next call with the same input buffer (callers that keep results must clone them).  It is
         opt-in because of that aliasing; bench.py and the sharded predictor, which consume each result before the
         next step, turn it on."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._run_train(x, feature, scale)
         if getattr(self, "use_cuda_graph", False) and x.is_cuda and not torch.cuda.is_current_stream_capturing():
             y = self._run_graphed(x, feature, scale)
             if y is not None:
@@ -277,6 +278,31 @@ class _RRDBNetBase(_lib.CacheMixin, nn.Module):
             return None
         entry[0].replay()
         return entry[1]
+
+    def _run_train(self, x: torch.Tensor, feature: bool, scale: int) -> torch.Tensor:
+        """Forward under autograd (SR fine-tuning, SR/rrdbnet_arch.py:538-592): layer by layer through the same
+        kernels in exact numerics, keeping the activations; backward = tensor-core dgrad / wgrad (rrdbnet_train.py).
+        The frozen pipeline (torch.no_grad(), train.py:243-244) never comes here."""
+        from .rrdbnet_train import RRDBNetTrainFn
+        _lib.require_cuda(x, "x")
+        first, last = self._child(0), self._child(6)
+        _check_widths(first.out_channels, self._tc_convs()[0].out_channels if len(self._child(1)) else 32)
+        if x.dtype != torch.float32:
+            x = x.float()
+        if scale == 2:
+            x = pixel_unshuffle(x, 2)
+        elif scale == 1:
+            x = pixel_unshuffle(x, 4)
+        if x.shape[1] != first.in_channels:
+            raise RuntimeError(f"expected input with {first.in_channels} channels, got {x.shape[1]}")
+        if x.shape[0] == 0 or x.shape[2] == 0 or x.shape[3] == 0:
+            raise RuntimeError("RRDBNet under autograd needs a non-empty batch")
+        convs = [first] + self._tc_convs() + [last]
+        for c in convs:
+            if c.bias is None:
+                raise _lib.BhsrError("RRDBNet convs must have biases (the reference's all do)")
+        params = [t for c in convs for t in (c.weight, c.bias)]
+        return RRDBNetTrainFn.apply(convs, x, bool(feature), *params)
 
     def _run_eager(self, x: torch.Tensor, feature: bool, scale: int) -> torch.Tensor:
         _lib.require_cuda(x, "x")
@@ -400,37 +426,151 @@ class OldRRDBNet(_RRDBNetBase):
 
 # ------------------------------------------------------------------ RealESRGAN shell
 class RealESRGAN:
-    """The `.net_g` surface of SR/rrdbnet_arch.py:437-509 without its training-time side effects.
+    """SR/rrdbnet_arch.py:437-592 on the B200 path: `.net_g` for the height pipeline and, with `is_train=True`, the
+    generator half of the SR fine-tune step.
 
-    The callers on the hot path (train.py:133-140, predict_realesanet_feature_globe.py:95-102)
-    only touch `net_g` (load_state_dict / eval / parameters / forward_feature).  The reference
-    constructor additionally builds an EMA copy, a U-Net discriminator, USM sharpening on CUDA, a
-    VGG19 perceptual loss (network download) and two optimisers — all SR-fine-tuning state that the
-    height pipeline never uses; they are out of scope here.
+    The callers on the hot path (train.py:133-140, predict_realesanet_feature_globe.py:95-102) only touch `net_g`
+    (load_state_dict / eval / parameters / forward_feature); the default construction therefore stays free of the
+    reference constructor's side effects (it always builds an EMA copy, a U-Net discriminator, USM sharpening on CUDA, a
+    VGG19 perceptual loss — a network download — and two optimisers).
+
+    `is_train=True` adds what `optimize_parameters` (:538-592) needs for the GENERATOR update, which
+    is where the B200 kernels are (forward + tensor-core backward of RRDBNet, rrdbnet_train.py): `net_g_ema` (:459-478),
+    `cri_pix = nn.L1Loss()` (:493), `optimizer_g = Adam(lr 1e-4, betas (0.9, 0.99))` (:502), its MultiStepLR (:505),
+    `feed_data`, `model_ema` (:531-536) and `optimize_parameters`.  The discriminator, the VGG perceptual loss, the GAN
+    loss and the USM sharpener are stock PyTorch modules outside this repo's scope: assign `net_d` / `optimizer_d` /
+    `cri_perceptual` / `cri_gan` / `usm_sharpener` to use them — `optimize_parameters` then runs the reference's
+    sequence including the discriminator update; unset, their terms are skipped (pixel loss only) and said so in the
+    returned dict.
     """
+
+    _OPTIONAL = ("net_d", "optimizer_d", "usm_sharpener", "cri_perceptual", "cri_gan")
+    _TRAIN_ONLY = ("net_g_ema", "cri_pix", "optimizer_g", "optimizers", "schedulers")
 
     def __init__(self, in_ch=3, out_ch=3, num_block=23, device='cuda', scale=4, ema_decay=0.999,
                  pretrain_g_path=None, pretrain_d_path=None, is_train=False):
         self.device = device
         self.scale = scale
         self.ema_decay = ema_decay
-        self.net_g = RRDBNet(num_in_ch=in_ch, num_out_ch=out_ch, num_feat=64, num_block=num_block,
-                             num_grow_ch=32, scale=scale).to(device)
-        if pretrain_g_path is not None:
+        self.is_train = bool(is_train)
+
+        def make():
+            return RRDBNet(num_in_ch=in_ch, num_out_ch=out_ch, num_feat=64, num_block=num_block,
+                           num_grow_ch=32, scale=scale).to(device)
+
+        def pretrained():
             weights = torch.load(pretrain_g_path, map_location=device)['params_ema']
             if in_ch == 1:  # same averaging as rrdbnet_arch.py:451-454
                 weights['conv_first.weight'] = torch.mean(weights['conv_first.weight'], dim=1, keepdim=True)
                 weights['conv_last.weight'] = torch.mean(weights['conv_last.weight'], dim=0, keepdim=True)
                 weights['conv_last.bias'] = torch.mean(weights['conv_last.bias'], dim=0, keepdim=True)
-            self.net_g.load_state_dict(weights)
+            return weights
+
+        self.net_g = make()
+        if pretrain_g_path is not None:
+            self.net_g.load_state_dict(pretrained())
         if self.ema_decay > 0:
             print(f'Use Exponential Moving Average with decay: {self.ema_decay}')
         self.net_g.train()
+        if not self.is_train:
+            return
+        if pretrain_d_path is not None:
+            raise NotImplementedError("RealESRGAN(pretrain_d_path=...): the discriminator is a stock PyTorch module outside "
+                                      "this repo; build it and assign `.net_d` / `.optimizer_d`")
+        if self.ema_decay > 0:
+            self.net_g_ema = make()
+            if pretrain_g_path is not None:
+                self.net_g_ema.load_state_dict(pretrained())
+            else:
+                self.model_ema(0)  # copy net_g weight (:476)
+            for p in self.net_g_ema.parameters():
+                p.requires_grad = False
+        self.cri_pix = nn.L1Loss().to(device)
+        self.net_d_iters = 1
+        self.net_d_init_iters = 0
+        self.optimizer_g = torch.optim.Adam(params=self.net_g.parameters(), lr=1e-4, betas=(0.9, 0.99), weight_decay=0)
+        self.optimizers = [self.optimizer_g]
+        self.schedulers = [torch.optim.lr_scheduler.MultiStepLR(self.optimizer_g, milestones=[400000], gamma=0.5)]
 
     def __getattr__(self, name):
-        if name in ("net_g_ema", "net_d", "usm_sharpener", "cri_pix", "cri_perceptual", "cri_gan",
-                    "optimizer_g", "optimizer_d", "optimizers", "schedulers"):
+        if name in RealESRGAN._OPTIONAL:
+            return None                      # stock PyTorch pieces the caller may plug in
+        if name in RealESRGAN._TRAIN_ONLY:
             raise AttributeError(
-                f"RealESRGAN.{name}: the SR fine-tuning state (EMA copy, discriminator, losses, "
-                "optimisers) is outside the B200 hot path; only .net_g is provided")
+                f"RealESRGAN.{name}: SR fine-tuning state is only built with is_train=True"
+                + (" and ema_decay > 0" if name == "net_g_ema" else ""))
         raise AttributeError(name)
+
+    @torch.no_grad()
+    def feed_data(self, data):
+        """:522-528 (USM sharpening only when a `usm_sharpener` module was assigned)."""
+        self.lq = data['lq'].to(self.device, non_blocking=True)
+        self.gt = data['gt'].to(self.device, non_blocking=True)
+        self.gt_usm = self.usm_sharpener(self.gt) if self.usm_sharpener is not None else self.gt
+
+    @torch.no_grad()
+    def model_ema(self, decay=0.999):
+        """:530-536.  The reference writes through `.data`, which does not bump tensor versions: the EMA copy's packed-
+        weight cache is invalidated explicitly."""
+        net_g_params = dict(self.net_g.named_parameters())
+        net_g_ema_params = dict(self.net_g_ema.named_parameters())
+        for k in net_g_ema_params.keys():
+            net_g_ema_params[k].data.mul_(decay).add_(net_g_params[k].data, alpha=1 - decay)
+        self.net_g_ema.invalidate_cache()
+
+    def optimize_parameters(self):
+        """:538-592.  Generator: output = net_g(lq) -> pixel (+ perceptual + GAN when plugged in) -> backward through the
+        B200 kernels -> Adam; discriminator update when `net_d` / `optimizer_d` / `cri_gan` are plugged in; EMA."""
+        from collections import OrderedDict
+        l1_gt = percep_gt = self.gt_usm
+        gan_gt = self.gt
+        have_d = self.net_d is not None and self.cri_gan is not None
+        if have_d:
+            for p in self.net_d.parameters():
+                p.requires_grad = False
+        self.optimizer_g.zero_grad()
+        self.output = self.net_g(self.lq)
+        loss_dict = OrderedDict()
+        l_g_pix = self.cri_pix(self.output, l1_gt)
+        l_g_total = l_g_pix
+        loss_dict['l_g_pix'] = l_g_pix.item()
+        if self.cri_perceptual is not None:
+            l_g_percep = self.cri_perceptual(self.output, percep_gt)
+            l_g_total = l_g_total + l_g_percep
+            loss_dict['l_g_percep'] = l_g_percep.item()
+        if have_d:
+            fake_g_pred = self.net_d(self.output)
+            l_g_gan = self.cri_gan(fake_g_pred, True, is_disc=False)
+            l_g_total = l_g_total + l_g_gan
+            loss_dict['l_g_gan'] = l_g_gan.item()
+        l_g_total.backward()
+        self.optimizer_g.step()
+        if have_d and self.optimizer_d is not None:
+            for p in self.net_d.parameters():
+                p.requires_grad = True
+            self.optimizer_d.zero_grad()
+            real_d_pred = self.net_d(gan_gt)
+            l_d_real = self.cri_gan(real_d_pred, True, is_disc=True)
+            loss_dict['l_d_real'] = l_d_real.item()
+            loss_dict['out_d_real'] = torch.mean(real_d_pred.detach())
+            l_d_real.backward()
+            fake_d_pred = self.net_d(self.output.detach().clone())
+            l_d_fake = self.cri_gan(fake_d_pred, False, is_disc=True)
+            loss_dict['l_d_fake'] = l_d_fake.item()
+            loss_dict['out_d_fake'] = torch.mean(fake_d_pred.detach())
+            l_d_fake.backward()
+            self.optimizer_d.step()
+        else:
+            loss_dict['skipped'] = 'perceptual / GAN / discriminator terms: no net_d / cri_perceptual / cri_gan assigned'
+        if self.ema_decay > 0:
+            self.model_ema(decay=self.ema_decay)
+        return loss_dict
+
+    def save(self, epoch, current_iter, respath):
+        """:508-519 (generator file; the discriminator file only when a `net_d` was assigned)."""
+        torch.save({'params': self.net_g.state_dict(),
+                    'params_ema': self.net_g_ema.state_dict() if 'net_g_ema' in self.__dict__ else None,
+                    'epoch': epoch, 'current_iter': current_iter}, os.path.join(respath, 'net_g.tar'))
+        if self.net_d is not None:
+            torch.save({'params': self.net_d.state_dict(), 'epoch': epoch, 'current_iter': current_iter},
+                       os.path.join(respath, 'net_d.tar'))

@@ -185,8 +185,14 @@ def test_realesrgan_shell_has_no_side_effects():
     from bhsr.rrdbnet import RealESRGAN
     m = RealESRGAN(device="cpu", num_block=1)   # the reference needs CUDA + a VGG19 download here
     assert len(m.net_g.state_dict()) == 42 and m.net_g.training
+    assert m.net_d is None and m.cri_perceptual is None          # stock PyTorch pieces: pluggable, not built
     with pytest.raises(AttributeError, match="fine-tuning"):
-        m.net_d
+        m.optimizer_g                                            # only with is_train=True
+    t = RealESRGAN(device="cpu", num_block=1, is_train=True, ema_decay=0.9)   # rrdbnet_arch.py:459-505
+    assert isinstance(t.optimizer_g, torch.optim.Adam) and t.optimizer_g.defaults["betas"] == (0.9, 0.99)
+    assert all(not p.requires_grad for p in t.net_g_ema.parameters())
+    for (k, a), (_, b) in zip(t.net_g.state_dict().items(), t.net_g_ema.state_dict().items()):
+        assert torch.equal(a, b), k                              # model_ema(0) copies the generator (:476)
 
 
 def test_packed_weight_caches_are_invalidated():

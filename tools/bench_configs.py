@@ -5,6 +5,9 @@
   config 4: the same step as a data-parallel training loop (32 tiles / GPU, Adam, one NCCL
             all-reduce of the flat gradient bucket per step) — run under torchrun
   config 5: inference sweep, 10k synthetic 64x64 grids, batch 128, sharded rank::world
+  config 6: SR fine-tune step: RealESRGAN(is_train=True).optimize_parameters — generator forward,
+            L1 pixel loss, tensor-core backward (rrdbnet_train.py), Adam, EMA — batch 12 (the upstream YAML's),
+            64x64 -> 256x256; the discriminator / VGG terms are stock PyTorch and not plugged in
 
 Prints one JSON line per config (rank 0).  CUDA events, max over ranks.
 """
@@ -22,7 +25,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5])
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5, 6])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0)
@@ -47,6 +50,30 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.config == 6:
+        from bhsr.rrdbnet import RealESRGAN
+        torch.manual_seed(1337)
+        B = args.batch or 12
+        m = RealESRGAN(device=str(dev), num_block=args.num_block, is_train=True, ema_decay=0.999)
+        m.feed_data({"lq": torch.rand(B, 3, 64, 64), "gt": torch.rand(B, 3, 256, 256)})
+        out = {}
+        for _ in range(args.warmup):
+            out = m.optimize_parameters()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = m.optimize_parameters()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        print(json.dumps({"config": 6, "metric": "SR fine-tune generator step (fwd + L1 + tensor-core bwd + Adam + EMA)",
+                          "value": B / ms * 1e3, "unit": "tiles/s", "ms_per_step": ms, "batch": B,
+                          "num_block": args.num_block, "l_g_pix": out.get("l_g_pix"), "numerics": "exact",
+                          "note": "reference-derived figure (BASELINE.md §2): 0.688 s/iter for the full G+D step, batch 12, unknown GPU"}),
+              flush=True)
+        return
 
     torch.manual_seed(1337)
     net_g = RRDBNet(3, 3, scale=4, num_feat=64, num_block=args.num_block, num_grow_ch=32).to(dev).eval()

@@ -1,0 +1,6 @@
+#!/bin/bash
+# Round 2, call 25: RRDBNet backward (row N3) bring-up
+mkdir -p gpurun_out
+python -c "import torch; torch.zeros(1).cuda()" > /dev/null 2>&1
+timeout 900 python -m pytest tests/test_rrdbnet_gpu.py -m gpu -q -s -k "backward_vs_oracle or finetune or error_behaviour" > gpurun_out/r2c25_n3.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2c25_n3.log
+grep -E "passed|failed|FAILED|rel-L2|rc=|Error|error|assert" gpurun_out/r2c25_n3.log | head -40

@@ -100,6 +100,10 @@ def run_case(name, desc_mode):
             cases[f"time_fast32_c{cc}_mb{mbv}"] = dict(nb=64, cin=cc, mb=mbv, time=True)
     cases["time_fast32_c96_mb2"] = dict(nb=64, cin=96, mb=2, time=True)
     cases["time_fast32_c128_mb2"] = dict(nb=64, cin=128, mb=2, time=True)
+    for cc in (16, 32, 64, 96):     # 64-output exact convs: CTA-pair kernel on even batches (cin % 32 == 0), per-tap otherwise
+        for nbv in (2, 3):
+            cases[f"exact64_c{cc}_nb{nbv}"] = dict(cout=64, cin=cc, ctot=96 if cc == 96 else 64, exact=True, mb=2, nb=nbv, lrelu=False, h=16, w=16)
+            cases[f"exact64_c{cc}_nb{nbv}_nchw"] = dict(cout=64, cin=cc, ctot=96 if cc == 96 else 64, exact=True, mb=2, nb=nbv, lrelu=False, h=16, w=16, nchw=True)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
