@@ -629,3 +629,30 @@ def test_realesrgan_optimize_parameters_generator_step(dev):
     out = m.optimize_parameters()
     assert {"l_g_pix", "l_g_gan", "l_d_real", "l_d_fake"} <= set(out) and "skipped" not in out
     assert all(p.grad is not None for p in m.net_g.parameters())
+
+
+def test_realesrgan_generator_step_cuda_graph_matches_eager(dev):
+    """The CUDA-graph replay of the pixel-loss generator step (RealESRGAN.use_cuda_graph) follows the same trajectory as
+    the eager step: same losses step by step, same weights and EMA copy at the end; the frozen forward afterwards uses
+    the updated weights (cache invalidation after replays)."""
+    from bhsr.rrdbnet import RealESRGAN
+    data = {"lq": torch.rand(2, 3, 8, 8, generator=torch.Generator().manual_seed(5)),
+            "gt": torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(6))}
+    runs = []
+    for graphed in (False, True):
+        torch.manual_seed(21)
+        m = RealESRGAN(device=str(dev), num_block=1, is_train=True, ema_decay=0.9)
+        m.use_cuda_graph = graphed
+        m.feed_data(data)
+        losses = [m.optimize_parameters() for _ in range(6)]
+        assert ("launch" in losses[-1]) == graphed
+        with torch.no_grad():
+            y = m.net_g(m.lq).clone()
+            ye = m.net_g_ema(m.lq).clone()
+        runs.append(([l["l_g_pix"] for l in losses], y, ye, [p.detach().clone() for p in m.net_g.parameters()]))
+    (la, ya, yea, pa), (lb, yb, yeb, pb) = runs
+    np.testing.assert_allclose(la, lb, rtol=1e-4)
+    for a, b in zip(pa, pb):
+        assert_close(b.cpu().numpy(), a.cpu().numpy(), 1e-3, 1e-5, "parameters after 6 steps")
+    assert_close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-3, 1e-4, "generator output after 6 steps")
+    assert_close(yeb.cpu().numpy(), yea.cpu().numpy(), 1e-3, 1e-4, "EMA output after 6 steps")

@@ -57,6 +57,10 @@ def main():
         B = args.batch or 12
         m = RealESRGAN(device=str(dev), num_block=args.num_block, is_train=True, ema_decay=0.999)
         m.feed_data({"lq": torch.rand(B, 3, 64, 64), "gt": torch.rand(B, 3, 256, 256)})
+        m.use_cuda_graph = os.environ.get("BHSR_SR_GRAPH", "1") != "0"
+        if m.use_cuda_graph:
+            for _ in range(3):       # two eager warm-up steps, then the capture
+                m.optimize_parameters()
         out = {}
         for _ in range(args.warmup):
             out = m.optimize_parameters()
@@ -70,7 +74,7 @@ def main():
         ms = e0.elapsed_time(e1) / args.steps
         print(json.dumps({"config": 6, "metric": "SR fine-tune generator step (fwd + L1 + tensor-core bwd + Adam + EMA)",
                           "value": B / ms * 1e3, "unit": "tiles/s", "ms_per_step": ms, "batch": B,
-                          "num_block": args.num_block, "l_g_pix": out.get("l_g_pix"), "numerics": "exact",
+                          "num_block": args.num_block, "l_g_pix": out.get("l_g_pix"), "numerics": "exact", "launch": out.get("launch", "eager"),
                           "note": "reference-derived figure (BASELINE.md §2): 0.688 s/iter for the full G+D step, batch 12, unknown GPU"}),
               flush=True)
         return
