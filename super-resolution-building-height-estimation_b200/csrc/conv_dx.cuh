@@ -49,6 +49,40 @@ constexpr int kDxBars = 4 * kMaxAStages + 8 + 2 * kMaxWSlots;
 constexpr int kDxTailBytes = kDxBars * 8 + 16 + 2 * 64 * 4 + 64 + kDxStageBytes + kDxXchgFloats * 4;
 constexpr int kDxBlk = 126;                         // valid output rows per 128-row block
 
+// ---- lean issue with the three window-row slabs at arbitrary ring slots (streamed weights): b0 / b1 / b2 are register
+// operands instead of an immediate stride.  NB = 1 or 2 blocks.  Used by the lean issuer below (desc_mode bit 11 / BHSR_DX_LEAN=1).
+// operands: %0 a_lo %1 b0 %2 b1 %3 b2 %4 desc_hi %5 d0 %6 d1 %7 idesc %8 acc_first | %9 A step to the next block minus
+//           the k advance, %10 A step to the next window row (minus what the block sequence advanced)
+#define BHSR_DXQ_PRE                                                                   \
+  "{\n.reg .pred pacc, ptrue;\n.reg .b32 alo, blo;\n.reg .b64 da, db;\n"               \
+  "setp.ne.b32 pacc, %8, 0;\nsetp.eq.b32 ptrue, 0, 0;\nmov.b32 alo, %0;\n"
+#define BHSR_DXQ_S(D, ACC)                                                             \
+  "mov.b64 da, {alo, %4};\nmov.b64 db, {blo, %4};\n"                                   \
+  "tcgen05.mma.cta_group::1.kind::f16 [" D "], da, db, %7, " ACC ";\n"                 \
+  "add.u32 alo, alo, 2;\nadd.u32 blo, blo, 2;\n"
+#define BHSR_DXQ_K1(D, A0) BHSR_DXQ_S(D, A0)
+#define BHSR_DXQ_K2(D, A0) BHSR_DXQ_S(D, A0) BHSR_DXQ_S(D, "ptrue")
+#define BHSR_DXQ_N1(K, B, A0) "mov.b32 blo, " B ";\n" K("%5", A0)
+#define BHSR_DXQ_N2(K, B, A0) "mov.b32 blo, " B ";\n" K("%5", A0) "add.u32 alo, alo, %9;\nmov.b32 blo, " B ";\n" K("%6", A0)
+#define BHSR_DXQ_PHASE(NMAC, K) NMAC(K, "%1", "pacc") "add.u32 alo, alo, %10;\n" NMAC(K, "%2", "ptrue") "add.u32 alo, alo, %10;\n" NMAC(K, "%3", "ptrue")
+#define BHSR_DXQ_ASM(BODY)                                                             \
+  asm volatile(BHSR_DXQ_PRE BODY "}\n"                                                 \
+               :: "r"(a_lo), "r"(b0), "r"(b1), "r"(b2), "r"(desc_hi), "r"(d0), "r"(d1), "r"(idesc), "r"(acc_first),  \
+                  "n"(ASTEP16 - 2 * KST), "n"(DYA16 - (NB - 1) * ASTEP16 - 2 * KST)                                   \
+               : "memory")
+template <int KST, int NB, int ASTEP16, int DYA16>
+__device__ __forceinline__ void issue_phase3(uint32_t a_lo, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t desc_hi,
+                                             uint32_t d0, uint32_t d1, uint32_t idesc, uint32_t acc_first) {
+  static_assert((KST == 1 || KST == 2) && (NB == 1 || NB == 2), "issue_phase3 variants");
+  if constexpr (NB == 1) {
+    if constexpr (KST == 2) BHSR_DXQ_ASM(BHSR_DXQ_PHASE(BHSR_DXQ_N1, BHSR_DXQ_K2));
+    else BHSR_DXQ_ASM(BHSR_DXQ_PHASE(BHSR_DXQ_N1, BHSR_DXQ_K1));
+  } else {
+    if constexpr (KST == 2) BHSR_DXQ_ASM(BHSR_DXQ_PHASE(BHSR_DXQ_N2, BHSR_DXQ_K2));
+    else BHSR_DXQ_ASM(BHSR_DXQ_PHASE(BHSR_DXQ_N2, BHSR_DXQ_K1));
+  }
+}
+
 template <bool EXACT, int MB, bool WRES, bool PAIR>
 __global__ void __launch_bounds__(kDxThreads, 1)
 conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
@@ -218,6 +252,139 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         }
         if (WRES) break;
       }
+    }
+  } else if (EXACT && !PAIR && MB == 2 && (p.desc_mode & 0x800) && warp == kDxWarpMma) {
+    // ------------------------------------------------ MMA issuer, lean form (round 2, Finding 5): per chunk and phase
+    // one blocking wait, ONE asm block with every MMA of the phase (3 window rows x blocks x k-steps) and one commit; no
+    // probes, no vote / reduce.  Block-major only where the two-slot accumulator hand-over needs it: the first chunk's
+    // hi phase waits for each block's drain, the last chunk's lo' phase publishes each block as soon as it is complete.
+    if constexpr (EXACT && !PAIR && MB == 2) {
+      const uint64_t desc0 = make_kmajor_desc<RB>(0);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
+      const uint32_t wb16 = desc_lo0 + ((w_base >> 4) & 0x3FFF);
+      const int n_chunks = p.n_chunks, cin = p.cin, wslots = p.wslots;
+      constexpr int DYA = kPitch * RB16;
+      constexpr uint32_t ASTEP = kDxBlk * RB16;
+      int sh = 0, h_ph = 0, sl = 0, l_ph = 0, ws_r = 0, w_ph = 0;
+      uint32_t tile_it = 0;
+#ifdef BHSR_TIMING
+      long long t_tempty = 0, t_afull = 0, t_wfull = 0, t_total = clock64(), tq = 0;
+      const bool dbg = p.dbg != nullptr;
+#endif
+      for (; item(static_cast<int>(tile_it), tile, sel); ++tile_it) {
+        const int t = tile % p.tiles_per_strip;
+        const int f0 = t * S_OUT;
+        const int r0 = (f0 + kPitch - 1) / kPitch - 2;
+        const uint32_t row0 = (f0 - r0 * kPitch - kPitch) * RB16;
+        const uint32_t t_par = tile_it & 1;          // two slots, two blocks per item: slot = block, parity = item
+        const int mb_lo = sel < 0 ? 0 : sel, mb_hi = sel < 0 ? MB : sel + 1;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t bw[3];
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            int ws;
+            if (WRES) {
+              ws = c * 3 + g;
+              if (tile_it == 0) mbar_wait(bar(B_WFULL + ws), 0);
+            } else {
+              ws = ws_r;
+#ifdef BHSR_TIMING
+              if (dbg) tq = clock64();
+#endif
+              mbar_wait(bar(B_WFULL + ws), w_ph);
+#ifdef BHSR_TIMING
+              if (dbg) t_wfull += clock64() - tq;
+#endif
+              if (++ws_r == wslots) { ws_r = 0; w_ph ^= 1; }
+            }
+            bw[g] = wb16 + ws * (W_SLAB >> 4);
+          }
+          const bool half = cin - c * CH < CH;
+          const bool first_chunk = c == 0, last_chunk = c + 1 == n_chunks;
+#ifdef BHSR_TIMING
+          if (dbg) tq = clock64();
+#endif
+          mbar_wait(bar(B_HFULL + sh), h_ph);
+#ifdef BHSR_TIMING
+          if (dbg) t_afull += clock64() - tq;
+#endif
+          tc_fence_after();
+          const uint32_t a_h0 = desc_lo0 + (((ah_base + sh * TILE) >> 4) & 0x3FFF) + row0;
+          const uint32_t a_l0 = desc_lo0 + (((al_base + sl * TILE) >> 4) & 0x3FFF) + row0;
+          // ---- hi activations x [W_hi | W_lo'] (N = 192) into main + correction columns
+          if (first_chunk || sel >= 0) {
+            for (int mb = mb_lo; mb < mb_hi; ++mb) {
+              if (first_chunk) {
+#ifdef BHSR_TIMING
+                if (dbg) tq = clock64();
+#endif
+                mbar_wait(bar(B_TEMPTY + mb), t_par ^ 1);
+#ifdef BHSR_TIMING
+                if (dbg) t_tempty += clock64() - tq;
+#endif
+                tc_fence_after();
+              }
+              if (elect_one()) {
+                const uint32_t a = a_h0 + mb * ASTEP, d = tmem_base + mb * COLS;
+                if (!half) issue_phase3<KSTEPS, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
+                else issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
+              }
+              __syncwarp();
+            }
+          } else {
+            if (elect_one()) {
+              if (!half) issue_phase3<KSTEPS, 2, ASTEP, DYA>(a_h0, bw[0], bw[1], bw[2], desc_hi, tmem_base, tmem_base + COLS, IDESC_WIDE, 1u);
+              else issue_phase3<KSTEPS / 2, 2, ASTEP, DYA>(a_h0, bw[0], bw[1], bw[2], desc_hi, tmem_base, tmem_base + COLS, IDESC_WIDE, 1u);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit(bar(B_HEMPTY + sh));
+          __syncwarp();
+          if (++sh == NS) { sh = 0; h_ph ^= 1; }
+          // ---- lo' activations x W_hi (N = 96) into the correction columns
+#ifdef BHSR_TIMING
+          if (dbg) tq = clock64();
+#endif
+          mbar_wait(bar(B_LFULL + sl), l_ph);
+#ifdef BHSR_TIMING
+          if (dbg) t_afull += clock64() - tq;
+#endif
+          tc_fence_after();
+          if (last_chunk || sel >= 0) {
+            for (int mb = mb_lo; mb < mb_hi; ++mb) {
+              if (elect_one()) {
+                const uint32_t a = a_l0 + mb * ASTEP, d = tmem_base + mb * COLS + 96;
+                if (!half) issue_phase3<KSTEPS, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_N, 1u);
+                else issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_N, 1u);
+                if (last_chunk) umma_commit(bar(B_TFULL + mb));
+              }
+              __syncwarp();
+            }
+          } else {
+            if (elect_one()) {
+              if (!half) issue_phase3<KSTEPS, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + 96, tmem_base + COLS + 96, IDESC_N, 1u);
+              else issue_phase3<KSTEPS / 2, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + 96, tmem_base + COLS + 96, IDESC_N, 1u);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            if (!WRES) {
+#pragma unroll
+              for (int g = 0; g < 3; ++g) umma_commit(bar(B_WEMPTY + static_cast<int>((bw[g] - wb16) / (W_SLAB >> 4))));
+            }
+            umma_commit(bar(B_LEMPTY + sl));
+          }
+          __syncwarp();
+          if (++sl == NS) { sl = 0; l_ph ^= 1; }
+        }
+      }
+#ifdef BHSR_TIMING
+      if (dbg && lane == 0) {
+        long long* o = p.dbg + blockIdx.x * 8;
+        o[0] = clock64() - t_total; o[1] = t_tempty; o[2] = t_afull; o[3] = t_wfull; o[4] = tile_it; o[5] = 0;
+      }
+#endif
     }
   } else if (warp == kDxWarpMma && (!PAIR || leader)) {
     // ------------------------------------------------ MMA issuer (pairs: the even CTA only)

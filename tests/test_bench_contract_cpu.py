@@ -30,9 +30,9 @@ def test_main_arm_fails_loudly_without_cuda():
 
 
 def test_committed_gpu_bench_line_carries_the_whole_contract():
-    """The last bench line measured on a B200 (profiles/r01_bench_final.json) has every key the
+    """The last bench line measured on a B200 (profiles/r02_bench_final.json) has every key the
     driver reads, and its derived numbers are self-consistent."""
-    path = os.path.join(ROOT, "profiles", "r01_bench_final.json")
+    path = os.path.join(ROOT, "profiles", "r02_bench_final.json")
     line = json.loads([ln for ln in open(path) if ln.startswith("{")][-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
@@ -50,5 +50,20 @@ def test_committed_gpu_bench_line_carries_the_whole_contract():
     assert {k["layer"] for k in r["kernels"]} == {f"rdb.conv{i}" for i in range(1, 6)}
     c = line["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    # the dominant kernel is the one with the largest share of the step, its figure is a mean over its layers
+    assert r["kernel"].startswith("conv_dx_kernel") and 0.3 < r["kernel_share_of_step"] < 0.7
+    assert abs(r["achieved"] - r["algorithmic_gflop_per_launch"] / r["us_per_launch"] * 1e3) < 1e-6 * r["achieved"]
+    assert r["step"]["sum_of_kernels_ms"] < line["ms_per_step"]
+    # fwd+bwd sub-record (BASELINE configs[2] / [3])
+    t = line["train"]
+    for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "batch_per_gpu", "global_batch", "launch",
+              "collective", "grad_bucket_floats", "roofline"):
+        assert k in t, k
+    assert abs(t["value"] - t["global_batch"] / t["ms_per_step"] * 1e3) < 1e-6 * t["value"]
+    assert t["roofline"]["algorithmic_gflop_per_tile"] == 169.63
+    if line["n_gpus"] > 1:      # one flat all-reduce per step; none at N = 1
+        assert t["collective"]["bytes"] == 4 * t["grad_bucket_floats"]
+    else:
+        assert t["collective"] is None
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
