@@ -312,8 +312,18 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
           tc_fence_after();
           const uint32_t a_h0 = desc_lo0 + (((ah_base + sh * TILE) >> 4) & 0x3FFF) + row0;
           const uint32_t a_l0 = desc_lo0 + (((al_base + sl * TILE) >> 4) & 0x3FFF) + row0;
-          // ---- hi activations x [W_hi | W_lo'] (N = 192) into main + correction columns
-          if (first_chunk || sel >= 0) {
+          if (last_chunk && (p.desc_mode & 0x1000)) {
+            // last chunk, block-major across BOTH phases (desc_mode bit 12): block 0 is complete and published a whole
+            // block's worth of MMAs (~1.5 k cycles) before block 1, so its drain is hidden behind block 1's MMAs instead
+            // of stalling the next tile's first chunk
+#ifdef BHSR_TIMING
+            if (dbg) tq = clock64();
+#endif
+            mbar_wait(bar(B_LFULL + sl), l_ph);
+#ifdef BHSR_TIMING
+            if (dbg) t_afull += clock64() - tq;
+#endif
+            tc_fence_after();
             for (int mb = mb_lo; mb < mb_hi; ++mb) {
               if (first_chunk) {
 #ifdef BHSR_TIMING
@@ -326,47 +336,78 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 tc_fence_after();
               }
               if (elect_one()) {
-                const uint32_t a = a_h0 + mb * ASTEP, d = tmem_base + mb * COLS;
-                if (!half) issue_phase3<KSTEPS, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
-                else issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
+                const uint32_t ah = a_h0 + mb * ASTEP, al = a_l0 + mb * ASTEP, d = tmem_base + mb * COLS;
+                if (!half) {
+                  issue_phase3<KSTEPS, 1, ASTEP, DYA>(ah, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
+                  issue_phase3<KSTEPS, 1, ASTEP, DYA>(al, bw[0], bw[1], bw[2], desc_hi, d + 96, 0, IDESC_N, 1u);
+                } else {
+                  issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(ah, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
+                  issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(al, bw[0], bw[1], bw[2], desc_hi, d + 96, 0, IDESC_N, 1u);
+                }
+                umma_commit(bar(B_TFULL + mb));
               }
               __syncwarp();
             }
-          } else {
-            if (elect_one()) {
-              if (!half) issue_phase3<KSTEPS, 2, ASTEP, DYA>(a_h0, bw[0], bw[1], bw[2], desc_hi, tmem_base, tmem_base + COLS, IDESC_WIDE, 1u);
-              else issue_phase3<KSTEPS / 2, 2, ASTEP, DYA>(a_h0, bw[0], bw[1], bw[2], desc_hi, tmem_base, tmem_base + COLS, IDESC_WIDE, 1u);
-            }
+            if (elect_one()) umma_commit(bar(B_HEMPTY + sh));
             __syncwarp();
-          }
-          if (elect_one()) umma_commit(bar(B_HEMPTY + sh));
-          __syncwarp();
-          if (++sh == NS) { sh = 0; h_ph ^= 1; }
-          // ---- lo' activations x W_hi (N = 96) into the correction columns
-#ifdef BHSR_TIMING
-          if (dbg) tq = clock64();
-#endif
-          mbar_wait(bar(B_LFULL + sl), l_ph);
-#ifdef BHSR_TIMING
-          if (dbg) t_afull += clock64() - tq;
-#endif
-          tc_fence_after();
-          if (last_chunk || sel >= 0) {
-            for (int mb = mb_lo; mb < mb_hi; ++mb) {
+            if (++sh == NS) { sh = 0; h_ph ^= 1; }
+          } else {
+            // ---- hi activations x [W_hi | W_lo'] (N = 192) into main + correction columns
+            if (first_chunk || sel >= 0) {
+              for (int mb = mb_lo; mb < mb_hi; ++mb) {
+                if (first_chunk) {
+  #ifdef BHSR_TIMING
+                  if (dbg) tq = clock64();
+  #endif
+                  mbar_wait(bar(B_TEMPTY + mb), t_par ^ 1);
+  #ifdef BHSR_TIMING
+                  if (dbg) t_tempty += clock64() - tq;
+  #endif
+                  tc_fence_after();
+                }
+                if (elect_one()) {
+                  const uint32_t a = a_h0 + mb * ASTEP, d = tmem_base + mb * COLS;
+                  if (!half) issue_phase3<KSTEPS, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
+                  else issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
+                }
+                __syncwarp();
+              }
+            } else {
               if (elect_one()) {
-                const uint32_t a = a_l0 + mb * ASTEP, d = tmem_base + mb * COLS + 96;
-                if (!half) issue_phase3<KSTEPS, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_N, 1u);
-                else issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_N, 1u);
-                if (last_chunk) umma_commit(bar(B_TFULL + mb));
+                if (!half) issue_phase3<KSTEPS, 2, ASTEP, DYA>(a_h0, bw[0], bw[1], bw[2], desc_hi, tmem_base, tmem_base + COLS, IDESC_WIDE, 1u);
+                else issue_phase3<KSTEPS / 2, 2, ASTEP, DYA>(a_h0, bw[0], bw[1], bw[2], desc_hi, tmem_base, tmem_base + COLS, IDESC_WIDE, 1u);
               }
               __syncwarp();
             }
-          } else {
-            if (elect_one()) {
-              if (!half) issue_phase3<KSTEPS, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + 96, tmem_base + COLS + 96, IDESC_N, 1u);
-              else issue_phase3<KSTEPS / 2, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + 96, tmem_base + COLS + 96, IDESC_N, 1u);
-            }
+            if (elect_one()) umma_commit(bar(B_HEMPTY + sh));
             __syncwarp();
+            if (++sh == NS) { sh = 0; h_ph ^= 1; }
+            // ---- lo' activations x W_hi (N = 96) into the correction columns
+  #ifdef BHSR_TIMING
+            if (dbg) tq = clock64();
+  #endif
+            mbar_wait(bar(B_LFULL + sl), l_ph);
+  #ifdef BHSR_TIMING
+            if (dbg) t_afull += clock64() - tq;
+  #endif
+            tc_fence_after();
+            if (last_chunk || sel >= 0) {
+              for (int mb = mb_lo; mb < mb_hi; ++mb) {
+                if (elect_one()) {
+                  const uint32_t a = a_l0 + mb * ASTEP, d = tmem_base + mb * COLS + 96;
+                  if (!half) issue_phase3<KSTEPS, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_N, 1u);
+                  else issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_N, 1u);
+                  if (last_chunk) umma_commit(bar(B_TFULL + mb));
+                }
+                __syncwarp();
+              }
+            } else {
+              if (elect_one()) {
+                if (!half) issue_phase3<KSTEPS, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + 96, tmem_base + COLS + 96, IDESC_N, 1u);
+                else issue_phase3<KSTEPS / 2, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + 96, tmem_base + COLS + 96, IDESC_N, 1u);
+              }
+              __syncwarp();
+            }
           }
           if (elect_one()) {
             if (!WRES) {

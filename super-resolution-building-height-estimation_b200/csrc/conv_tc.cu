@@ -323,7 +323,8 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   {
     static const char* lean = getenv("BHSR_DX_LEAN");    // lean MMA issuer of the exact two-block kernel (desc_mode bit 11)
     if (lean && lean[0] == '1') p.desc_mode |= 0x800;
-    if (lean && lean[0] == '0') p.desc_mode &= ~0x800;
+    if (lean && lean[0] == '2') p.desc_mode |= 0x1800;      // + last chunk block-major across both phases (bit 12)
+    if (lean && lean[0] == '0') p.desc_mode &= ~0x1800;
   }
   if (p.w_resident) return launch_dx_kernel<EXACT, MB, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
   return launch_dx_kernel<EXACT, MB, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);

@@ -656,3 +656,40 @@ def test_realesrgan_generator_step_cuda_graph_matches_eager(dev):
         assert_close(b.cpu().numpy(), a.cpu().numpy(), 1e-3, 1e-5, "parameters after 6 steps")
     assert_close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-3, 1e-4, "generator output after 6 steps")
     assert_close(yeb.cpu().numpy(), yea.cpu().numpy(), 1e-3, 1e-4, "EMA output after 6 steps")
+
+
+def test_rrdbnet_backward_scale2_and_old_names(dev):
+    """Autograd through the pixel_unshuffle front end (scale 2: SR/rrdbnet_arch.py:209-214; a torch view op, so the
+    input gradient flows back through it) and through the ESRGAN-era `OldRRDBNet` names (SR/RRDBNet.py:53-78), both
+    against fp64 autograd of the oracle on a well-conditioned input."""
+    from bhsr import rrdbnet
+    # ---- scale 2
+    sd = synth.rrdbnet_state(num_block=1, seed=31, scale=2)
+    for seed in range(40):
+        rng = np.random.RandomState(500 + seed)
+        x = rng.rand(2, 3, 16, 16).astype(np.float32)
+        wy = rng.standard_normal((2, 3, 32, 32)).astype(np.float32)
+        y_ref, dx_ref, g_ref, zmin = _oracle_grads(sd, x, wy, False, scale=2)
+        if zmin > 2e-6:
+            break
+    net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=2, num_block=1), sd, dev).train()
+    xt = cuda(x, dev).requires_grad_(True)
+    y = net(xt)
+    (y * cuda(wy, dev)).sum().backward()
+    assert_close(y.detach().cpu().numpy(), y_ref, 1e-3, 1e-4, "scale-2 training forward")
+    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+    assert rel(xt.grad.cpu().numpy(), dx_ref) < 2e-4
+    for name, prm in net.named_parameters():
+        assert rel(prm.grad.cpu().numpy(), g_ref[name]) < 2e-4, name
+    # ---- old-style names: same arithmetic, different attribute names
+    new = rrdbnet.RRDBNet(3, 3, scale=4, num_block=1).to(dev).train()
+    old = rrdbnet.OldRRDBNet(in_nc=3, out_nc=3, nf=64, nb=1, gc=32).to(dev).train()
+    with torch.no_grad():
+        for a, b in zip(old.parameters(), new.parameters()):     # same construction order of the children
+            a.copy_(b)
+    xin = torch.rand(1, 3, 8, 8, device=dev)
+    wgt = torch.randn(1, 3, 32, 32, device=dev)
+    (new(xin) * wgt).sum().backward()
+    (old(xin) * wgt).sum().backward()
+    for a, b in zip(old.parameters(), new.parameters()):
+        assert torch.equal(a.grad, b.grad)
