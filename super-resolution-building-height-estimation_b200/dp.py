@@ -190,9 +190,19 @@ class GraphedTrainStep:
         graph B: optimiser step
     The optimiser must be built with `capturable=True` (its step counter lives on the device).  Inputs are copied
     into static buffers before each replay.  Tensors produced inside a graph (the loss) are overwritten by the next
-    replay."""
+    replay.
 
-    def __init__(self, net_g, net, criterion, optimizer, bucket: "FlatGradAllReduce", example, warmup: int = 3):
+    `overlap_smp` (default on, BHSR_TRAIN_OVERLAP=0 disables): inside graph A the smp encoder / decoders (hundreds of
+    small stock-PyTorch kernels that leave most SMs idle) run on a forked stream next to the frozen RRDBNet forward
+    (148-CTA tensor-core kernels); both feed `forward_head`.  Same arithmetic, fewer exposed microseconds."""
+
+    def __init__(self, net_g, net, criterion, optimizer, bucket: "FlatGradAllReduce", example, warmup: int = 3,
+                 overlap_smp: Optional[bool] = None):
+        import os
+        if overlap_smp is None:
+            overlap_smp = os.environ.get("BHSR_TRAIN_OVERLAP", "1") != "0"
+        self.overlap_smp = bool(overlap_smp) and hasattr(net, "forward_smp")
+        self._fork = torch.cuda.Stream() if self.overlap_smp else None
         self.bucket, self.optimizer = bucket, optimizer
         self.static = [t.clone() for t in example]          # lr, height, height_aggre, build, weight, weight_aggre
         self._args = (net_g, net, criterion)
@@ -215,11 +225,23 @@ class GraphedTrainStep:
     def _fwd_bwd(self):
         net_g, net, criterion = self._args
         lr, height, height_aggre, build, weight, weight_aggre = self.static
-        with torch.no_grad():
-            # train.py:244 indexes lr[:, [0, 1, 2]]; a Python index list becomes a host tensor copied to the device,
-            # which a graph capture refuses — the equivalent strided view needs no copy at all
-            hr_fea = net_g.forward_feature(lr[:, :3])
-        height_pred, build_pred, height_pred_aggre = net(lr, hr_fea)
+        if self.overlap_smp:
+            cur = torch.cuda.current_stream()
+            self._fork.wait_stream(cur)
+            with torch.cuda.stream(self._fork):
+                height_fea, build_fea = net.forward_smp(lr)
+            with torch.no_grad():
+                hr_fea = net_g.forward_feature(lr[:, :3])
+            cur.wait_stream(self._fork)
+            height_fea.record_stream(cur)
+            build_fea.record_stream(cur)
+            height_pred, build_pred, height_pred_aggre = net.forward_head(height_fea, build_fea, hr_fea)
+        else:
+            with torch.no_grad():
+                # train.py:244 indexes lr[:, [0, 1, 2]]; a Python index list becomes a host tensor copied to the device,
+                # which a graph capture refuses — the equivalent strided view needs no copy at all
+                hr_fea = net_g.forward_feature(lr[:, :3])
+            height_pred, build_pred, height_pred_aggre = net(lr, hr_fea)
         loss = criterion[0](height_pred.squeeze(1), height, weight) + \
             criterion[1](height_pred_aggre.squeeze(1), height_aggre, weight_aggre) + \
             criterion[2](build_pred, build, weight)

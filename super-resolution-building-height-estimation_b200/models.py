@@ -59,6 +59,24 @@ class SRRegress_Cls_feature(torch.nn.Module):
             return height, build, height_aggre
         return height, build
 
+    def forward_smp(self, x):
+        """The third-party part of `forward` alone: encoder + both U-Net decoders -> (height_fea, build_fea).  It does not
+        depend on `super_fea`, so a caller may run it on a second stream next to the frozen RRDBNet forward
+        (dp.GraphedTrainStep); `forward_head` is the rest."""
+        encode_fea = self.encoder(x)
+        return self.decoder1(*encode_fea), self.decoder2(*encode_fea)
+
+    def forward_head(self, height_fea, build_fea, super_fea):
+        """`forward` after `forward_smp`: hrfeat, aggre_height, reg, seg (mymodels.py:276-293, same arithmetic)."""
+        super_fea = self.hrfeat(super_fea)
+        if self.isaggre:
+            height_aggre = self._aggre(height_fea)
+        height = self.reg(height_fea, super_fea)
+        build = self.seg(build_fea, super_fea)
+        if self.isaggre:
+            return height, build, height_aggre
+        return height, build
+
     def forward_unsup(self, x, super_fea):
         """mymodels.py:295-312: height only, squeezed."""
         encode_fea = self.encoder(x)

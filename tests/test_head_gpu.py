@@ -468,3 +468,41 @@ def test_epoch_harness_two_epochs(dev, tmp_path):
     assert set(ck) == {"epoch", "state_dict", "log_vars", "best_acc"} and ck["epoch"] == 2      # train.py:202-208
     more = dp.fit(net, net_g, train, val, str(tmp_path), epochs=3, init_lr=1e-3, device=dev)    # resumes at epoch 3
     assert [r["epoch"] for r in more] == [3]
+
+
+def test_graphed_train_step_overlap_matches_serial(dev):
+    """dp.GraphedTrainStep with the smp encoder / decoders forked onto a second stream next to the frozen RRDBNet
+    forward (`overlap_smp`) against the single-stream capture and against `net.forward`: `forward_head(forward_smp(x))`
+    is the same arithmetic as `forward` (mymodels.py:270-293), and three replayed steps give the same losses."""
+    import copy
+    from bhsr import dp
+    from bhsr.models import SRRegress_Cls_feature
+    from bhsr.rrdbnet import RRDBNet
+    torch.manual_seed(0)
+    net_g = RRDBNet(3, 3, scale=4, num_feat=64, num_block=1, num_grow_ch=32).to(dev).eval()
+    for p in net_g.parameters():
+        p.requires_grad = False
+    net0 = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64, super_mid=16,
+                                 upscale=4, isaggre=True, chans_build=7).to(dev)
+    x = torch.from_numpy(synth.tiles(2, 8, seed=3)).to(dev)
+    labels = dp.synthetic_labels(2, dev, seed=4)
+    net0.eval()
+    with torch.no_grad():
+        hr = net_g.forward_feature(x[:, :3])
+        a = net0(x, hr)
+        b = net0.forward_head(*net0.forward_smp(x), hr)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    losses = []
+    for overlap in (False, True):
+        net = copy.deepcopy(net0).train()
+        crit = [dp.MSE_adapt_weight(0.0, dev), dp.MSE_adapt_weight(0.0, dev), dp.CE_DICE_adapt_weight(0.0, dev)]
+        params = list(net.parameters()) + [c.log_var for c in crit]
+        opt = torch.optim.Adam([{"params": list(net.parameters())}, {"params": [c.log_var for c in crit], "name": "lossweight"}],
+                               lr=1e-3, weight_decay=1e-4, capturable=True)
+        bucket = dp.FlatGradAllReduce(params)
+        step = dp.GraphedTrainStep(net_g, net, crit, opt, bucket, (x, *labels), warmup=2, overlap_smp=overlap)
+        assert step.overlap_smp == overlap
+        losses.append([float(step(x, *labels)) for _ in range(3)])
+    np.testing.assert_allclose(losses[1], losses[0], rtol=2e-3)
+    assert losses[0][-1] < losses[0][0]
