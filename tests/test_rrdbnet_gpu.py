@@ -693,3 +693,29 @@ def test_rrdbnet_backward_scale2_and_old_names(dev):
     (old(xin) * wgt).sum().backward()
     for a, b in zip(old.parameters(), new.parameters()):
         assert torch.equal(a.grad, b.grad)
+
+
+def test_rrdbnet_23block_backward_vs_oracle_autograd(dev):
+    """The full-depth generator (23 RRDBs = 345 trunk convs) under autograd, B = 2 on 32x32 inputs, against fp64 autograd
+    of the oracle: output within the north-star tolerance, every one of the 702 parameter gradients and the input gradient
+    within 2e-2 relative L2 — the bound a handful of LeakyReLU masks that flip between fp32 and fp64 allow (see
+    test_rrdbnet_backward_vs_oracle_autograd); the median gradient error is required to stay at the kernels' own level."""
+    from bhsr import rrdbnet
+    sd = synth.rrdbnet_state(num_block=23, seed=123)
+    rng = np.random.RandomState(77)
+    x = rng.rand(2, 3, 32, 32).astype(np.float32)
+    wy = rng.standard_normal((2, 3, 128, 128)).astype(np.float32)
+    y_ref, dx_ref, g_ref, zmin = _oracle_grads(sd, x, wy, False)
+    net = load_np_state(rrdbnet.RRDBNet(3, 3, scale=4, num_block=23), sd, dev).train()
+    xt = cuda(x, dev).requires_grad_(True)
+    y = net(xt)
+    (y * cuda(wy, dev)).sum().backward()
+    assert_close(y.detach().cpu().numpy(), y_ref, 1e-3, 1e-4, "23-block training-path forward")
+    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+    errs = {"dL/dx": rel(xt.grad.cpu().numpy(), dx_ref)}
+    for name, prm in net.named_parameters():
+        errs[name] = rel(prm.grad.cpu().numpy(), g_ref[name])
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    med = float(np.median(list(errs.values())))
+    print(f"RRDBNet-23 backward: {len(errs)} gradients, median rel-L2 {med:.2e}, worst {worst[1]:.2e} ({worst[0]}), min|z| {zmin:.1e}")
+    assert len(errs) == 703 and worst[1] < 2e-2 and med < 2e-3, (worst, med)
