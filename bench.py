@@ -326,10 +326,13 @@ def train_leg(args, dev, dist, world, rank, K, W, peak):
 
             def gstep(i):
                 h, h_aggre, build, w, w_aggre = labels[i % 2]
-                box["loss"] = graphed(xs[i % 2], h, h_aggre, build, w, w_aggre)
+                # the next batch's tiles are announced so that their frozen features are computed during this step
+                box["loss"] = graphed(xs[i % 2], h, h_aggre, build, w, w_aggre, lr_next=xs[(i + 1) % 2])
 
             ms = timed_steps(gstep)
-            launch = "cuda-graph (fwd+bwd graph, eager NCCL all-reduce, optimiser graph)"
+            launch = ("cuda-graph (fwd+bwd graph with the smp part and the next batch's frozen RRDBNet forward on forked streams, "
+                      "eager NCCL all-reduce, optimiser graph)" if graphed.prefetch else
+                      "cuda-graph (fwd+bwd graph, eager NCCL all-reduce, optimiser graph)")
         except Exception as e:  # capture refused: keep the eager number, say why
             launch = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
     loss = float(box["loss"].item())

@@ -194,15 +194,28 @@ class GraphedTrainStep:
 
     `overlap_smp` (default on, BHSR_TRAIN_OVERLAP=0 disables): inside graph A the smp encoder / decoders (hundreds of
     small stock-PyTorch kernels that leave most SMs idle) run on a forked stream next to the frozen RRDBNet forward
-    (148-CTA tensor-core kernels); both feed `forward_head`.  Same arithmetic, fewer exposed microseconds."""
+    (148-CTA tensor-core kernels); both feed `forward_head`.  Same arithmetic, fewer exposed microseconds.
+
+    `prefetch` ("RRDBNet is frozen, so its forward for step t+1 is independent of step t's weight update"):
+    call the step with `lr_next=<the next batch's tiles>` and the frozen features of the NEXT batch are computed on a
+    forked stream during THIS step's head forward / backward (a second captured graph; the features wait in a static
+    buffer).  A call whose `lr` was not announced by the previous call computes its features first.  Every step still
+    runs exactly one RRDBNet forward.  OPT-IN (prefetch=True / BHSR_TRAIN_PREFETCH=1): measured SLOWER on a B200
+    (62.9 -> 66.9 ms per step, same losses): the trunk's persistent CTAs take a whole SM each (352 threads x 168
+    registers, 227 KB of shared memory), so while one of its kernels is resident the backward's kernels queue behind
+    it instead of filling idle SMs, and the critical path lengthens by more than the 15 ms it sheds."""
 
     def __init__(self, net_g, net, criterion, optimizer, bucket: "FlatGradAllReduce", example, warmup: int = 3,
-                 overlap_smp: Optional[bool] = None):
+                 overlap_smp: Optional[bool] = None, prefetch: Optional[bool] = None):
         import os
         if overlap_smp is None:
             overlap_smp = os.environ.get("BHSR_TRAIN_OVERLAP", "1") != "0"
+        if prefetch is None:
+            prefetch = os.environ.get("BHSR_TRAIN_PREFETCH", "0") == "1"
         self.overlap_smp = bool(overlap_smp) and hasattr(net, "forward_smp")
+        self.prefetch = bool(prefetch) and self.overlap_smp
         self._fork = torch.cuda.Stream() if self.overlap_smp else None
+        self._fork2 = torch.cuda.Stream() if self.prefetch else None
         self.bucket, self.optimizer = bucket, optimizer
         self.static = [t.clone() for t in example]          # lr, height, height_aggre, build, weight, weight_aggre
         self._args = (net_g, net, criterion)
@@ -221,6 +234,19 @@ class GraphedTrainStep:
         self.graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_b):
             optimizer.step()
+        self.graph_p = None            # pipelined variant of graph A, captured on first use
+        self._announced = None         # (data_ptr, version) of the batch whose features sit in self._hr_next
+
+    def _head_loss_backward(self, height_fea, build_fea, hr_fea):
+        net_g, net, criterion = self._args
+        lr, height, height_aggre, build, weight, weight_aggre = self.static
+        height_pred, build_pred, height_pred_aggre = net.forward_head(height_fea, build_fea, hr_fea)
+        loss = criterion[0](height_pred.squeeze(1), height, weight) + \
+            criterion[1](height_pred_aggre.squeeze(1), height_aggre, weight_aggre) + \
+            criterion[2](build_pred, build, weight)
+        self.bucket.zero_()
+        loss.backward()
+        return loss.detach()
 
     def _fwd_bwd(self):
         net_g, net, criterion = self._args
@@ -235,13 +261,12 @@ class GraphedTrainStep:
             cur.wait_stream(self._fork)
             height_fea.record_stream(cur)
             build_fea.record_stream(cur)
-            height_pred, build_pred, height_pred_aggre = net.forward_head(height_fea, build_fea, hr_fea)
-        else:
-            with torch.no_grad():
-                # train.py:244 indexes lr[:, [0, 1, 2]]; a Python index list becomes a host tensor copied to the device,
-                # which a graph capture refuses — the equivalent strided view needs no copy at all
-                hr_fea = net_g.forward_feature(lr[:, :3])
-            height_pred, build_pred, height_pred_aggre = net(lr, hr_fea)
+            return self._head_loss_backward(height_fea, build_fea, hr_fea)
+        with torch.no_grad():
+            # train.py:244 indexes lr[:, [0, 1, 2]]; a Python index list becomes a host tensor copied to the device,
+            # which a graph capture refuses — the equivalent strided view needs no copy at all
+            hr_fea = net_g.forward_feature(lr[:, :3])
+        height_pred, build_pred, height_pred_aggre = net(lr, hr_fea)
         loss = criterion[0](height_pred.squeeze(1), height, weight) + \
             criterion[1](height_pred_aggre.squeeze(1), height_aggre, weight_aggre) + \
             criterion[2](build_pred, build, weight)
@@ -249,14 +274,74 @@ class GraphedTrainStep:
         loss.backward()
         return loss.detach()
 
-    def __call__(self, lr, height, height_aggre, build, weight, weight_aggre) -> torch.Tensor:
+    def _fwd_bwd_pipelined(self):
+        """Graph A with the RRDBNet forward taken out of the critical path: this step's features were computed during
+        the previous replay (self._hr_next); the features of `self._lr_next` are computed on a forked stream now."""
+        net_g, net, _ = self._args
+        lr = self.static[0]
+        cur = torch.cuda.current_stream()
+        self._hr_cur.copy_(self._hr_next)                    # before the forked stream overwrites it
+        self._fork2.wait_stream(cur)
+        with torch.cuda.stream(self._fork2):
+            with torch.no_grad():
+                self._hr_next.copy_(net_g.forward_feature(self._lr_next[:, :3]))
+        self._fork.wait_stream(cur)
+        with torch.cuda.stream(self._fork):
+            height_fea, build_fea = net.forward_smp(lr)
+        cur.wait_stream(self._fork)
+        height_fea.record_stream(cur)
+        build_fea.record_stream(cur)
+        loss = self._head_loss_backward(height_fea, build_fea, self._hr_cur)
+        cur.wait_stream(self._fork2)
+        return loss
+
+    def _capture_pipelined(self):
+        net_g = self._args[0]
+        lr = self.static[0]
+        with torch.no_grad():
+            hr = net_g.forward_feature(lr[:, :3])
+        self._hr_cur = torch.empty_like(hr)
+        self._hr_next = hr.clone()
+        self._lr_next = lr.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        state = [p.detach().clone() for p in self._args[1].parameters()]   # the warm-up pass below must not train
+        bufs = [b.detach().clone() for b in self._args[1].buffers()]
+        with torch.cuda.stream(side):
+            self._fwd_bwd_pipelined()                        # warm-up of the forked streams outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for p, q in zip(self._args[1].parameters(), state):
+                p.copy_(q)
+            for b, q in zip(self._args[1].buffers(), bufs):
+                b.copy_(q)
+        self.graph_p = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_p):
+            self.loss_p = self._fwd_bwd_pipelined()
+
+    def __call__(self, lr, height, height_aggre, build, weight, weight_aggre, lr_next=None) -> torch.Tensor:
         for dst, src in zip(self.static, (lr, height, height_aggre, build, weight, weight_aggre)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        self.graph_a.replay()
+        if self.prefetch and lr_next is not None:
+            if self.graph_p is None:
+                self._capture_pipelined()
+            tag = (lr.data_ptr(), lr._version)
+            if self._announced != tag:                       # not prefetched: compute this batch's features now
+                with torch.no_grad():
+                    self._hr_next.copy_(self._args[0].forward_feature(self.static[0][:, :3]))
+            self._lr_next.copy_(lr_next, non_blocking=True)
+            self._announced = (lr_next.data_ptr(), lr_next._version)
+            self.graph_p.replay()
+            loss = self.loss_p
+        else:
+            self._announced = None
+            self.graph_a.replay()
+            loss = self.loss
         self.bucket.all_reduce()
         self.graph_b.replay()
-        return self.loss
+        return loss
 
 
 @torch.no_grad()

@@ -494,15 +494,24 @@ def test_graphed_train_step_overlap_matches_serial(dev):
     for u, v in zip(a, b):
         assert torch.equal(u, v)
     losses = []
-    for overlap in (False, True):
+    x2 = torch.from_numpy(synth.tiles(2, 8, seed=9)).to(dev)
+    for overlap, prefetch in ((False, False), (True, False), (True, True)):
         net = copy.deepcopy(net0).train()
         crit = [dp.MSE_adapt_weight(0.0, dev), dp.MSE_adapt_weight(0.0, dev), dp.CE_DICE_adapt_weight(0.0, dev)]
         params = list(net.parameters()) + [c.log_var for c in crit]
         opt = torch.optim.Adam([{"params": list(net.parameters())}, {"params": [c.log_var for c in crit], "name": "lossweight"}],
                                lr=1e-3, weight_decay=1e-4, capturable=True)
         bucket = dp.FlatGradAllReduce(params)
-        step = dp.GraphedTrainStep(net_g, net, crit, opt, bucket, (x, *labels), warmup=2, overlap_smp=overlap)
-        assert step.overlap_smp == overlap
-        losses.append([float(step(x, *labels)) for _ in range(3)])
+        step = dp.GraphedTrainStep(net_g, net, crit, opt, bucket, (x, *labels), warmup=2, overlap_smp=overlap,
+                                   prefetch=prefetch)
+        assert step.overlap_smp == overlap and step.prefetch == prefetch
+        # batches alternate x, x2, x, x2: with prefetch the next batch's tiles are announced, so its frozen features are
+        # computed during the current step (the first call, and any unannounced batch, computes them up front)
+        seq = [x, x2, x, x2]
+        out = []
+        for i, xb in enumerate(seq):
+            nxt = seq[i + 1] if prefetch and i + 1 < len(seq) else None
+            out.append(float(step(xb, *labels, lr_next=nxt)))
+        losses.append(out)
     np.testing.assert_allclose(losses[1], losses[0], rtol=2e-3)
-    assert losses[0][-1] < losses[0][0]
+    np.testing.assert_allclose(losses[2], losses[0], rtol=2e-3)
