@@ -280,6 +280,8 @@ def train_leg(args, dev, dist, world, rank, K, W, peak):
     net = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64, super_mid=16,
                                 upscale=4, isaggre=True, chans_build=7).to(dev).train()
     dp.broadcast_module(net)
+    if os.environ.get("BHSR_SMP_NHWC", "1") != "0":      # stock-PyTorch encoder / decoders in channels_last (see models.py)
+        net.smp_channels_last()
     crit = [dp.MSE_adapt_weight(0.0, dev), dp.MSE_adapt_weight(0.0, dev), dp.CE_DICE_adapt_weight(0.0, dev)]
     params = list(net.parameters()) + [c.log_var for c in crit]
     opt = torch.optim.Adam([{"params": list(net.parameters())},

@@ -59,10 +59,25 @@ class SRRegress_Cls_feature(torch.nn.Module):
             return height, build, height_aggre
         return height, build
 
+    def smp_channels_last(self, enable: bool = True):
+        """Run the third-party encoder / decoders in torch.channels_last (NHWC): cuDNN then needs no NCHW<->NHWC
+        conversion kernels around its convolutions and takes its own depthwise-conv weight-gradient kernels instead of
+        PyTorch's native NCHW one.  Parameters keep their values and state_dict keys; only strides change.  The decoder
+        outputs are made NCHW-contiguous again for the head kernels.  Opt-in deployment choice for the stock-PyTorch
+        part of the model; affects `forward_smp` (and therefore dp.GraphedTrainStep) only."""
+        fmt = torch.channels_last if enable else torch.contiguous_format
+        for m in (self.encoder, self.decoder1, self.decoder2):
+            m.to(memory_format=fmt)
+        self._smp_nhwc = bool(enable)
+        return self
+
     def forward_smp(self, x):
         """The third-party part of `forward` alone: encoder + both U-Net decoders -> (height_fea, build_fea).  It does not
         depend on `super_fea`, so a caller may run it on a second stream next to the frozen RRDBNet forward
         (dp.GraphedTrainStep); `forward_head` is the rest."""
+        if getattr(self, "_smp_nhwc", False):
+            encode_fea = self.encoder(x.contiguous(memory_format=torch.channels_last))
+            return self.decoder1(*encode_fea).contiguous(), self.decoder2(*encode_fea).contiguous()
         encode_fea = self.encoder(x)
         return self.decoder1(*encode_fea), self.decoder2(*encode_fea)
 

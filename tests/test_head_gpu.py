@@ -515,3 +515,26 @@ def test_graphed_train_step_overlap_matches_serial(dev):
         losses.append(out)
     np.testing.assert_allclose(losses[1], losses[0], rtol=2e-3)
     np.testing.assert_allclose(losses[2], losses[0], rtol=2e-3)
+
+
+def test_smp_channels_last_matches_nchw(dev):
+    """SRRegress_Cls_feature.smp_channels_last(): the stock-PyTorch encoder / decoders in NHWC give the same decoder
+    features (to cuDNN algorithm noise) and the same state_dict keys; the head sees NCHW-contiguous tensors."""
+    from bhsr.models import SRRegress_Cls_feature
+    torch.manual_seed(0)
+    net = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64, super_mid=16,
+                                upscale=4, isaggre=True, chans_build=7).to(dev).eval()
+    keys = list(net.state_dict())
+    x = torch.from_numpy(synth.tiles(2, 8, seed=5)).to(dev)
+    with torch.no_grad():
+        a = net.forward_smp(x)
+        net.smp_channels_last()
+        b = net.forward_smp(x)
+        net.smp_channels_last(False)
+        c = net.forward_smp(x)
+    assert list(net.state_dict()) == keys
+    for u, v, w in zip(a, b, c):
+        assert v.is_contiguous() and v.shape == u.shape
+        # cuDNN convolutions run in TF32 by default (as in the reference): another layout picks other algorithms
+        assert_close(v.cpu().numpy(), u.cpu().numpy(), 2e-2, 2e-3, "channels_last decoder features")
+        assert_close(w.cpu().numpy(), u.cpu().numpy(), 1e-5, 1e-6, "back to NCHW")
