@@ -350,9 +350,32 @@ def predict_shard(net_g, net, tiles: torch.Tensor) -> Tuple[torch.Tensor, torch.
     fused post-processing kernel (`bhsr_predict_postproc`): height -> max(h, 0), round(h * 10) -> uint16; height
     levels -> softmax over the K channels, round(p * 255) -> uint16.  Returns (uint16 [B,1,256,256], uint16
     [B,K,256,256]) — the reference's numbers, one pass over the head's outputs."""
-    hr_fea = net_g.forward_feature(tiles[:, :3])
-    ypred, build_pred = net(tiles, hr_fea)[:2]
+    if hasattr(net, "forward_smp") and tiles.is_cuda and not torch.cuda.is_current_stream_capturing():
+        # the stock-PyTorch encoder / decoders (small kernels) on a forked stream next to the frozen RRDBNet forward
+        cur = torch.cuda.current_stream()
+        side = _side_stream(tiles.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            height_fea, build_fea = net.forward_smp(tiles)
+        hr_fea = net_g.forward_feature(tiles[:, :3])
+        cur.wait_stream(side)
+        height_fea.record_stream(cur)
+        build_fea.record_stream(cur)
+        ypred, build_pred = net.forward_head(height_fea, build_fea, hr_fea)[:2]
+    else:
+        hr_fea = net_g.forward_feature(tiles[:, :3])
+        ypred, build_pred = net(tiles, hr_fea)[:2]
     return predict_postprocess(ypred, build_pred)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 @torch.no_grad()

@@ -88,6 +88,9 @@ def main():
     net = SRRegress_Cls_feature("efficientnet-b4", encoder_weights=None, in_channels=8, super_in=64, super_mid=16,
                                 upscale=4, isaggre=isaggre, chans_build=7).to(dev)
 
+    if os.environ.get("BHSR_SMP_NHWC", "1") != "0":
+        net.smp_channels_last()
+
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
