@@ -361,6 +361,73 @@ __device__ __forceinline__ void finish_planes32_rolled(const ConvTcKernelParams&
   __syncwarp();   // the staging tile is rewritten by this warp's next block
 }
 
+// 16-channel version of finish_planes32_rolled (conv_dx_kernel<..., NOUT = 16>): 64-byte staging rows (chunk index
+// XOR-ed with (row >> 1) & 3: conflict-free both ways), two rolled iterations of 16 rows x two 8-channel chunks.
+__device__ __forceinline__ void finish_planes16_rolled(const ConvTcKernelParams& p, const float (&v)[32], bool valid,
+                                                       size_t in_pix, size_t out_pix, int lane, uint8_t* stg,
+                                                       const float* s_bias, const float* s_scale) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<float4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+        make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  const uint32_t opix32 = valid ? static_cast<uint32_t>(out_pix) : 0xFFFFFFFFu;
+  const uint32_t ipix32 = static_cast<uint32_t>(in_pix);
+  const int cg = lane & 1;
+  float b8[8], s8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    b8[j] = s_bias[cg * 8 + j];
+    s8[j] = s_scale[cg * 8 + j];
+  }
+  const bool chan_ok = cg * 8 < p.cout_valid;
+  const int epi = p.epilogue;
+  const float lo_mul = p.lo_mul;
+  __syncwarp();
+#pragma unroll 1
+  for (int it = 0; it < 2; ++it) {
+    const int r = it * 16 + (lane >> 1);
+    const uint8_t* rowp = stg + r * 64;
+    const int sw = (r >> 1) & 3;
+    const float4 lo4 = *reinterpret_cast<const float4*>(rowp + (((2 * cg) ^ sw) << 4));
+    const float4 hi4 = *reinterpret_cast<const float4*>(rowp + (((2 * cg + 1) ^ sw) << 4));
+    const uint32_t op = __shfl_sync(0xffffffffu, opix32, r);
+    const uint32_t ip = __shfl_sync(0xffffffffu, ipix32, r);
+    float x[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], s8[j], b8[j]);
+    if (epi & BHSR_EPI_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = lrelu02(x[j]);
+    }
+    const bool ok = (op != 0xFFFFFFFFu) && chan_ok;
+    if (ok) {
+      if (epi & BHSR_EPI_RES1)
+        add_residual8(x, p.alpha1, p.res1_hi, p.res1_lo, static_cast<size_t>(ip) * p.res1_ctot + p.res1_choff + cg * 8);
+      if (epi & BHSR_EPI_RES2)
+        add_residual8(x, p.alpha2, p.res2_hi, p.res2_lo, static_cast<size_t>(ip) * p.res2_ctot + p.res2_choff + cg * 8);
+    }
+    if (epi & BHSR_EPI_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+    if (ok) {
+      __align__(16) __half2 hh[4];
+      __align__(16) __half2 ll[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 h2 = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+        const float2 back = __half22float2(h2);
+        hh[j] = h2;
+        ll[j] = __floats2half2_rn((x[2 * j] - back.x) * lo_mul, (x[2 * j + 1] - back.y) * lo_mul);
+      }
+      const size_t off = static_cast<size_t>(op) * p.out_ctot + p.out_choff + cg * 8;
+      *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hh);
+      if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(ll);
+    }
+  }
+  __syncwarp();
+}
+
 // Work item `it` of this CTA: a whole tile (sel = -1) or, in the split last round, one block of it.
 __device__ __forceinline__ bool dx_item_at(const ConvTcKernelParams& p, int it, int idx, int cnt, int& tile,
                                            int& sel) {

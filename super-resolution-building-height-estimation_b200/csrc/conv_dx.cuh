@@ -83,7 +83,7 @@ __device__ __forceinline__ void issue_phase3(uint32_t a_lo, uint32_t b0, uint32_
   }
 }
 
-template <bool EXACT, int MB, bool WRES, bool PAIR>
+template <bool EXACT, int MB, bool WRES, bool PAIR, int NOUT = 32>
 __global__ void __launch_bounds__(kDxThreads, 1)
 conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo,
@@ -94,7 +94,11 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   constexpr int RB16 = RB / 16;
   constexpr int KSTEPS = CH / 16;
   constexpr int NPART = EXACT ? 2 : 1;
-  constexpr int COLS = 96 * NPART;                 // weight rows per window row = TMEM columns per block
+  // NOUT = 16 (round 2): the head's 16-channel layers (SR/HRfuse.py:164-190) stop paying for 32 padded outputs —
+  // half the MMA columns, half the accumulator drain, half the epilogue; exact numerics, single CTA only
+  static_assert(NOUT == 32 || (NOUT == 16 && EXACT && !PAIR), "16 outputs: exact numerics, single CTA");
+  constexpr int G3 = 3 * NOUT;                      // the three dx groups of one part
+  constexpr int COLS = G3 * NPART;                  // weight rows per window row = TMEM columns per block
   // one (chunk, dy) weight slab: 12288 B; in a CTA pair this CTA keeps 144 of the 192 rows:
   // X = its half of the wide operand (96 rows: W_hi in the even CTA, W_lo' in the odd one, couts in
   // halves of 16: row = half*48 + dx*16 + cout%16), Y = W_hi half `rank` (48 rows) for the lo' phase
@@ -103,11 +107,11 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   constexpr uint32_t W_Y16 = PAIR ? ((96 * RB) >> 4) : 0;   // descriptor units from X to Y
   constexpr int TILE = G::kTileBytes;              // one plane of one halo tile
   constexpr int A_TX = G::kTileBytesRaw;
-  constexpr int NSLOT = EXACT ? 2 : 4;             // accumulator blocks in TMEM (192 / 96 columns each)
+  constexpr int NSLOT = (EXACT && NOUT == 32) ? 2 : 4;   // accumulator blocks in TMEM (192 / 96 columns each)
   constexpr int S_OUT = kDxBlk * MB;               // valid output rows per tile
   static_assert(NSLOT * COLS <= 512, "TMEM overflow");
   constexpr uint32_t IDESC_WIDE = make_idesc_f16(COLS, PAIR ? 256 : 128);
-  constexpr uint32_t IDESC_N = make_idesc_f16(96, PAIR ? 256 : 128);
+  constexpr uint32_t IDESC_N = make_idesc_f16(G3, PAIR ? 256 : 128);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -156,7 +160,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
     if (EXACT) tma_prefetch_desc(&tm_a_lo);
     tma_prefetch_desc(&tm_w);
   }
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < NOUT) {
     s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
     s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
   }
@@ -253,12 +257,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         if (WRES) break;
       }
     }
-  } else if (EXACT && !PAIR && MB == 2 && (p.desc_mode & 0x800) && warp == kDxWarpMma) {
+  } else if (EXACT && !PAIR && MB == 2 && NOUT == 32 && (p.desc_mode & 0x800) && warp == kDxWarpMma) {
     // ------------------------------------------------ MMA issuer, lean form (round 2, Finding 5): per chunk and phase
     // one blocking wait, ONE asm block with every MMA of the phase (3 window rows x blocks x k-steps) and one commit; no
     // probes, no vote / reduce.  Block-major only where the two-slot accumulator hand-over needs it: the first chunk's
     // hi phase waits for each block's drain, the last chunk's lo' phase publishes each block as soon as it is complete.
-    if constexpr (EXACT && !PAIR && MB == 2) {
+    if constexpr (EXACT && !PAIR && MB == 2 && NOUT == 32) {
       const uint64_t desc0 = make_kmajor_desc<RB>(0);
       const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
       const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
@@ -339,10 +343,10 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                 const uint32_t ah = a_h0 + mb * ASTEP, al = a_l0 + mb * ASTEP, d = tmem_base + mb * COLS;
                 if (!half) {
                   issue_phase3<KSTEPS, 1, ASTEP, DYA>(ah, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
-                  issue_phase3<KSTEPS, 1, ASTEP, DYA>(al, bw[0], bw[1], bw[2], desc_hi, d + 96, 0, IDESC_N, 1u);
+                  issue_phase3<KSTEPS, 1, ASTEP, DYA>(al, bw[0], bw[1], bw[2], desc_hi, d + G3, 0, IDESC_N, 1u);
                 } else {
                   issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(ah, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_WIDE, c > 0 ? 1u : 0u);
-                  issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(al, bw[0], bw[1], bw[2], desc_hi, d + 96, 0, IDESC_N, 1u);
+                  issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(al, bw[0], bw[1], bw[2], desc_hi, d + G3, 0, IDESC_N, 1u);
                 }
                 umma_commit(bar(B_TFULL + mb));
               }
@@ -394,7 +398,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             if (last_chunk || sel >= 0) {
               for (int mb = mb_lo; mb < mb_hi; ++mb) {
                 if (elect_one()) {
-                  const uint32_t a = a_l0 + mb * ASTEP, d = tmem_base + mb * COLS + 96;
+                  const uint32_t a = a_l0 + mb * ASTEP, d = tmem_base + mb * COLS + G3;
                   if (!half) issue_phase3<KSTEPS, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_N, 1u);
                   else issue_phase3<KSTEPS / 2, 1, ASTEP, DYA>(a, bw[0], bw[1], bw[2], desc_hi, d, 0, IDESC_N, 1u);
                   if (last_chunk) umma_commit(bar(B_TFULL + mb));
@@ -403,8 +407,8 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
               }
             } else {
               if (elect_one()) {
-                if (!half) issue_phase3<KSTEPS, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + 96, tmem_base + COLS + 96, IDESC_N, 1u);
-                else issue_phase3<KSTEPS / 2, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + 96, tmem_base + COLS + 96, IDESC_N, 1u);
+                if (!half) issue_phase3<KSTEPS, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + G3, tmem_base + COLS + G3, IDESC_N, 1u);
+                else issue_phase3<KSTEPS / 2, 2, ASTEP, DYA>(a_l0, bw[0], bw[1], bw[2], desc_hi, tmem_base + G3, tmem_base + COLS + G3, IDESC_N, 1u);
               }
               __syncwarp();
             }
@@ -618,7 +622,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                   for (int g = 0; g < 3; ++g) {
                     const uint32_t r = issue_dx<KST, 1, 0, PAIR>(
                         a_l0 + (g * kPitch + mb * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4) + W_Y16, desc_hi,
-                        acc0 + mb * COLS + 96, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
+                        acc0 + mb * COLS + G3, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
                         nbar[g], npar[g]);
                     if (mb == mb_hi - 1) okbits |= (r & 1u) | ((r >> 1) << (1 + g));
                   }
@@ -636,13 +640,13 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                   uint32_t r;
                   if (pair || MB == 1)
                     r = issue_dx<KST, MB, ASTEP, PAIR>(
-                        a_l0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4) + W_Y16, desc_hi, acc0 + 96,
-                        acc0 + COLS + 96, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next), nbar[g],
+                        a_l0 + g * kPitch * RB16, b0 + wsl[g] * (W_SLAB >> 4) + W_Y16, desc_hi, acc0 + G3,
+                        acc0 + COLS + G3, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next), nbar[g],
                         npar[g]);
                   else
                     r = issue_dx<KST, 1, 0, PAIR>(
                         a_l0 + (g * kPitch + mb_lo * kDxBlk) * RB16, b0 + wsl[g] * (W_SLAB >> 4) + W_Y16, desc_hi,
-                        acc0 + mb_lo * COLS + 96, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
+                        acc0 + mb_lo * COLS + G3, 0, IDESC_N, 1u, bar_h_next, static_cast<uint32_t>(h_ph_next),
                         nbar[g], npar[g]);
                   okbits |= (r & 1u) | ((r >> 1) << (1 + g));
                 }
@@ -734,24 +738,37 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             }
             return;
           }
-          uint32_t raw[32];
-          tmem_ld_32x32(t_row + col, raw);
-          if (EXACT) {
-            uint32_t rawl[32];
-            tmem_ld_32x32(t_row + 96 + col, rawl);
+          if constexpr (NOUT == 16) {
+            uint32_t raw[16], rawl[16];
+            tmem_ld_32x16(t_row + col, raw);
+            tmem_ld_32x16(t_row + G3 + col, rawl);
             tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
+            for (int jj = 0; jj < 16; ++jj) {
               dst[jj] = fmaf(__uint_as_float(rawl[jj]), 1.f / 2048.f, __uint_as_float(raw[jj]));
+              dst[16 + jj] = 0.f;
+            }
+            return;
           } else {
-            tmem_ld_wait();
+            uint32_t raw[32];
+            tmem_ld_32x32(t_row + col, raw);
+            if (EXACT) {
+              uint32_t rawl[32];
+              tmem_ld_32x32(t_row + G3 + col, rawl);
+              tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) dst[jj] = __uint_as_float(raw[jj]);
+              for (int jj = 0; jj < 32; ++jj)
+                dst[jj] = fmaf(__uint_as_float(rawl[jj]), 1.f / 2048.f, __uint_as_float(raw[jj]));
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) dst[jj] = __uint_as_float(raw[jj]);
+            }
           }
         };
         drain(0, v0);
-        drain(32, v1);
-        drain(64, v2);
+        drain(NOUT, v1);
+        drain(2 * NOUT, v2);
         tc_fence_before();
         if (PAIR) mbar_arrive_leader(bar(B_TEMPTY + slot)); else mbar_arrive(bar(B_TEMPTY + slot));
 #ifdef BHSR_TIMING
@@ -793,19 +810,19 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         float* xb = s_xchg + ((grp * 2 + xpar) * 4) * 64;
         if (lane == 31) {
 #pragma unroll
-          for (int jj = 0; jj < 32; jj += 4)
+          for (int jj = 0; jj < NOUT; jj += 4)
             *reinterpret_cast<float4*>(xb + q * 64 + jj) = make_float4(v0[jj], v0[jj + 1], v0[jj + 2], v0[jj + 3]);
         }
         if (lane == 0) {
 #pragma unroll
-          for (int jj = 0; jj < 32; jj += 4)
+          for (int jj = 0; jj < NOUT; jj += 4)
             *reinterpret_cast<float4*>(xb + q * 64 + 32 + jj) = make_float4(v2[jj], v2[jj + 1], v2[jj + 2], v2[jj + 3]);
         }
         if (grp == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
         xpar ^= 1;
         float v[32];
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
+        for (int jj = 0; jj < NOUT; ++jj) {
           const float up = __shfl_up_sync(0xffffffffu, v0[jj], 1);
           const float dn = __shfl_down_sync(0xffffffffu, v2[jj], 1);
           v0[jj] = up;
@@ -813,20 +830,20 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         }
         if (lane == 0 && q > 0) {
 #pragma unroll
-          for (int jj = 0; jj < 32; jj += 4) {
+          for (int jj = 0; jj < NOUT; jj += 4) {
             const float4 x = *reinterpret_cast<const float4*>(xb + (q - 1) * 64 + jj);
             v0[jj] = x.x; v0[jj + 1] = x.y; v0[jj + 2] = x.z; v0[jj + 3] = x.w;
           }
         }
         if (lane == 31 && q < 3) {
 #pragma unroll
-          for (int jj = 0; jj < 32; jj += 4) {
+          for (int jj = 0; jj < NOUT; jj += 4) {
             const float4 x = *reinterpret_cast<const float4*>(xb + (q + 1) * 64 + 32 + jj);
             v2[jj] = x.x; v2[jj + 1] = x.y; v2[jj + 2] = x.z; v2[jj + 3] = x.w;
           }
         }
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) v[jj] = (v0[jj] + v1[jj]) + v2[jj];
+        for (int jj = 0; jj < 32; ++jj) v[jj] = jj < NOUT ? (v0[jj] + v1[jj]) + v2[jj] : 0.f;
 
         const int f = (t * MB + mb) * kDxBlk - 1 + row;
         const int py = f / kPitch;
@@ -837,7 +854,10 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int oy = py * p.out_scale + p.out_oy;
         const int ox = px * p.out_scale + p.out_ox;
         const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
-        finish_planes32_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
+        if constexpr (NOUT == 16)
+          finish_planes16_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
+        else
+          finish_planes32_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
       }
     }
 #ifdef BHSR_TIMING

@@ -224,13 +224,13 @@ static int launch(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t s
 // 5-D view of the packed weight blob [chunk][tap = dy*3+dx][part][32 couts][CH] that lands one
 // (chunk, dy) slab in shared memory as [part][dx][cout][CH] rows (see conv_dx_kernel).
 static int make_weight_map_dx(CUtensorMap* tm, const void* base, int n_chunks, int nparts, int ch,
-                              int box_couts = 32, int box_parts = -1, int box_ch = -1) {
+                              int box_couts = 32, int box_parts = -1, int box_ch = -1, int nout = 32) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return BHSR_ECUDA;
   const cuuint64_t rb = (cuuint64_t)ch * 2;
-  const cuuint64_t tap_bytes = (cuuint64_t)nparts * 32 * rb;
-  cuuint64_t dims[5] = {(cuuint64_t)ch, 32, 3, (cuuint64_t)nparts, (cuuint64_t)n_chunks * 3};
-  cuuint64_t strides[4] = {rb, tap_bytes, 32 * rb, 3 * tap_bytes};
+  const cuuint64_t tap_bytes = (cuuint64_t)nparts * nout * rb;     // packed blob: [chunk][tap][part][nout couts][ch]
+  cuuint64_t dims[5] = {(cuuint64_t)ch, (cuuint64_t)nout, 3, (cuuint64_t)nparts, (cuuint64_t)n_chunks * 3};
+  cuuint64_t strides[4] = {rb, tap_bytes, (cuuint64_t)nout * rb, 3 * tap_bytes};
   if (box_ch < 0) box_ch = ch;   // conv_dxs: 32-channel boxes out of the fast blob's 64-channel chunks
   cuuint32_t box[5] = {(cuuint32_t)box_ch, (cuuint32_t)box_couts, 3, (cuuint32_t)(box_parts < 0 ? nparts : box_parts), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -242,10 +242,10 @@ static int make_weight_map_dx(CUtensorMap* tm, const void* base, int n_chunks, i
   return 0;
 }
 
-template <bool EXACT, int MB, bool WRES>
+template <bool EXACT, int MB, bool WRES, int NOUT = 32>
 static int launch_dx_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
                             const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
-  auto kern = conv_dx_kernel<EXACT, MB, WRES, false>;
+  auto kern = conv_dx_kernel<EXACT, MB, WRES, false, NOUT>;
   static PerDeviceOnce attr_once;
   if (attr_once.first())
     BHSR_CUDA_CHECK(
@@ -265,12 +265,12 @@ static int launch_dx_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, 
 }
 
 // dx-in-N launch for a 32-output 3x3 layer (plain window, planes output).
-template <bool EXACT, int MB>
+template <bool EXACT, int MB, int NOUT = 32>
 static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream) {
   constexpr int CH = EXACT ? 32 : 64;
   using G = TileGeom<MB, CH>;
   constexpr int NPART = EXACT ? 2 : 1;
-  constexpr int W_SLAB = 96 * NPART * G::kRowBytes;
+  constexpr int W_SLAB = 3 * NOUT * NPART * G::kRowBytes;
   constexpr int A_STAGE = G::kTileBytes * NPART;   // one hi stage + one lo stage
   constexpr int S_OUT = kDxBlk * MB;               // valid output rows per tile
   p.tiles_per_strip = (d.h * kPitch + S_OUT - 1) / S_OUT;
@@ -310,7 +310,7 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   if (rc) return rc;
   rc = make_act_map(&tm_lo, EXACT ? d.in_lo : d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, CH);
   if (rc) return rc;
-  rc = make_weight_map_dx(&tm_w, d.w_packed, p.n_chunks, NPART, CH);
+  rc = make_weight_map_dx(&tm_w, d.w_packed, p.n_chunks, NPART, CH, NOUT, -1, -1, NOUT);
   if (rc) return rc;
 
   int sms = device_sm_count();
@@ -318,6 +318,7 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
   set_split(p, grid, MB, EXACT);
+  if (NOUT == 16) { p.split_round = -1; p.desc_mode &= ~0x1800; }   // four accumulator slots; probing issuer only
   static const char* no_pdl = getenv("BHSR_NO_PDL");
   p.pdl = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   {
@@ -326,8 +327,8 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
     if (lean && lean[0] == '2') p.desc_mode |= 0x1800;      // + last chunk block-major across both phases (bit 12)
     if (lean && lean[0] == '0') p.desc_mode &= ~0x1800;
   }
-  if (p.w_resident) return launch_dx_kernel<EXACT, MB, true>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
-  return launch_dx_kernel<EXACT, MB, false>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  if (p.w_resident) return launch_dx_kernel<EXACT, MB, true, NOUT>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  return launch_dx_kernel<EXACT, MB, false, NOUT>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
 }
 
 // Single-accumulator dx-in-N launch (conv_dxs.cuh): MB = 2..4 blocks per tile, CH channels per chunk.
@@ -561,7 +562,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   if (!dp) return set_error(BHSR_EINVAL, "conv_tc: null descriptor");
   const BhsrConvTcDesc& d = *dp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BHSR_REQUIRE(d.cout == 32 || d.cout == 64, "conv_tc: cout must be 32 or 64 (got %d)", d.cout);
+  BHSR_REQUIRE(d.cout == 16 || d.cout == 32 || d.cout == 64, "conv_tc: cout must be 16, 32 or 64 (got %d)", d.cout);
   BHSR_REQUIRE(d.w > 0 && d.h > 0 && d.nb > 0, "conv_tc: empty input");
   BHSR_REQUIRE(d.cin > 0 && d.cin % (d.numerics == BHSR_NUMERICS_EXACT_F16X3 ? 16 : 32) == 0,
                "conv_tc: cin must be a multiple of 16 (exact) / 32 (fast), got %d", d.cin);
@@ -652,6 +653,11 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
   {
     static const char* dxn = getenv("BHSR_DXN");
     const bool use_dx = !(dxn && dxn[0] == '0') && !(d.desc_mode & 0x100);  // desc_mode bit 8: per-tap kernel
+    if (d.cout == 16) {   // 16-output layers: the exact two-block dx kernel only (the head's 16-channel convs)
+      BHSR_REQUIRE(exact && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2) && mb == 2,
+                   "conv_tc: cout 16 needs exact numerics, a plain 3x3 window, plane output and two blocks per tile");
+      return launch_dx<true, 2, 16>(d, p, stream);
+    }
     if (use_dx && d.cout == 32 && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2)) {
       // tall tiles on the single-accumulator kernel (fast numerics; exact needs plane format 1)
       static const char* dxs = getenv("BHSR_DXS_MB");

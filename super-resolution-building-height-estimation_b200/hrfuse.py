@@ -89,6 +89,8 @@ def _wgrad(x: Tensor, dy: Tensor, cout: int, cin: int, k: int, *, in_affine=None
 # ------------------------------------------------------------------ tensor-core training convs (head_tc.cu)
 # BHSR_HEAD_TC_TRAIN=0 keeps the round-1 fp32 CUDA-core kernels (head.cu) for the autograd path.
 TC_TRAIN = os.environ.get("BHSR_HEAD_TC_TRAIN", "1") != "0"
+# 16-output variant of the dx-in-N kernel for the head's 16-channel convs (BHSR_HEAD_TC16=0: pad them to 32 as before)
+TC16 = os.environ.get("BHSR_HEAD_TC16", "1") != "0"
 
 
 def _grad_scale(g: Tensor) -> Tensor:
@@ -130,7 +132,7 @@ def _conv_tc_train(x: Tensor, w: Tensor, b: Optional[Tensor] = None, *, in_affin
         h, wd = x.shape[2], x.shape[3]
     cin_pad = (cin + 15) // 16 * 16
     ctot_in = (cin_pad + 31) // 32 * 32
-    cop = 32 if cout <= 32 else 64
+    cop = (16 if (cout <= 16 and TC16) else 32) if cout <= 32 else 64
     xin = _planes(nb, h, wd, ctot_in, dev)
     xf = ops.head_xform(x, cin, h, wd, unshuffle=x_unshuffle, in_affine=in_affine, in_relu=in_relu, premul=gscale)
     ops.head_to_planes(x, xf, xin[0], xin[1], 0, ctot_in)
@@ -153,7 +155,7 @@ def _conv_tc_train(x: Tensor, w: Tensor, b: Optional[Tensor] = None, *, in_affin
         if accumulate:
             raise ValueError("accumulate needs an output tensor")
         y = torch.empty((nb, cout, h, wd), dtype=torch.float32, device=dev)
-    if cop == 32:
+    if cop <= 32:
         # the dx-in-N kernel (planes output) + one pass back to fp32 NCHW that also divides the gradient scale out,
         # accumulates and takes the BatchNorm statistics
         out = _planes(nb, h, wd, 32, dev)
@@ -455,6 +457,8 @@ def _cache_get(module: nn.Module, build):
 def _pad_cout(n: int) -> int:
     if n > 64:
         raise NotImplementedError("tensor-core head path supports at most 64 output channels")
+    if n <= 16 and TC16:
+        return 16
     return 32 if n <= 32 else 64
 
 
@@ -500,7 +504,7 @@ def _basic_block_tc(blk: "BasicBlock", xin, cin: int):
     c = _cache_get(blk, build)
     nb, h, w, _ = xin[0].shape
     dev = xin[0].device
-    ctot = 32 if cp == 32 else 64
+    ctot = 32 if cp <= 32 else 64      # plane width: a whole 32-channel chunk for the next conv's TMA box
     c1 = _planes(nb, h, w, ctot, dev)
     ops.conv_tc(xin[0], xin[1], 0, cin, c["w1"], cp, c["t1"], ops.PLAIN_TAPS, c1[0], c1[1], scale=c["s1"],
                 cout_valid=planes_out, relu=True, numerics=NUMERICS_EXACT)

@@ -110,6 +110,43 @@ def test_conv_dx_kernel_vs_per_tap_and_oracle(dev, numerics, rtol, atol, cin, h,
         assert_close(outs[2], outs[0], 1e-5, 1e-6, "dx pair vs dx single")
 
 
+@pytest.mark.parametrize("cin,h,w,nb,max_ctas", [(16, 64, 64, 3, 0), (64, 40, 130, 2, 5), (32, 2, 64, 1, 0), (16, 256, 256, 2, 0),
+                                                  (48, 23, 70, 4, 3)])
+def test_conv_dx_kernel_16_outputs_vs_padded_and_oracle(dev, cin, h, w, nb, max_ctas):
+    """conv_dx_kernel<exact, NOUT = 16> (the head's 16-channel convs, SR/HRfuse.py:164-190: 48 + 48 accumulator columns,
+    four TMEM slots, 16-channel epilogue) against the oracle and against the same layer zero-padded to 32 outputs,
+    with the scale / residual / ReLU epilogue, few CTAs, several strips and tiny images."""
+    from bhsr import ops
+    from bhsr._lib import NUMERICS
+    rng = np.random.RandomState(cin + h + w)
+    x = (rng.rand(nb, cin, h, w) * 2 - 0.5).astype(np.float32)
+    wt = (rng.standard_normal((16, cin, 3, 3)) * (0.5 / np.sqrt(cin * 9))).astype(np.float32)
+    b = (rng.standard_normal(16) * 0.1).astype(np.float32)
+    sc = (rng.rand(16) + 0.5).astype(np.float32)
+    r1 = rng.standard_normal((nb, 16, h, w)).astype(np.float32)
+    conv = R.conv2d(x, wt, None, padding=1, acc_dtype=np.float64)
+    ref = np.maximum((conv * sc[None, :, None, None] + b[None, :, None, None]) * 0.5 + r1, 0.0)
+    num = NUMERICS["exact"]
+    ctot = (cin + 31) // 32 * 32
+    hi, lo = _planes(x, ctot, dev)
+    rhi, rlo = _planes(r1, 32, dev)
+    outs = []
+    for cout in (16, 32):
+        wpad = np.zeros((cout, cin, 3, 3), np.float32); wpad[:16] = wt
+        bpad = np.zeros(cout, np.float32); bpad[:16] = b
+        spad = np.ones(cout, np.float32); spad[:16] = sc
+        wp = ops.pack_conv_weights(cuda(wpad, dev), num)
+        out_hi = torch.zeros((nb, h, w, 32), dtype=torch.float16, device=dev)
+        out_lo = torch.zeros_like(out_hi)
+        ops.conv_tc(hi, lo, 0, cin, wp, cout, cuda(bpad, dev), ops.PLAIN_TAPS, out_hi, out_lo, out_choff=0,
+                    scale=cuda(spad, dev), res1=(rhi, rlo, 0), alpha1=0.5, relu=True, numerics=num, cout_valid=16,
+                    max_ctas=max_ctas)
+        assert float(out_hi[..., 16:].abs().max()) == 0.0        # channels past cout_valid are never written
+        outs.append(ops.planes_to_nchw(out_hi, out_lo, 16, 0).cpu().numpy())
+    assert_close(outs[0], ref, 1e-3, 1e-4, f"16-output dx kernel {cin}->16")
+    assert_close(outs[0], outs[1], 1e-5, 1e-6, "16-output kernel vs the layer padded to 32 outputs")
+
+
 @pytest.mark.parametrize("mb", [3, 4])
 @pytest.mark.parametrize("cin,h,w,nb,max_ctas", [(64, 64, 64, 3, 0), (160, 64, 64, 3, 5), (96, 23, 130, 2, 3),
                                                   (32, 2, 64, 1, 0), (128, 64, 64, 5, 40)])

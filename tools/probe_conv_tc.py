@@ -104,6 +104,12 @@ def run_case(name, desc_mode):
         for nbv in (2, 3):
             cases[f"exact64_c{cc}_nb{nbv}"] = dict(cout=64, cin=cc, ctot=96 if cc == 96 else 64, exact=True, mb=2, nb=nbv, lrelu=False, h=16, w=16)
             cases[f"exact64_c{cc}_nb{nbv}_nchw"] = dict(cout=64, cin=cc, ctot=96 if cc == 96 else 64, exact=True, mb=2, nb=nbv, lrelu=False, h=16, w=16, nchw=True)
+    # 16-output variant of the exact dx kernel (the head's 16-channel convs) vs the same layer padded to 32 outputs
+    cases["exact16_c16"] = dict(cout=16, cin=16, ctot=32, exact=True, mb=2, nb=3, h=40, w=130)
+    cases["exact16_c64"] = dict(cout=16, cin=64, ctot=64, exact=True, mb=2, nb=2, lrelu=False)
+    cases["exact16_c32_small"] = dict(cout=16, cin=32, ctot=32, exact=True, mb=2, nb=5, h=7, w=40, max_ctas=3)
+    cases["time_exact16_c16_256"] = dict(cout=16, cin=16, ctot=32, exact=True, mb=2, nb=32, h=256, w=256, time=True)
+    cases["time_exact32_c16_256"] = dict(cout=32, cin=16, ctot=32, exact=True, mb=2, nb=32, h=256, w=256, time=True)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
