@@ -83,8 +83,12 @@ __device__ __forceinline__ void issue_phase3(uint32_t a_lo, uint32_t b0, uint32_
   }
 }
 
+// epilogue groups (of four warps) of a conv_dx_kernel instantiation: the 16-output variant keeps four blocks in flight
+__host__ __device__ constexpr int dx_groups(int nout) { return nout == 16 ? 4 : 2; }
+__host__ __device__ constexpr int dx_threads(int nout) { return (4 * dx_groups(nout) + 3) * 32; }
+
 template <bool EXACT, int MB, bool WRES, bool PAIR, int NOUT = 32>
-__global__ void __launch_bounds__(kDxThreads, 1)
+__global__ void __launch_bounds__(dx_threads(NOUT), 1)
 conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w, const ConvTcKernelParams p) {
@@ -98,6 +102,13 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   // half the MMA columns, half the accumulator drain, half the epilogue; exact numerics, single CTA only
   static_assert(NOUT == 32 || (NOUT == 16 && EXACT && !PAIR), "16 outputs: exact numerics, single CTA");
   constexpr int G3 = 3 * NOUT;                      // the three dx groups of one part
+  // warp roles: NGRP epilogue groups of four warps, then the two producers and the MMA issuer.  The 16-channel layers have
+  // K = 144: their time is the LATENCY of one block's drain -> exchange -> shuffle -> store chain (round 2: halving the
+  // chain's instructions changed nothing), so they keep four blocks in flight instead of two (131 -> <= 107 registers)
+  constexpr int NGRP = dx_groups(NOUT);
+  constexpr int kDxWarpProdA = 4 * NGRP, kDxWarpProdW = 4 * NGRP + 1, kDxWarpMma = 4 * NGRP + 2;
+  constexpr int STG_WARP = NOUT == 16 ? 32 * 64 : kStageWarpBytes;      // staging bytes per epilogue warp
+  static_assert(4 * NGRP * STG_WARP <= kDxStageBytes, "epilogue staging overflow");
   constexpr int COLS = G3 * NPART;                  // weight rows per window row = TMEM columns per block
   // one (chunk, dy) weight slab: 12288 B; in a CTA pair this CTA keeps 144 of the 192 rows:
   // X = its half of the wide operand (96 rows: W_hi in the even CTA, W_lo' in the odd one, couts in
@@ -701,7 +712,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       for (int mb = 0; mb < MB; ++mb) {                  // rolled: one copy of the epilogue body (I-cache)
         if (sel >= 0 && mb != sel) continue;             // split last round: one block of the tile
         const uint32_t blk = tile_it * MB + mb;
-        if (static_cast<int>(blk & 1u) != grp) continue;   // warp-uniform
+        if (static_cast<int>(blk % NGRP) != grp) continue;   // warp-uniform
         const uint32_t slot = blk % NSLOT;
 #ifdef BHSR_TIMING
         const long long tw0 = clock64();
@@ -802,23 +813,24 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
           const int py3 = f3 / kPitch, pc3 = f3 - py3 * kPitch, px3 = s * kStrip + pc3;
           const bool valid3 = (row >= 1) && (row <= kDxBlk) && (pc3 < kStrip) && (py3 < p.h) && (px3 < p.w);
           const size_t pix3 = (static_cast<size_t>(n) * p.h + py3) * p.w + px3;
-          finish_planes32_rolled(p, v1, valid3, pix3, pix3, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
+          finish_planes32_rolled(p, v1, valid3, pix3, pix3, lane, s_stage + warp * STG_WARP, s_bias, s_scale);
           continue;
         }
 #endif
         // out[row] = g0[row-1] + g1[row] + g2[row+1]: lane shifts inside the warp, smem across warps
-        float* xb = s_xchg + ((grp * 2 + xpar) * 4) * 64;
+        constexpr int XQ = 2 * NOUT;                       // floats per warp: v0 of lane 31 | v2 of lane 0
+        float* xb = s_xchg + ((grp * 2 + xpar) * 4) * XQ;
         if (lane == 31) {
 #pragma unroll
           for (int jj = 0; jj < NOUT; jj += 4)
-            *reinterpret_cast<float4*>(xb + q * 64 + jj) = make_float4(v0[jj], v0[jj + 1], v0[jj + 2], v0[jj + 3]);
+            *reinterpret_cast<float4*>(xb + q * XQ + jj) = make_float4(v0[jj], v0[jj + 1], v0[jj + 2], v0[jj + 3]);
         }
         if (lane == 0) {
 #pragma unroll
           for (int jj = 0; jj < NOUT; jj += 4)
-            *reinterpret_cast<float4*>(xb + q * 64 + 32 + jj) = make_float4(v2[jj], v2[jj + 1], v2[jj + 2], v2[jj + 3]);
+            *reinterpret_cast<float4*>(xb + q * XQ + NOUT + jj) = make_float4(v2[jj], v2[jj + 1], v2[jj + 2], v2[jj + 3]);
         }
-        if (grp == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
+        named_bar_sync(1 + grp, 128);
         xpar ^= 1;
         float v[32];
 #pragma unroll
@@ -831,14 +843,14 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         if (lane == 0 && q > 0) {
 #pragma unroll
           for (int jj = 0; jj < NOUT; jj += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(xb + (q - 1) * 64 + jj);
+            const float4 x = *reinterpret_cast<const float4*>(xb + (q - 1) * XQ + jj);
             v0[jj] = x.x; v0[jj + 1] = x.y; v0[jj + 2] = x.z; v0[jj + 3] = x.w;
           }
         }
         if (lane == 31 && q < 3) {
 #pragma unroll
           for (int jj = 0; jj < NOUT; jj += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(xb + (q + 1) * 64 + 32 + jj);
+            const float4 x = *reinterpret_cast<const float4*>(xb + (q + 1) * XQ + NOUT + jj);
             v2[jj] = x.x; v2[jj + 1] = x.y; v2[jj + 2] = x.z; v2[jj + 3] = x.w;
           }
         }
@@ -855,9 +867,9 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         const int ox = px * p.out_scale + p.out_ox;
         const size_t out_pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
         if constexpr (NOUT == 16)
-          finish_planes16_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
+          finish_planes16_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * STG_WARP, s_bias, s_scale);
         else
-          finish_planes32_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * kStageWarpBytes, s_bias, s_scale);
+          finish_planes32_rolled(p, v, valid, in_pix, out_pix, lane, s_stage + warp * STG_WARP, s_bias, s_scale);
       }
     }
 #ifdef BHSR_TIMING

@@ -9,10 +9,9 @@ namespace bhsr {
 // conv_dxs_kernel — dx-in-N conv for the 32-output 3x3 layers (SR/rrdbnet_arch.py:137-140) with
 // 96 TMEM columns per 128-row block, so that a tile is MB = 3 or 4 blocks tall.
 //
-// Why (profiles/r02_dx_layer_model.md): conv2..conv5 of a ResidualDenseBlock run at the rate the
-// L2 -> SM fabric delivers their operands (~30 B/clk/SM, 7 TB/s over the chip), and a 2-block
-// tile loads 7 image rows for 3.8 rows of outputs (1.83x) and re-streams the layer's weights for
-// every 252 pixels.  The 2-block limit came from TMEM: exact numerics kept TWO accumulators per
+// Why it was built (the premise of VERDICT r1 item 3): conv2..conv5 of a ResidualDenseBlock move 3.3x their unique
+// input from L2 to the SMs — a 2-block tile loads 7 image rows for 3.8 rows of outputs (1.83x) and re-streams the
+// layer's weights for every 252 pixels.  The 2-block limit came from TMEM: exact numerics kept TWO accumulators per
 // block (hi*hi and the 2^-11 cross terms; 192 columns).  Here all three split products of a
 // k-step go into the SAME 96 columns:
 //     D += A_hi * W_hi^T      D += A_hi * W_lo^T      D += A_lo * W_hi^T
@@ -22,6 +21,8 @@ namespace bhsr {
 // multiplies by 2^-8).  CPU emulation of the 23-block trunk: max err/tol 0.042 (random init) /
 // 0.055 (x4plus), identical to the two-accumulator split (tools/numerics_probe_single_acc.py).
 // Fast numerics is the same kernel with one product per k-step.
+// What was measured (Finding 4): with 4-block tiles the L2 -> SM bytes fall by a third and the layer
+// times do not move — those bytes are not what bounds these layers.  Fast numerics is wired and tested; it is opt-in.
 //
 // Tile geometry: blocks advance by 126 flat pixels (rows 0 / 127 of a block have no neighbour for
 // the lane-shift combine); a tile of MB blocks needs ceil((326 + 126 (MB-1)) / 66) image rows of
@@ -101,7 +102,7 @@ __device__ __forceinline__ uint32_t issue_dxs(uint32_t a_lo, uint32_t b_lo, uint
 }
 
 // ---- lean issue: ALL MMAs of one phase of a chunk (3 window rows x NB blocks x KST k-steps, x2 when DUAL) as one asm
-// block with no barrier probes.  Round 2 measured (profiles/r02_mma_issue_gaps.md) that the MMA warp spends ~45 % of a
+// block with no barrier probes.  Round 2 measured (profiles/r02_mma_issue_region_cycles.log) that the MMA warp spends ~45 % of a
 // tile OUTSIDE its issue blocks — probe bookkeeping, per-window-row slab indices, vote / reduce — while the tensor
 // queue (a few MMAs deep) runs dry; with resident weights the three slabs of a chunk are consecutive, so a phase needs
 // one wait, one asm block and one commit.

@@ -252,7 +252,7 @@ static int launch_dx_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, 
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kDxThreads);
+  cfg.blockDim = dim3(dx_threads(NOUT));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
