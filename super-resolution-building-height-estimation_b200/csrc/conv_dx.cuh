@@ -83,8 +83,11 @@ __device__ __forceinline__ void issue_phase3(uint32_t a_lo, uint32_t b0, uint32_
   }
 }
 
-// epilogue groups (of four warps) of a conv_dx_kernel instantiation: the 16-output variant keeps four blocks in flight
-__host__ __device__ constexpr int dx_groups(int nout) { return nout == 16 ? 4 : 2; }
+// epilogue groups (of four warps) of a conv_dx_kernel instantiation.  Four groups for the 16-output variant were measured
+// (608 threads, 96 registers): no faster — those layers are supply-bound (profiles/r02_head_layer_ncu.md) — so it keeps two
+// and spends the shared memory on a deeper activation ring instead (its staging needs 2 KB per warp, not 4)
+__host__ __device__ constexpr int dx_groups(int nout) { return nout == 16 ? 2 : 2; }
+__host__ __device__ constexpr int dx_stage_bytes(int nout) { return 4 * dx_groups(nout) * (nout == 16 ? 32 * 64 : kStageWarpBytes); }
 __host__ __device__ constexpr int dx_threads(int nout) { return (4 * dx_groups(nout) + 3) * 32; }
 
 template <bool EXACT, int MB, bool WRES, bool PAIR, int NOUT = 32>
@@ -103,12 +106,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   static_assert(NOUT == 32 || (NOUT == 16 && EXACT && !PAIR), "16 outputs: exact numerics, single CTA");
   constexpr int G3 = 3 * NOUT;                      // the three dx groups of one part
   // warp roles: NGRP epilogue groups of four warps, then the two producers and the MMA issuer.  The 16-channel layers have
-  // K = 144: their time is the LATENCY of one block's drain -> exchange -> shuffle -> store chain (round 2: halving the
-  // chain's instructions changed nothing), so they keep four blocks in flight instead of two (131 -> <= 107 registers)
+  // K = 144 (group count and staging size per instantiation: dx_groups / dx_stage_bytes above)
   constexpr int NGRP = dx_groups(NOUT);
   constexpr int kDxWarpProdA = 4 * NGRP, kDxWarpProdW = 4 * NGRP + 1, kDxWarpMma = 4 * NGRP + 2;
   constexpr int STG_WARP = NOUT == 16 ? 32 * 64 : kStageWarpBytes;      // staging bytes per epilogue warp
-  static_assert(4 * NGRP * STG_WARP <= kDxStageBytes, "epilogue staging overflow");
+  constexpr int DX_STAGE = dx_stage_bytes(NOUT);
+  static_assert(4 * NGRP * STG_WARP <= DX_STAGE && DX_STAGE <= kDxStageBytes, "epilogue staging overflow");
   constexpr int COLS = G3 * NPART;                  // weight rows per window row = TMEM columns per block
   // one (chunk, dy) weight slab: 12288 B; in a CTA pair this CTA keeps 144 of the 192 rows:
   // X = its half of the wide operand (96 rows: W_hi in the even CTA, W_lo' in the odd one, couts in
@@ -142,7 +145,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
   float* s_scale = s_bias + 64;
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_scale + 64);
-  float* s_xchg = reinterpret_cast<float*>(s_stage + kDxStageBytes);
+  float* s_xchg = reinterpret_cast<float*>(s_stage + dx_stage_bytes(NOUT));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

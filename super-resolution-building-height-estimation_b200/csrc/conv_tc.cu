@@ -276,8 +276,9 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   p.tiles_per_strip = (d.h * kPitch + S_OUT - 1) / S_OUT;
   p.total_tiles = d.nb * p.n_strips * p.tiles_per_strip;
   const int slabs = p.n_chunks * 3;
+  constexpr int kTail = kDxTailBytes - kDxStageBytes + dx_stage_bytes(NOUT);   // the 16-output epilogue stages 2 KB per warp
   auto slots_for = [&](int ns) {
-    const int avail = kSmemLimit - 1024 - ns * A_STAGE - kDxTailBytes;
+    const int avail = kSmemLimit - 1024 - ns * A_STAGE - kTail;
     return avail < 0 ? 0 : avail / W_SLAB;
   };
   int astages = 2, wslots = slots_for(2);
@@ -293,6 +294,10 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
       wslots = slots_for(astages);
     }
   }
+  if (NOUT == 16 && astages > 2) {      // measured (profiles/r02_dx_16_outputs.log): a third stage makes these layers 5 % slower
+    static const char* force_ns = getenv("BHSR_ASTAGES");
+    if (!force_ns) { astages = 2; wslots = slots_for(2); }
+  }
   if (wslots > kMaxWSlots) wslots = kMaxWSlots;
   if (wslots < 3) return set_error(BHSR_EINVAL, "conv_tc(dx): no room for the weight ring");
   p.w_resident = slabs <= wslots ? 1 : 0;
@@ -303,7 +308,7 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   if (p.w_resident) wslots = slabs;
   p.wslots = wslots;
   p.astages = astages;
-  const int smem_bytes = 1024 + astages * A_STAGE + wslots * W_SLAB + kDxTailBytes;
+  const int smem_bytes = 1024 + astages * A_STAGE + wslots * W_SLAB + kTail;
 
   CUtensorMap tm_hi, tm_lo, tm_w;
   int rc = make_act_map(&tm_hi, d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, CH);
