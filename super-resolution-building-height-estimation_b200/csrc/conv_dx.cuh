@@ -90,12 +90,15 @@ __host__ __device__ constexpr int dx_groups(int nout) { return nout == 16 ? 2 : 
 __host__ __device__ constexpr int dx_stage_bytes(int nout) { return 4 * dx_groups(nout) * (nout == 16 ? 32 * 64 : kStageWarpBytes); }
 __host__ __device__ constexpr int dx_threads(int nout) { return (4 * dx_groups(nout) + 3) * 32; }
 
-template <bool EXACT, int MB, bool WRES, bool PAIR, int NOUT = 32>
+template <bool EXACT, int MB, bool WRES, bool PAIR, int NOUT = 32, bool C16 = false>
 __global__ void __launch_bounds__(dx_threads(NOUT), 1)
 conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w, const ConvTcKernelParams p) {
-  constexpr int CH = EXACT ? 32 : 64;
+  // C16: 16-channel chunks (32-byte pixel rows, SWIZZLE_32B, one k-step per chunk) for the 16 -> 16 layers of the head
+  // on 16-channel planes: contiguous pixel records, half the bytes of a 32-channel box
+  static_assert(!C16 || (NOUT == 16 && EXACT && !PAIR), "16-channel chunks: the 16-output exact kernel");
+  constexpr int CH = C16 ? 16 : EXACT ? 32 : 64;
   using G = TileGeom<MB, CH>;
   constexpr int RB = G::kRowBytes;
   constexpr int RB16 = RB / 16;
@@ -679,8 +682,12 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
             if (!WRES) ok_w = (okbits >> 1) & 7u;
           }
         };
-        if (rem >= CH) issue_chunk(std::integral_constant<int, KSTEPS>{});
-        else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
+        if constexpr (KSTEPS >= 2) {
+          if (rem >= CH) issue_chunk(std::integral_constant<int, KSTEPS>{});
+          else issue_chunk(std::integral_constant<int, KSTEPS / 2>{});
+        } else {
+          issue_chunk(std::integral_constant<int, 1>{});
+        }
         sh = sh_next;
         h_ph = h_ph_next;
         if (EXACT) {

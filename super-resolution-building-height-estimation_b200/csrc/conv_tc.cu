@@ -101,7 +101,7 @@ static int make_act_map(CUtensorMap* tm, const void* base, int nb, int h, int w,
   if (promo >= 0) l2p = static_cast<CUtensorMapL2promotion>(promo);  // 0 none, 1 64B, 2 128B, 3 256B
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : ch == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                    l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(act) -> %d", (int)r);
   return 0;
@@ -236,16 +236,16 @@ static int make_weight_map_dx(CUtensorMap* tm, const void* base, int n_chunks, i
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   box_ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_ch == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(BHSR_ECUDA, "cuTensorMapEncodeTiled(w, dx) -> %d", (int)r);
   return 0;
 }
 
-template <bool EXACT, int MB, bool WRES, int NOUT = 32>
+template <bool EXACT, int MB, bool WRES, int NOUT = 32, bool C16 = false>
 static int launch_dx_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_w,
                             const ConvTcKernelParams& p, int grid, int smem_bytes, cudaStream_t stream) {
-  auto kern = conv_dx_kernel<EXACT, MB, WRES, false, NOUT>;
+  auto kern = conv_dx_kernel<EXACT, MB, WRES, false, NOUT, C16>;
   static PerDeviceOnce attr_once;
   if (attr_once.first())
     BHSR_CUDA_CHECK(
@@ -265,9 +265,10 @@ static int launch_dx_kernel(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, 
 }
 
 // dx-in-N launch for a 32-output 3x3 layer (plain window, planes output).
-template <bool EXACT, int MB, int NOUT = 32>
+template <bool EXACT, int MB, int NOUT = 32, bool C16 = false>
 static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_t stream) {
-  constexpr int CH = EXACT ? 32 : 64;
+  constexpr int CH = C16 ? 16 : EXACT ? 32 : 64;
+  constexpr int PACK_CH = EXACT ? 32 : 64;          // channels per chunk of the packed weight blob
   using G = TileGeom<MB, CH>;
   constexpr int NPART = EXACT ? 2 : 1;
   constexpr int W_SLAB = 3 * NOUT * NPART * G::kRowBytes;
@@ -315,7 +316,7 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
   if (rc) return rc;
   rc = make_act_map(&tm_lo, EXACT ? d.in_lo : d.in_hi, d.nb, d.h, d.w, d.in_ctot, G::kRows, CH);
   if (rc) return rc;
-  rc = make_weight_map_dx(&tm_w, d.w_packed, p.n_chunks, NPART, CH, NOUT, -1, -1, NOUT);
+  rc = make_weight_map_dx(&tm_w, d.w_packed, (d.cin + PACK_CH - 1) / PACK_CH, NPART, PACK_CH, NOUT, -1, CH, NOUT);
   if (rc) return rc;
 
   int sms = device_sm_count();
@@ -332,8 +333,8 @@ static int launch_dx(const BhsrConvTcDesc& d, ConvTcKernelParams& p, cudaStream_
     if (lean && lean[0] == '2') p.desc_mode |= 0x1800;      // + last chunk block-major across both phases (bit 12)
     if (lean && lean[0] == '0') p.desc_mode &= ~0x1800;
   }
-  if (p.w_resident) return launch_dx_kernel<EXACT, MB, true, NOUT>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
-  return launch_dx_kernel<EXACT, MB, false, NOUT>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  if (p.w_resident) return launch_dx_kernel<EXACT, MB, true, NOUT, C16>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
+  return launch_dx_kernel<EXACT, MB, false, NOUT, C16>(tm_hi, tm_lo, tm_w, p, grid, smem_bytes, stream);
 }
 
 // Single-accumulator dx-in-N launch (conv_dxs.cuh): MB = 2..4 blocks per tile, CH channels per chunk.
@@ -579,7 +580,9 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
                      (d.cout_valid == 0 || d.cout_valid % 32 == 0),
                  "conv_tc: pixel-shuffle epilogue needs plane output of twice the size and whole 32-channel slices");
   const bool exact_ = d.numerics == BHSR_NUMERICS_EXACT_F16X3;
-  const int ch_ = exact_ ? 32 : 64;
+  // 16 -> 16 exact layers on planes that are not 32-channel aligned: 16-channel chunks (conv_dx_kernel<..., C16>)
+  const bool c16_ = exact_ && d.cout == 16 && d.cin == 16 && (d.in_ctot % 32 != 0 || d.in_choff % 32 != 0);
+  const int ch_ = c16_ ? 16 : exact_ ? 32 : 64;
   BHSR_REQUIRE(d.in_ctot % ch_ == 0 && d.in_choff % ch_ == 0 &&
                    d.in_choff + (d.cin + ch_ - 1) / ch_ * ch_ <= d.in_ctot,
                "conv_tc: input channel window [%d,+%d) must sit on %d-channel chunks of %d",
@@ -661,6 +664,7 @@ extern "C" int bhsr_conv_tc(const BhsrConvTcDesc* dp, void* stream_) {
     if (d.cout == 16) {   // 16-output layers: the exact two-block dx kernel only (the head's 16-channel convs)
       BHSR_REQUIRE(exact && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2) && mb == 2,
                    "conv_tc: cout 16 needs exact numerics, a plain 3x3 window, plane output and two blocks per tile");
+      if (c16_) return launch_dx<true, 2, 16, true>(d, p, stream);
       return launch_dx<true, 2, 16>(d, p, stream);
     }
     if (use_dx && d.cout == 32 && ks == 3 && !nchw && !(d.epilogue & BHSR_EPI_SHUFFLE2)) {

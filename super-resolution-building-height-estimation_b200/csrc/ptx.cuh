@@ -187,16 +187,16 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t start, uint32_t bas
   return d;
 }
 // Same for a row pitch of ROWB bytes: 128 -> SWIZZLE_128B (8-row groups 1024 B apart),
-// 64 -> SWIZZLE_64B (layout code 4, 8-row groups 512 B apart).
+// 64 -> SWIZZLE_64B (layout code 4, 8-row groups 512 B apart), 32 -> SWIZZLE_32B (layout code 6, 256 B apart).
 template <int ROWB>
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t start) {
-  static_assert(ROWB == 128 || ROWB == 64, "row pitch must be 64 or 128 bytes");
+  static_assert(ROWB == 128 || ROWB == 64 || ROWB == 32, "row pitch must be 32, 64 or 128 bytes");
   uint64_t d = 0;
   d |= static_cast<uint64_t>((start >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>((8 * ROWB) >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(ROWB == 128 ? 2 : 4) << 61;
+  d |= static_cast<uint64_t>(ROWB == 128 ? 2 : ROWB == 64 ? 4 : 6) << 61;   // SWIZZLE_128B / _64B / _32B
   return d;
 }
 // Instruction descriptor, kind::f16: fp16 A/B (K-major), fp32 D, M=128, N given.

@@ -145,6 +145,17 @@ def test_conv_dx_kernel_16_outputs_vs_padded_and_oracle(dev, cin, h, w, nb, max_
         outs.append(ops.planes_to_nchw(out_hi, out_lo, 16, 0).cpu().numpy())
     assert_close(outs[0], ref, 1e-3, 1e-4, f"16-output dx kernel {cin}->16")
     assert_close(outs[0], outs[1], 1e-5, 1e-6, "16-output kernel vs the layer padded to 32 outputs")
+    if cin == 16:   # 16-channel planes in and out: 16-channel chunks, SWIZZLE_32B operands (conv_dx_kernel<..., C16>)
+        hi16, lo16 = _planes(x, 16, dev)
+        r16 = _planes(r1, 16, dev)
+        wp = ops.pack_conv_weights(cuda(wt, dev), num)
+        out_hi = torch.zeros((nb, h, w, 16), dtype=torch.float16, device=dev)
+        out_lo = torch.zeros_like(out_hi)
+        ops.conv_tc(hi16, lo16, 0, 16, wp, 16, cuda(b, dev), ops.PLAIN_TAPS, out_hi, out_lo, out_choff=0,
+                    scale=cuda(sc, dev), res1=(r16[0], r16[1], 0), alpha1=0.5, relu=True, numerics=num, max_ctas=max_ctas)
+        got16 = ops.planes_to_nchw(out_hi, out_lo, 16, 0).cpu().numpy()
+        assert_close(got16, ref, 1e-3, 1e-4, "16-channel-plane path")
+        assert_close(got16, outs[0], 1e-5, 1e-6, "16-channel chunks vs 32-channel chunks")
 
 
 @pytest.mark.parametrize("mb", [3, 4])

@@ -110,6 +110,12 @@ def run_case(name, desc_mode):
     cases["exact16_c32_small"] = dict(cout=16, cin=32, ctot=32, exact=True, mb=2, nb=5, h=7, w=40, max_ctas=3)
     cases["time_exact16_c16_256"] = dict(cout=16, cin=16, ctot=32, exact=True, mb=2, nb=32, h=256, w=256, time=True)
     cases["time_exact32_c16_256"] = dict(cout=32, cin=16, ctot=32, exact=True, mb=2, nb=32, h=256, w=256, time=True)
+    # 16-channel planes: conv_dx_kernel<..., C16> (16-channel chunks, SWIZZLE_32B) reads and writes contiguous 32-byte records
+    cases["exact16_t16"] = dict(cout=16, cin=16, ctot=16, exact=True, mb=2, nb=3, h=40, w=130, octot=16, ochoff=0)
+    cases["exact16_t16_small"] = dict(cout=16, cin=16, ctot=16, exact=True, mb=2, nb=5, h=7, w=40, max_ctas=3, octot=16, ochoff=0)
+    cases["exact16_t48_off16"] = dict(cout=16, cin=16, ctot=16, exact=True, mb=2, nb=2, octot=48, ochoff=16)
+    cases["time_exact16_t16_256"] = dict(cout=16, cin=16, ctot=16, exact=True, mb=2, nb=32, h=256, w=256, time=True, octot=16, ochoff=0)
+    cases["time_exact16_c16_256_o32"] = dict(cout=16, cin=16, ctot=32, exact=True, mb=2, nb=32, h=256, w=256, time=True, octot=32, ochoff=0)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
@@ -186,11 +192,12 @@ def run_case(name, desc_mode):
                                        out_f32=out, lrelu=cfg["lrelu"], numerics=numerics,
                                        mblocks=cfg["mb"], desc_mode=desc_mode, **kw)
         else:
-            octot = 192
+            octot = cfg.get("octot", 192)
+            ochoff = cfg.get("ochoff", 64)
             out_hi = torch.zeros(nb, h, w, octot, dtype=torch.float16, device=dev)
             out_lo = torch.zeros_like(out_hi)
             call = lambda: ops.conv_tc(in_hi, in_lo, 0, cin, wp, cout, bias, ops.PLAIN_TAPS, out_hi, out_lo,
-                                       out_choff=64, lrelu=cfg["lrelu"], numerics=numerics,
+                                       out_choff=ochoff, lrelu=cfg["lrelu"], numerics=numerics,
                                        mblocks=cfg["mb"], desc_mode=desc_mode, max_ctas=cfg["max_ctas"], **kw)
         torch.cuda.synchronize()
         note("inputs ready")
@@ -200,8 +207,8 @@ def run_case(name, desc_mode):
         if cfg["nchw"]:
             got = out.double()
         else:
-            got = decode(out_hi, out_lo, True)[:, 64:64 + cout]
-            untouched = float(out_hi[..., :64].abs().max()) + float(out_hi[..., 64 + cout:].abs().max())
+            got = decode(out_hi, out_lo, True)[:, ochoff:ochoff + cout]
+            untouched = (float(out_hi[..., :ochoff].abs().max()) if ochoff else 0.0) + (float(out_hi[..., ochoff + cout:].abs().max()) if ochoff + cout < octot else 0.0)
         if cfg["time"]:
             for _ in range(3):
                 call()
