@@ -116,6 +116,10 @@ def run_case(name, desc_mode):
     cases["exact16_t48_off16"] = dict(cout=16, cin=16, ctot=16, exact=True, mb=2, nb=2, octot=48, ochoff=16)
     cases["time_exact16_t16_256"] = dict(cout=16, cin=16, ctot=16, exact=True, mb=2, nb=32, h=256, w=256, time=True, octot=16, ochoff=0)
     cases["time_exact16_c16_256_o32"] = dict(cout=16, cin=16, ctot=32, exact=True, mb=2, nb=32, h=256, w=256, time=True, octot=32, ochoff=0)
+    # output layout: 64-byte results into 384-byte records (the RDB concat buffer) vs a compact 32-channel plane
+    for cc in (64, 96, 128, 160):
+        cases[f"time_exact32_c{cc}_o32"] = dict(nb=64, cin=cc, exact=True, mb=2, time=True, octot=32, ochoff=0)
+    cases["time_fast32_c64_o32"] = dict(nb=64, cin=64, mb=2, time=True, octot=32, ochoff=0)
     cases["small_multi"] = dict(nb=8, max_ctas=4)
     cases["small_multi_mb2"] = dict(nb=8, max_ctas=4, mb=2)
     cases["small_multi_exact"] = dict(nb=8, max_ctas=4, exact=True)
