@@ -591,7 +591,7 @@ extern "C" int bhsr_channel_stats(const float* y, int32_t y_ctot, int32_t y_chof
 extern "C" size_t bhsr_head_wgrad_workspace_bytes(int32_t nb, int32_t cin, int32_t cout, int32_t ksize, int32_t h,
                                                   int32_t w) {
   const int cinp = (cin + 15) / 16 * 16;
-  const int nco = cout <= 16 ? 16 : 64;
+  const int nco = cout <= 16 ? 16 : cout <= 32 ? 32 : 64;
   const int wp = (w + 7) / 8 * 8;
   const size_t xplane = static_cast<size_t>(nb) * cinp * h * wp * 2;
   const size_t gplane = static_cast<size_t>(nb) * nco * h * wp * 2 * ksize;   // one shifted dY copy per kx
@@ -611,7 +611,7 @@ extern "C" int bhsr_head_wgrad_tc(const BhsrHeadXform* xt, const BhsrHeadXform* 
   const int cin = xt->c, cout = gt->c, h = xt->h, w = xt->w;
   BHSR_REQUIRE(cout <= 64, "head_wgrad_tc: at most 64 output channels (got %d)", cout);
   const int cinp = (cin + 15) / 16 * 16;
-  const int nco = cout <= 16 ? 16 : 64;
+  const int nco = cout <= 16 ? 16 : cout <= 32 ? 32 : 64;
   const int mrows = ksize * cinp, mblk = (mrows + 127) / 128;
   BHSR_REQUIRE(ksize * mblk * 2 * nco <= 512, "head_wgrad_tc: cin %d x cout %d does not fit the TMEM accumulators", cin, cout);
   BHSR_REQUIRE(cinp <= 256, "head_wgrad_tc: cin too large");
@@ -669,8 +669,9 @@ extern "C" int bhsr_head_wgrad_tc(const BhsrHeadXform* xt, const BhsrHeadXform* 
   if (rc) return rc;
   rc = make_nchw_map(&gl, g_lo, nb * ksize, nco, h, w, wp, nco, 1);
   if (rc) return rc;
-  rc = nco == 16 ? launch_wgrad<16>(xh, xl, gh, gl, p, grid, smem, stream)
-                 : launch_wgrad<64>(xh, xl, gh, gl, p, grid, smem, stream);
+  rc = nco == 16   ? launch_wgrad<16>(xh, xl, gh, gl, p, grid, smem, stream)
+       : nco == 32 ? launch_wgrad<32>(xh, xl, gh, gl, p, grid, smem, stream)
+                   : launch_wgrad<64>(xh, xl, gh, gl, p, grid, smem, stream);
   if (rc) return rc;
   // padded input channels (cin..cinp) are zero rows: the reduce kernel walks the logical cin only
   wgrad_reduce_kernel<<<ksize * cin * ksize, 256, 0, stream>>>(partial, grid, ksize, mblk * 128, nco, cin, cout,

@@ -11,8 +11,8 @@ from the same kernels:
                   five contributions a ResidualDenseBlock's concat channels receive (SR/rrdbnet_arch.py:137-143) add up
                   in one 192-channel gradient buffer; the gradient is pre-scaled by a power of two before the hi/lo split
                   (fp16 range) and un-scaled by the conv's per-channel `scale` vector;
-  weight gradient dW = sum_pixels dY * X: `bhsr_head_wgrad_tc` (tcgen05, K = pixels; head_tc.cu) on 32-input-channel
-                  groups (its TMEM budget), reading channel slices of the fp32 copy of the saved concat buffer;
+  weight gradient dW = sum_pixels dY * X: `bhsr_head_wgrad_tc` (tcgen05, K = pixels; head_tc.cu) on groups of 64 (32-output
+                  convs) or 32 (64-output convs) input channels (its TMEM budget), reading channel slices of the fp32 copy of the saved concat buffer;
   LeakyReLU       mask from the SAVED post-activation values (sign-preserving), nearest-x2 upsample backward = 2x2 sum.
 
 Saved activations are the NHWC hi/lo planes the forward pass produces anyway: one 192-channel concat buffer per RDB
@@ -68,7 +68,8 @@ def conv_backward(x_f32: Tensor, x_choff: int, cin: int, g: Tensor, weight: Tens
     dw = db = None
     if need_dw:
         dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
-        group = 32 if cout > 16 else 64          # TMEM budget of wgrad_tc_kernel: 3 * ceil(3 cin / 128) * 2 * nco <= 512
+        # TMEM budget of wgrad_tc_kernel: 3 * ceil(3 cin / 128) * 2 * nco <= 512 with nco = 16 / 32 / 64 padded outputs
+        group = 32 if cout > 32 else 64
         for c0 in range(0, cin, group):
             cg = min(group, cin - c0)
             xf = ops.head_xform(x_f32, cg, h, w)
