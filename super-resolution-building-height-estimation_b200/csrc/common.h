@@ -35,4 +35,8 @@ EncodeTiledFn get_encode_tiled();
 
 int device_sm_count();
 
+// plumbing.cu: pack a conv whose weight tensor has fewer rows than the kernel's (padded) output count
+int pack_conv_weights_padded(const float* w_oihw, int cout_real, int cout_pad, int cin, int numerics, void* w_packed,
+                             void* stream);
+
 }  // namespace bhsr

@@ -18,7 +18,7 @@ __device__ __forceinline__ void split2(float v, __half& hi, __half& lo) {
 // ch = channels per chunk = 64 (fast) or 32 (exact), matching conv_tc.cu.
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int cout, int cin,
                                          int fold_phase, int exact, __half* __restrict__ out,
-                                         int ntaps, size_t total) {
+                                         int ntaps, size_t total, int cout_real) {
   size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int rows = exact ? 2 * cout : cout;
@@ -33,7 +33,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int cout, 
   const int n = row % cout;
   const int part = row / cout;
   float v = 0.f;
-  if (ch < cin) {
+  if (ch < cin && n < cout_real) {      // rows [cout_real, cout) are zero padding (the weight tensor has cout_real rows)
     const float* wp = w + (static_cast<size_t>(n) * cin + ch) * 9;
     if (fold_phase < 0) {
       v = wp[tap];
@@ -251,7 +251,22 @@ extern "C" int bhsr_pack_conv_weights(const float* w_oihw, int32_t cout, int32_t
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
   pack_conv_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, cout, cin, fold_phase, exact, static_cast<__half*>(w_packed), ntaps, total);
+      w_oihw, cout, cin, fold_phase, exact, static_cast<__half*>(w_packed), ntaps, total, cout);
+  BHSR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// [cout_real, cin, 3, 3] fp32 -> packed blob of a conv with cout_pad (32 / 64) outputs whose extra rows are zero
+// (conv_last of RRDBNet.forward on the tensor-core kernel: rrdbnet.cu)
+int bhsr::pack_conv_weights_padded(const float* w_oihw, int cout_real, int cout_pad, int cin, int numerics,
+                                   void* w_packed, void* stream) {
+  BHSR_REQUIRE(w_oihw && w_packed && cout_real > 0 && cout_real <= cout_pad && cin > 0, "pack_conv_weights_padded: bad arguments");
+  const int exact = numerics == BHSR_NUMERICS_EXACT_F16X3;
+  const size_t total = bhsr_packed_conv_weight_bytes(cout_pad, cin, 9, numerics) / sizeof(__half);
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  pack_conv_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, cout_pad, cin, -1, exact, static_cast<__half*>(w_packed), 9, total, cout_real);
   BHSR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

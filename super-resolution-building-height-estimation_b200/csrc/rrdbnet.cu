@@ -16,7 +16,7 @@
 //   trunk   [nb][h][w][64]    feat + conv_body(body(feat))
 //   up1     [nb][2h][2w][64]
 //   up2     [nb][4h][4w][64]
-//   hr      [nb][4h][4w][64]  only for forward() (conv_hr output feeding conv_last)
+//   hr      [nb][4h][4w][64]  only for forward(): lrelu(conv_hr) feeding conv_last, + conv_last's packed weights / bias
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <string.h>
@@ -34,6 +34,8 @@ struct Planes {
 
 struct Workspace {
   Planes buf[3], feat, trunk, up1, up2, hr;
+  void* last_w;      // forward(): conv_last packed for the tensor-core kernel (3 outputs padded to 32)
+  float* last_b;     // ... and its bias padded to 32 floats
   size_t total;
 };
 
@@ -55,7 +57,13 @@ static Workspace carve(void* base, int nb, int h, int w, bool feature_only) {
   ws.trunk = take(px, 64);
   ws.up1 = take(px * 4, 64);
   ws.up2 = take(px * 16, 64);
-  if (!feature_only) ws.hr = take(px * 16, 64);
+  if (!feature_only) {
+    ws.hr = take(px * 16, 64);
+    ws.last_w = static_cast<char*>(base) + off;
+    off += align_up(bhsr_packed_conv_weight_bytes(32, 64, 9, BHSR_NUMERICS_EXACT_F16X3), 1024);
+    ws.last_b = reinterpret_cast<float*>(static_cast<char*>(base) + off);
+    off += 1024;
+  }
   ws.total = off;
   return ws;
 }
@@ -275,14 +283,27 @@ extern "C" int bhsr_rrdbnet_forward(const BhsrRrdbNetDesc* dp, const float* x, i
       cd.epilogue = BHSR_EPI_OUT_NCHW_F32;
     } else {
       cd.out_hi = ws.hr.hi; cd.out_lo = ws.hr.lo; cd.out_ctot = 64; cd.out_choff = 0;
-      cd.epilogue = 0;
+      cd.epilogue = BHSR_EPI_LRELU;        // conv_last reads lrelu(conv_hr) (SR/rrdbnet_arch.py:222)
     }
     rc = bhsr_conv_tc(&cd, stream);
     if (rc) return rc;
     advance(64);
     if (!feature) {
-      rc = bhsr_conv3x3_last(ws.hr.hi, ws.hr.lo, 64, 0, d.nb, 64, h, w, /*lrelu_in=*/1,
-                             d.conv_last_w, d.conv_last_b, d.num_out_ch, y, stream);
+      // conv_last (64 -> num_out_ch) on the tensor-core kernel: outputs padded to 32, fp32 NCHW epilogue writes the real
+      // ones.  (Round 1 ran it as a thread-per-pixel CUDA-core kernel: 1.9 ms at B = 12, 256x256 — 60x its HBM time.)
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      rc = pack_conv_weights_padded(d.conv_last_w, d.num_out_ch, 32, 64, d.numerics, ws.last_w, stream);
+      if (rc) return rc;
+      BHSR_CUDA_CHECK(cudaMemsetAsync(ws.last_b, 0, 32 * sizeof(float), st));
+      BHSR_CUDA_CHECK(cudaMemcpyAsync(ws.last_b, d.conv_last_b, d.num_out_ch * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      BhsrConvTcDesc cl = base_desc(ws.hr, 64, 64, 32, h, w);
+      plain_taps(cl);
+      cl.w_packed = ws.last_w;
+      cl.bias = ws.last_b;
+      cl.out_f32 = y; cl.out_ctot = d.num_out_ch; cl.out_choff = 0;
+      cl.cout_valid = d.num_out_ch;
+      cl.epilogue = BHSR_EPI_OUT_NCHW_F32;
+      rc = bhsr_conv_tc(&cl, stream);
       if (rc) return rc;
     }
   }

@@ -161,7 +161,15 @@ class RRDBNetTrainFn(torch.autograd.Function):
                 hr = _planes(nb, 4 * h, 4 * w, 64, dev)
                 ops.conv_tc(up2[0], up2[1], 0, 64, ops.pack_conv_weights(W(i_hr), num), 64, B(i_hr), ops.PLAIN_TAPS,
                             hr[0], hr[1], out_choff=0, lrelu=True, numerics=num)
-                y = ops.conv3x3_last(hr[0], hr[1], 0, 64, W(i_hr + 1), B(i_hr + 1), False)
+                # conv_last on the tensor-core kernel (outputs padded to 32; the fp32 NCHW epilogue stores the real ones)
+                n_out = W(i_hr + 1).shape[0]
+                if n_out > 32:
+                    raise NotImplementedError("RRDBNet under autograd: at most 32 output channels")
+                b_last = torch.zeros(32, dtype=torch.float32, device=dev)
+                b_last[:n_out] = B(i_hr + 1)
+                y = torch.empty((nb, n_out, 4 * h, 4 * w), dtype=torch.float32, device=dev)
+                ops.conv_tc(hr[0], hr[1], 0, 64, ops.pack_conv_weights(_pad_oihw(W(i_hr + 1), 32, 64), num), 32, b_last,
+                            ops.PLAIN_TAPS, None, None, out_f32=y, cout_valid=n_out, numerics=num)
         ctx.n_rdb, ctx.feature = n_rdb, feature
         ctx.x = x
         ctx.weights = [W(i) for i in range(len(convs))]
