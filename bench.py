@@ -6,7 +6,7 @@ RRDBNet-23 x4 `forward_feature`, batch 64 per GPU, 6-band 64x64 synthetic tiles 
 the RGB view x[:, :3] like train.py:244), random-init weights of the reference architecture.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--numerics exact|fast] [--batch B]
-    python bench.py --impl reference ...     # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference ...     # the reference's CPU path on host cores (staged reference, else oracle port)
 
 value  : tiles/s with inputs resident in HBM (CUDA events, max over ranks).
 e2e    : same metric through the public nn.Module call with HOST (pinned) input every step
@@ -196,23 +196,46 @@ def layer_kernels_live(dev, B, numerics):
 
 # ---------------------------------------------------------------------------------- reference arm
 def cpu_reference_run(args, steps, warmup, tiles_per_step):
-    """The reference's CPU path for the same workload: oracle/ref_torch.py (the stock
-    torch.nn.functional calls the reference modules dispatch to), all host threads."""
+    """The reference's CPU path for the same workload on all host threads.  With the staged reference present
+    (baseline/_ref, written by oracle/stage_reference.py in the build container; it travels to the GPU box) this is the
+    UNMODIFIED reference `RRDBNet(3, 3, 4, 64, 23, 32).forward_feature` (SR/rrdbnet_arch.py:227-240) in eval mode under
+    no_grad — kind "reference"; otherwise the oracle port oracle/ref_torch.py (the torch.nn.functional calls the
+    reference modules dispatch to) — kind "port".  Same synthetic weights and tiles either way.
+    Returns (tiles/s, ms/step, threads, kind, description)."""
     import torch
-    from oracle import ref_torch as T
     import synth
+    from oracle import stage_reference
     torch.set_num_threads(os.cpu_count() or 1)
     net = synth_state_torch(NUM_BLOCK)
     sd = {k: v.detach() for k, v in net.state_dict().items()}
     x = torch.from_numpy(synth.tiles(tiles_per_step, 6, seed=1337))[:, :3]
+    if stage_reference.available() and os.environ.get("BHSR_CPU_ARM", "reference") != "port":
+        ref = stage_reference.load().arch.RRDBNet(3, 3, 4, 64, NUM_BLOCK, 32)
+        ref.load_state_dict(sd, strict=True)
+        ref.eval()
+        kind = "reference"
+        what = ("baseline/_ref/SR/rrdbnet_arch.py = the UNMODIFIED reference RRDBNet.forward_feature (eval, no_grad, "
+                "torch CPU)")
+
+        def run():
+            with torch.no_grad():
+                return ref.forward_feature(x)
+    else:
+        from oracle import ref_torch as T
+        kind = "port"
+        what = ("oracle/ref_torch.py = oracle PORT of the reference modules (torch.nn.functional on CPU) — no staged "
+                "reference under baseline/_ref")
+
+        def run():
+            return T.rrdbnet_forward_feature(x, sd)
     for _ in range(warmup):
-        T.rrdbnet_forward_feature(x, sd)
+        run()
     t0 = time.perf_counter()
     for _ in range(steps):
-        y = T.rrdbnet_forward_feature(x, sd)
+        y = run()
     dt = time.perf_counter() - t0
     del y
-    return tiles_per_step * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+    return tiles_per_step * steps / dt, dt / steps * 1e3, torch.get_num_threads(), kind, what
 
 
 def forward_config(B, tiles, numerics, world):
@@ -226,21 +249,22 @@ def forward_config(B, tiles, numerics, world):
 
 
 def reference_main(args):
-    """`--impl reference`: the reference's own CPU path for the same config on the box's host cores — the oracle
-    port (oracle/ref_torch.py: the stock torch.nn.functional calls the reference modules dispatch to; the
-    reference is a script repo that cannot be installed and /root/reference is not on the GPU box).  Honours
+    """`--impl reference`: the reference's own CPU path for the same config on the box's host cores — the UNMODIFIED
+    reference module from the staged copy baseline/_ref (oracle/stage_reference.py; `cpu_baseline.kind` "reference"),
+    or, on a clone without the staged copy, the oracle port oracle/ref_torch.py (kind "port"; the reference is a script
+    repo that cannot be pip-installed and /root/reference is not on the GPU box).  Honours
     --steps / --warmup; each step is a bounded sample of the arm's batch (8 tiles: the host path's best batch size),
     shrunk only if a probe step says the whole run would not end within CPU_ARM_BUDGET_S."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    probe_tps, _, cores = cpu_reference_run(args, 1, 0, 2 if args.cpu_sample_tiles in (1, 2) else 4)
+    probe_tps = cpu_reference_run(args, 1, 0, 2 if args.cpu_sample_tiles in (1, 2) else 4)[0]
     # 8 tiles per CPU step is where the host path peaks (measured on the GPU box: 11.2 tiles/s at 8 tiles per
     # step, 5.8 tiles/s at the arm's 64 — the 1 GB activations of a 64-tile batch fall out of the host caches),
     # so the reference is timed at ITS best batch; fewer only if the run would not fit the time budget
     tiles = int(min(args.batch, args.cpu_sample_tiles or 8, max(1, CPU_ARM_BUDGET_S * probe_tps / (steps + warmup))))
-    tps, ms, cores = cpu_reference_run(args, steps, warmup, tiles)
+    tps, ms, cores, kind, what = cpu_reference_run(args, steps, warmup, tiles)
     cfg = forward_config(args.batch, args.batch, "f32 (reference CPU path)", 1)
     cfg["cpu_tiles_per_step"] = tiles
     line = {
@@ -249,10 +273,8 @@ def reference_main(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": cfg,
-        "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps x {tiles} tiles (+{warmup} warm-up), oracle/ref_torch.py = oracle PORT of "
-                                   f"the reference modules (torch.nn.functional on CPU, {cores} threads) — /root/reference "
-                                   f"is not on the GPU box"},
+        "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} steps x {tiles} tiles (+{warmup} warm-up), {what}, {cores} threads"},
         "e2e": {"value": tps, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -554,11 +576,9 @@ def main():
         line["train"] = train_leg(args, dev, dist, world, rank, K, W, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_tiles = args.cpu_sample_tiles or 8
-        tps, cms, cores = cpu_reference_run(args, 2, 1, cpu_tiles)
-        line["cpu_baseline"] = {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
-                                "sample": f"2 steps x {cpu_tiles} tiles of the same workload, "
-                                          "oracle/ref_torch.py = oracle PORT of the reference modules "
-                                          "(torch.nn.functional, all host threads)"}
+        tps, cms, cores, kind, what = cpu_reference_run(args, 2, 1, cpu_tiles)
+        line["cpu_baseline"] = {"value": tps, "unit": "tiles/s", "cores": cores, "kind": kind,
+                                "sample": f"2 steps x {cpu_tiles} tiles of the same workload, {what}, all host threads"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
