@@ -67,11 +67,25 @@ def _default_numerics() -> str:
     return mode
 
 
+def _wants_autograd(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def _no_autograd(name: str, *tensors) -> None:
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError(
-            f"{name}: backward through a stand-alone block is not built (RRDBNet.forward / forward_feature have one, "
-            "rrdbnet_train.py); call under torch.no_grad() / detach inputs and set requires_grad=False on its parameters")
+    if _wants_autograd(*tensors):
+        raise NotImplementedError(f"{name}: this entry is the frozen (no-grad) schedule; the autograd path is "
+                                  "rrdbnet_train.py — call the module's forward / forward_feature instead")
+
+
+def _block_autograd(convs, x, rrdb: bool):
+    """A stand-alone dense block / RRDB under autograd: exact numerics, tensor-core backward (rrdbnet_train.py)."""
+    from .rrdbnet_train import RDBChainTrainFn
+    params = []
+    for c in convs:
+        if c.bias is None:
+            raise NotImplementedError("ResidualDenseBlock / RRDB under autograd: convs without bias are not supported")
+        params += [c.weight, c.bias]
+    return RDBChainTrainFn.apply(convs, x, rrdb, *params)
 
 
 # ------------------------------------------------------------------ blocks (parameter containers)
@@ -121,8 +135,9 @@ class ResidualDenseBlock(nn.Module):
 
     def forward(self, x):
         _lib.require_cuda(x, "x")
-        _no_autograd("ResidualDenseBlock", x, *self.parameters())
         _check_widths(self.conv1.in_channels, self.conv1.out_channels)
+        if _wants_autograd(x, *self.parameters()):
+            return _block_autograd(self._convs(), x, rrdb=False)
         nb, _, h, w = x.shape
         cur = _new_planes(nb, h, w, 192, x.device)
         nxt = _new_planes(nb, h, w, 192, x.device)
@@ -143,8 +158,9 @@ class RRDB(nn.Module):
 
     def forward(self, x):
         _lib.require_cuda(x, "x")
-        _no_autograd("RRDB", x, *self.parameters())
         _check_widths(self.rdb1.conv1.in_channels, self.rdb1.conv1.out_channels)
+        if _wants_autograd(x, *self.parameters()):
+            return _block_autograd(self.rdb1._convs() + self.rdb2._convs() + self.rdb3._convs(), x, rrdb=True)
         nb, _, h, w = x.shape
         bufs = [_new_planes(nb, h, w, 192, x.device) for _ in range(3)]
         ops.nchw_to_planes(x.float().contiguous(), bufs[0][0], bufs[0][1], 0)

@@ -18,6 +18,9 @@ from the same kernels:
 Saved activations are the NHWC hi/lo planes the forward pass produces anyway: one 192-channel concat buffer per RDB
 (2 x 192 x 2 B per pixel: 13.9 GB for 23 blocks at B = 64, 64x64 — sized for 180 GB of HBM, no recomputation).
 This path is functional and parity-tested, not yet tuned: weight packing and fp32 copies happen per call.
+
+Stand-alone `ResidualDenseBlock` / `RRDB` modules (SR/rrdbnet_arch.py:113-167) get the same treatment from
+`RDBChainTrainFn` (one or three dense blocks, same kernels, same saved planes).
 """
 from __future__ import annotations
 
@@ -265,3 +268,79 @@ class RRDBNetTrainFn(torch.autograd.Function):
             dw, db = conv_backward(xc, 0, cin0, d_feat.contiguous(), Wt[0], dx)
             put(0, dw, db)
         return (None, dx, None, *grads)
+
+
+class RDBChainTrainFn(torch.autograd.Function):
+    """A stand-alone `ResidualDenseBlock` (rrdb=False, five convs; SR/rrdbnet_arch.py:137-143) or `RRDB` (rrdb=True,
+    fifteen convs, `out * 0.2 + x` around three dense blocks; :160-167) with a backward pass — the trunk section of
+    `RRDBNetTrainFn` on its own.  `convs`: conv1..conv5 of every dense block in order; `params`: their weights and
+    biases flat (weight then bias)."""
+
+    @staticmethod
+    def forward(ctx, convs: Sequence[torch.nn.Conv2d], x: Tensor, rrdb: bool, *params: Tensor) -> Tensor:
+        num = NUMERICS_EXACT
+        n_rdb = len(convs) // 5
+        assert len(convs) == (15 if rrdb else 5) and len(params) == 2 * len(convs)
+        x = x.detach().float().contiguous()
+        nb, _, h, w = x.shape
+        dev = x.device
+        P = [p.detach().to(dev, torch.float32).contiguous() for p in params]
+        with torch.cuda.device(dev):
+            cats = [_planes(nb, h, w, 192, dev) for _ in range(n_rdb)]
+            out = _planes(nb, h, w, 64, dev)
+            ops.nchw_to_planes(x, cats[0][0], cats[0][1], 0)
+            for r in range(n_rdb):
+                cur = cats[r]
+                nxt = cats[r + 1] if r + 1 < n_rdb else out
+                for k in range(5):
+                    ci = 5 * r + k
+                    cin = 64 + 32 * k
+                    wp = ops.pack_conv_weights(P[2 * ci], num)
+                    if k < 4:
+                        ops.conv_tc(cur[0], cur[1], 0, cin, wp, 32, P[2 * ci + 1], ops.PLAIN_TAPS, cur[0], cur[1],
+                                    out_choff=cin, lrelu=True, numerics=num)
+                    else:
+                        kw = {}
+                        if rrdb and r == 2:                # third dense block of an RRDB: out * 0.2 + RRDB input
+                            kw = dict(res2=(cats[0][0], cats[0][1], 0), alpha2=_SLOPE)
+                        ops.conv_tc(cur[0], cur[1], 0, cin, wp, 64, P[2 * ci + 1], ops.PLAIN_TAPS, nxt[0], nxt[1],
+                                    out_choff=0, res1=(cur[0], cur[1], 0), alpha1=_SLOPE, numerics=num, **kw)
+            y = ops.planes_to_nchw(out[0], out[1], 64, 0)
+        ctx.rrdb = rrdb
+        ctx.weights = [P[2 * i] for i in range(len(convs))]
+        ctx.cats = cats
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        cats, Wt, rrdb = ctx.cats, ctx.weights, ctx.rrdb
+        n_rdb = len(cats)
+        need = ctx.needs_input_grad          # (convs, x, rrdb, *params)
+        grads: List[Optional[Tensor]] = [None] * (2 * len(Wt))
+        d = gy.contiguous().float()
+        with torch.cuda.device(d.device):
+            d_out = d                                       # gradient of the block's output
+            if rrdb:
+                d = d * _SLOPE                              # into the third dense block's output
+            for r in range(n_rdb - 1, -1, -1):
+                cat_f = ops.planes_to_nchw(cats[r][0], cats[r][1], 192, 0)
+                d_cat = torch.zeros_like(cat_f)
+                d_cat[:, :64] += d                          # x5 * 0.2 + x: identity branch
+                gk = (d * _SLOPE).contiguous()
+                for k in range(4, -1, -1):
+                    ci = 5 * r + k
+                    cin = 64 + 32 * k
+                    if k < 4:
+                        sl = slice(cin, cin + 32)
+                        gk = (d_cat[:, sl] * _lrelu_mask(cat_f[:, sl])).contiguous()
+                    need_dw = need[3 + 2 * ci] or need[3 + 2 * ci + 1]
+                    dw, db = conv_backward(cat_f, 0, cin, gk, Wt[ci], d_cat, need_dw=need_dw)
+                    if need[3 + 2 * ci]:
+                        grads[2 * ci] = dw
+                    if need[3 + 2 * ci + 1]:
+                        grads[2 * ci + 1] = db
+                d = d_cat[:, :64].contiguous()
+                del cat_f, d_cat
+            if rrdb:
+                d = d + d_out                               # RRDB: out * 0.2 + x
+        return (None, d if need[1] else None, None, *grads)

@@ -529,8 +529,8 @@ def test_error_behaviour(dev):
     net = rrdbnet.RRDBNet(3, 3, num_block=1).to(dev)
     with pytest.raises(BhsrError):
         net.forward_feature(torch.zeros(1, 3, 64, 64))  # CPU tensor: no fallback
-    with pytest.raises(NotImplementedError):   # stand-alone blocks have no backward (the full net does: rrdbnet_train.py)
-        net.body[0](torch.zeros(1, 64, 16, 16, device=dev, requires_grad=True))
+    # stand-alone blocks run under autograd too (rrdbnet_train.RDBChainTrainFn)
+    assert net.body[0](torch.zeros(1, 64, 16, 16, device=dev, requires_grad=True)).requires_grad
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             net.forward_feature(torch.zeros(1, 5, 64, 64, device=dev))
@@ -618,6 +618,66 @@ def test_rrdbnet_backward_vs_oracle_autograd(dev, feature, num_block, nb, hw, ti
     bound = 2e-4 if tight else 2e-2
     bad = {k: v for k, v in errs.items() if not v < bound}
     assert not bad, f"gradient rel-L2 above {bound}: {bad}"
+
+
+@pytest.mark.parametrize("kind,nb,hw", [("rdb", 2, 16), ("rrdb", 1, 16), ("rrdb", 3, 12)])
+def test_standalone_blocks_backward_vs_oracle_autograd(dev, kind, nb, hw):
+    """`ResidualDenseBlock` / `RRDB` called on their own under autograd (SR/rrdbnet_arch.py:137-143, 160-167):
+    output, input gradient and every parameter gradient against fp64 autograd of the oracle.  The data seed is searched
+    for an input without a LeakyReLU pre-activation within 2e-6 of zero (see test_rrdbnet_backward_vs_oracle_autograd)."""
+    import torch.nn.functional as F
+    from bhsr import rrdbnet
+    from oracle import ref_torch as T
+    full = synth.rrdbnet_state(num_block=1, seed=55)
+    pre = "body.0." if kind == "rrdb" else "body.0.rdb2."
+    sd = {k[len(pre):]: v for k, v in full.items() if k.startswith(pre)}
+    orig = F.leaky_relu
+    for seed in range(40):
+        rng = np.random.RandomState(77 * hw + seed)
+        x = (rng.standard_normal((nb, 64, hw, hw)) * 0.5).astype(np.float32)
+        wy = rng.standard_normal((nb, 64, hw, hw)).astype(np.float32)
+        p = {("blk." + k): torch.from_numpy(np.ascontiguousarray(v)).double().requires_grad_(True) for k, v in sd.items()}
+        xt = torch.from_numpy(x).double().requires_grad_(True)
+        zmin = [float("inf")]
+
+        def spy(inp, negative_slope=0.01, inplace=False):
+            zmin[0] = min(zmin[0], float(inp.detach().abs().min()))
+            return orig(inp, negative_slope, False)
+
+        F.leaky_relu = spy
+        try:
+            y_ref = T.rrdb(xt, p, "blk") if kind == "rrdb" else T.residual_dense_block(xt, p, "blk")
+        finally:
+            F.leaky_relu = orig
+        (y_ref * torch.from_numpy(wy).double()).sum().backward()
+        if zmin[0] > 2e-6:
+            break
+    else:
+        pytest.fail("no well-conditioned input found in 40 seeds")
+    blk = rrdbnet.RRDB(64, 32) if kind == "rrdb" else rrdbnet.ResidualDenseBlock(64, 32)
+    blk = load_np_state(blk, sd, dev)
+    blk.train()
+    xc = cuda(x, dev).requires_grad_(True)
+    y = blk(xc)
+    assert y.requires_grad
+    (y * cuda(wy, dev)).sum().backward()
+    assert_close(y.detach().cpu().numpy(), y_ref.detach().numpy(), 1e-3, 1e-4, f"stand-alone {kind} forward under autograd")
+    with torch.no_grad():
+        y_frozen = blk(xc.detach())
+    assert_close(y_frozen.cpu().numpy(), y_ref.detach().numpy(), 1e-3, 1e-4, f"stand-alone {kind} frozen forward")
+
+    def rel_l2(a, b):
+        return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+    errs = {"dL/dx": rel_l2(xc.grad.cpu().numpy(), xt.grad.numpy())}
+    for name, prm in blk.named_parameters():
+        assert prm.grad is not None, name
+        errs[name] = rel_l2(prm.grad.cpu().numpy(), p["blk." + name].grad.numpy())
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print(f"stand-alone {kind} backward (nb={nb}, {hw}x{hw}, seed {seed}, min|z| {zmin[0]:.1e}): "
+          f"dL/dx rel-L2 {errs['dL/dx']:.2e}, worst gradient rel-L2 {worst[1]:.2e} ({worst[0]})")
+    bad = {k: v for k, v in errs.items() if not v < 2e-4}
+    assert not bad, f"gradient rel-L2 above 2e-4: {bad}"
 
 
 def test_rrdbnet_finetune_step_reduces_l1_loss(dev):
