@@ -201,6 +201,57 @@ def test_cuda_head_blocks_vs_live_reference(ref, dev):
 
 @needs_ref
 @pytest.mark.gpu
+@pytest.mark.parametrize("training", [True, False])
+def test_cuda_head_training_step_vs_live_reference_autograd(ref, dev, training):
+    """Row K10: HRfeature -> HRfuse_residual under autograd (tcgen05 forward / dgrad / wgrad, BatchNorm forward and
+    backward kernels) against the live reference modules differentiated by stock PyTorch autograd in fp64
+    (SR/HRfuse.py:143-190 as driven by train.py:246-257): output, both input gradients, every parameter gradient and
+    the BatchNorm running statistics."""
+    from bhsr import hrfuse
+    oc = 7
+    sdf = synth.hrfeature_state(seed=81)
+    sdr = synth.hrfuse_residual_state(out=oc, seed=82)
+    hr = synth.features(2, 64, 32, 32, seed=14)
+    lr = synth.features(2, 16, 8, 8, seed=15)
+    g = np.random.RandomState(16).standard_normal((2, oc, 32, 32)).astype(np.float32)
+
+    rf = ref.hrfuse.HRfeature(in_chans=64, mid_chans=16, out_chans=16)
+    rf.load_state_dict(_tsd(sdf), strict=True)
+    rr = ref.hrfuse.HRfuse_residual(hr_chans=16, lr_chans=16, mid_chans=16, out_chans=oc, upscale=4)
+    rr.load_state_dict(_tsd(sdr), strict=True)
+    rf, rr = rf.double().train(training), rr.double().train(training)
+    a = torch.from_numpy(lr).double().requires_grad_(True)
+    b = torch.from_numpy(hr).double().requires_grad_(True)
+    y = rr(a, rf(b))
+    (y * torch.from_numpy(g).double()).sum().backward()
+
+    mf = _load(hrfuse.HRfeature(64, 16, 16), sdf, dev).train(training)
+    mr = _load(hrfuse.HRfuse_residual(16, 16, 16, oc, 4), sdr, dev).train(training)
+    ac = torch.from_numpy(lr).to(dev).requires_grad_(True)
+    bc = torch.from_numpy(hr).to(dev).requires_grad_(True)
+    yc = mr(ac, mf(bc))
+    (yc * torch.from_numpy(g).to(dev)).sum().backward()
+
+    assert_close(yc.detach().cpu().numpy(), y.detach().numpy(), what="forward")
+    scale = lambda r: 1e-4 * max(1.0, float(np.abs(r).max()))
+    for got, want, what in ((ac.grad, a.grad, "grad x_lr"), (bc.grad, b.grad, "grad hr_fea")):
+        assert_close(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=scale(want.numpy()), what=what)
+    for mod, rmod, tag in ((mf, rf, "hrfeat"), (mr, rr, "fuse")):
+        rgrads = dict(rmod.named_parameters())
+        for name, prm in mod.named_parameters():
+            assert prm.grad is not None, name
+            want = rgrads[name].grad.numpy()
+            assert_close(prm.grad.cpu().numpy(), want, rtol=2e-3, atol=scale(want), what=f"grad {tag}.{name}")
+        rbufs = dict(rmod.named_buffers())
+        for name, buf in mod.named_buffers():
+            if "running" in name:
+                np.testing.assert_allclose(buf.cpu().numpy(), rbufs[name].numpy(), rtol=1e-4, atol=1e-5, err_msg=name)
+            elif "num_batches_tracked" in name:
+                assert int(buf) == int(rbufs[name]), name
+
+
+@needs_ref
+@pytest.mark.gpu
 def test_cuda_aggregate_vs_live_reference(ref, dev):
     """aggregate_torch / aggregate_torch_gpu (aggregate_utils.py:29-59): 4x4 block sums over the valid-pixel count of
     256x256 height labels (82 % zeros, like the loader's), against the live reference functions (a stock conv on the
