@@ -277,11 +277,19 @@ int bhsr_aggregate(const float* x, int32_t nimg, int32_t h, int32_t w, int32_t s
  * bhsr_weighted_mse: losses_pytorch/selfloss.py:81-90 — loss = mean(weight * (pred - target)^2) * exp(-log_var) +
  *   log_var, forward and backward in one pass: grad_pred[n] (may be NULL), *grad_log_var (may be NULL), *loss;
  *   scratch = one double of device memory.
+ * bhsr_ce_dice: losses_pytorch/selfloss.py:145-168 (CE_DICE_adapt_weight; Dice :6-17) — logits [nb][c][h][w] fp32,
+ *   labels [nb][h][w] int64 in [0, c), weight [nb][h][w] fp32:
+ *   loss = (mean(weight * CE(logits, labels)) + Dice(sum_{k>=1} softmax_k, labels > 0)) * exp(-log_var) + log_var,
+ *   forward and backward: grad_logits [nb][c][h][w] (may be NULL), *grad_log_var (may be NULL), *loss;
+ *   2 <= c <= 16; scratch = four doubles of device memory.
  * ------------------------------------------------------------------------------------------ */
 int bhsr_predict_postproc(const float* height, const float* build, int32_t nb, int32_t k, int32_t h, int32_t w,
                           uint16_t* out_height, uint16_t* out_build, void* stream);
 int bhsr_weighted_mse(const float* pred, const float* target, const float* weight, int64_t n, const float* log_var,
                       float* loss, float* grad_pred, float* grad_log_var, double* scratch, void* stream);
+int bhsr_ce_dice(const float* logits, const int64_t* labels, const float* weight, int32_t nb, int32_t c, int32_t h,
+                 int32_t w, const float* log_var, float* loss, float* grad_logits, float* grad_log_var,
+                 double* scratch, void* stream);
 
 #ifdef __cplusplus
 }

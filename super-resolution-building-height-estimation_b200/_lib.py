@@ -160,6 +160,7 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "bhsr_predict_postproc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
     "bhsr_weighted_mse": (C.c_int, [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 6),
+    "bhsr_ce_dice": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p] * 6),
     "bhsr_aggregate": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p,
                                  C.c_void_p]),
     "bhsr_rrdbnet_forward": (C.c_int, [C.POINTER(RrdbNetDesc), C.c_void_p] + [C.c_int64] * 4 +

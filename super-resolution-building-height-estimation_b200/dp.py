@@ -22,11 +22,15 @@
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+
+FUSED_CE_DICE = os.environ.get("BHSR_FUSED_CE_DICE", "1") != "0"   # 0: keep CE_DICE_adapt_weight on stock torch ops
 
 
 class Dice(nn.Module):
@@ -88,8 +92,40 @@ class MSE_adapt_weight(nn.Module):
         return loss * torch.exp(-self.log_var) + self.log_var
 
 
+class _CEDiceFn(torch.autograd.Function):
+    """`bhsr_ce_dice` (post.cu): weighted cross-entropy + Dice, loss and both gradients in two passes over the logits
+    (the Dice gradient needs the global sums of the first pass)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight, log_var):
+        from . import _lib
+        z = logits.contiguous().float()
+        t = labels.contiguous()
+        w = weight.contiguous().float()
+        nb, c, h, wd = z.shape
+        dev = z.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[3]
+        gz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        gs = torch.empty((), dtype=torch.float32, device=dev) if need else None
+        scratch = torch.empty(4, dtype=torch.float64, device=dev)
+        with _lib.on_device(z):
+            _lib.check(_lib.load().bhsr_ce_dice(z.data_ptr(), t.data_ptr(), w.data_ptr(), nb, c, h, wd,
+                                                log_var.data_ptr(), loss.data_ptr(), _lib.ptr(gz), _lib.ptr(gs),
+                                                scratch.data_ptr(), _lib.stream_ptr(dev)), "bhsr_ce_dice")
+        ctx.save_for_backward(gz, gs)
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        gz, gs = ctx.saved_tensors
+        return (gz * go if gz is not None else None, None, None, gs * go if gs is not None else None)
+
+
 class CE_DICE_adapt_weight(nn.Module):
-    """weighted CE + Dice on P(class>0), uncertainty weighted (selfloss.py:145-168)."""
+    """weighted CE + Dice on P(class>0), uncertainty weighted (selfloss.py:145-168).  CUDA fp32 logits [N,C,H,W] with
+    int64 labels and weights [N,H,W] (what train.py:253 passes) run the fused forward+backward kernel (`bhsr_ce_dice`,
+    C <= 16); anything else (host tensors, other shapes) the same formula in torch."""
 
     def __init__(self, log_var=0.0, device="cuda"):
         super().__init__()
@@ -98,6 +134,11 @@ class CE_DICE_adapt_weight(nn.Module):
         self.log_var = nn.Parameter(torch.tensor(float(log_var), device=device))
 
     def forward(self, pmask, rmask, weight):
+        if (FUSED_CE_DICE and pmask.is_cuda and pmask.dtype == torch.float32 and pmask.dim() == 4 and
+                2 <= pmask.shape[1] <= 16 and pmask.numel() > 0 and rmask.dtype == torch.int64 and
+                rmask.shape == (pmask.shape[0],) + pmask.shape[2:] and weight.shape == rmask.shape and
+                weight.is_cuda and rmask.is_cuda and self.log_var.is_cuda and not weight.requires_grad):
+            return _CEDiceFn.apply(pmask, rmask, weight, self.log_var)
         loss_ce = (self.ce(pmask, rmask) * weight).mean()
         p = pmask.softmax(dim=1)[:, 1:].sum(dim=1)
         loss = loss_ce + self.dice(p, (rmask > 0))
