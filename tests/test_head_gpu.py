@@ -423,6 +423,47 @@ def test_fused_weighted_mse_loss_vs_oracle(dev):
     np.testing.assert_allclose(float(loss), float(l2), rtol=1e-5)
 
 
+@pytest.mark.parametrize("nb,c,h,w,log_var", [(4, 7, 256, 256, 0.3), (3, 2, 33, 17, -0.4), (1, 16, 8, 40, 0.0)])
+def test_fused_ce_dice_loss_vs_fp64_formula(dev, monkeypatch, nb, c, h, w, log_var):
+    """N4: `CE_DICE_adapt_weight` (selfloss.py:145-168, Dice :6-17) as the fused `bhsr_ce_dice` kernel: loss, d loss /
+    d logits and d loss / d log_var against the reference's formula evaluated by stock torch ops in fp64 — and against
+    the same module with the kernel switched off (fp32 stock ops, what round 1 ran)."""
+    from bhsr import dp
+    rng = np.random.RandomState(9 + c)
+    z = (rng.standard_normal((nb, c, h, w)) * 3).astype(np.float32)
+    t = (rng.randint(0, c, (nb, h, w)) * (rng.rand(nb, h, w) > 0.6)).astype(np.int64)      # ~60 % background
+    wt = (0.1 + 3 * rng.rand(nb, h, w)).astype(np.float32)
+
+    zd = torch.from_numpy(z).double().requires_grad_(True)
+    lv = torch.tensor(float(log_var), dtype=torch.float64, requires_grad=True)
+    ce = (torch.nn.functional.cross_entropy(zd, torch.from_numpy(t), reduction="none") * torch.from_numpy(wt).double()).mean()
+    p = zd.softmax(dim=1)[:, 1:].sum(dim=1)
+    m2 = (torch.from_numpy(t) > 0).double()
+    dice = 1 - (2.0 * (p * m2).sum() + 1.0) / (p.sum() + m2.sum() + 1.0)
+    ref = (ce + dice) * torch.exp(-lv) + lv
+    (ref * 1.5).backward()
+
+    crit = dp.CE_DICE_adapt_weight(log_var, dev)
+    zg = cuda(z, dev).requires_grad_(True)
+    loss = crit(zg, cuda(t, dev), cuda(wt, dev))
+    assert loss.grad_fn is not None and "CEDice" in type(loss.grad_fn).__name__      # the fused path ran
+    (loss * 1.5).backward()
+    np.testing.assert_allclose(float(loss), float(ref), rtol=1e-5)
+    gref = zd.grad.numpy()
+    assert_close(zg.grad.cpu().numpy(), gref, rtol=1e-4, atol=1e-6 * float(np.abs(gref).max()), what="d loss / d logits")
+    np.testing.assert_allclose(float(crit.log_var.grad), float(lv.grad), rtol=1e-5, atol=1e-7)
+
+    monkeypatch.setattr(dp, "FUSED_CE_DICE", False)
+    crit2 = dp.CE_DICE_adapt_weight(log_var, dev)
+    z2 = cuda(z, dev).requires_grad_(True)
+    l2 = crit2(z2, cuda(t, dev), cuda(wt, dev))
+    assert "CEDice" not in type(l2.grad_fn).__name__
+    (l2 * 1.5).backward()
+    np.testing.assert_allclose(float(loss), float(l2), rtol=1e-5)
+    assert_close(zg.grad.cpu().numpy(), z2.grad.cpu().numpy(), rtol=1e-3, atol=1e-5 * float(np.abs(gref).max()),
+                 what="fused vs stock-op gradient")
+
+
 @pytest.mark.parametrize("training", [False, True])
 def test_hrfuse_ablation_heads_vs_golden(dev, golden, training):
     """HRfuse / HRfuse_x2 (SR/HRfuse.py:47-89) against the reference modules' outputs."""
