@@ -7,6 +7,9 @@
   unscaled (proposed): lo stored unscaled (fp16 subnormals), weights pre-scaled by 2^8; the three
            products accumulate into ONE fp32 accumulator, the epilogue multiplies by 2^-8.
   fast     one fp16 product.
+  fp8corr  (probe, round 2): fp16 main product + BOTH correction products on the fp8 tensor path (e4m3 operands, 2x the
+           fp16 rate): 2 product-equivalents instead of 3 — would lift the exact path's 33 % ceiling to 50 %.
+  fp8half  (probe, round 2): fp16 main + fp16 hi*lo' + fp8 lo'*hi: 2.5 product-equivalents.
 
 Prints max |err| / (1e-4 + 1e-3 |ref|) of the [1,64,256,256] feature map against fp32 for random-init
 weights and (when present) the shipped RealESRGAN_x4plus checkpoint.
@@ -25,6 +28,15 @@ def h16(t):
     return t.to(torch.float16).to(torch.float32)
 
 
+def e4m3(t):
+    """Round to fp8 e4m3 with a per-tensor power-of-two scale that puts max|t| just under the format's 448."""
+    amax = float(t.abs().max())
+    if amax == 0.0:
+        return t
+    sc = 2.0 ** (8 - int(torch.ceil(torch.log2(torch.tensor(amax))).item()))     # amax * sc in (128, 256]
+    return (t * sc).to(torch.float8_e4m3fn).to(torch.float32) / sc
+
+
 def conv(x, w, b, mode):
     if mode == "fp32":
         return F.conv2d(x, w, b, padding=1)
@@ -35,6 +47,16 @@ def conv(x, w, b, mode):
         wh = h16(w); wl = h16((w - wh) * 2048.0)
         main = F.conv2d(xh, wh, None, padding=1)
         corr = F.conv2d(torch.cat((xh, xl), 1), torch.cat((wl, wh), 1), None, padding=1)
+        out = main + corr / 2048.0
+        return out + b.view(1, -1, 1, 1) if b is not None else out
+    if mode in ("fp8corr", "fp8half"):
+        xh = h16(x); xl = (x - xh) * 2048.0
+        wh = h16(w); wl = (w - wh) * 2048.0
+        main = F.conv2d(xh, wh, None, padding=1)
+        if mode == "fp8corr":
+            corr = F.conv2d(torch.cat((e4m3(xh), e4m3(xl)), 1), torch.cat((e4m3(wl), e4m3(wh)), 1), None, padding=1)
+        else:
+            corr = F.conv2d(xh, h16(wl), None, padding=1) + F.conv2d(e4m3(xl), e4m3(wh), None, padding=1)
         out = main + corr / 2048.0
         return out + b.view(1, -1, 1, 1) if b is not None else out
     if mode == "unscaled":
@@ -84,7 +106,7 @@ def main():
     with torch.no_grad():
         for name, p in nets.items():
             ref = forward_feature(x, p, "fp32")
-            for mode in ("scaled", "unscaled", "fast"):
+            for mode in (sys.argv[1:] or ("scaled", "unscaled", "fast")):
                 got = forward_feature(x, p, mode)
                 err = (got - ref).abs()
                 tol = 1e-4 + 1e-3 * ref.abs()
