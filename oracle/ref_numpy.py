@@ -324,3 +324,32 @@ def mse_adapt_weight(pred: np.ndarray, target: np.ndarray, weight: np.ndarray, l
     mean = (w * d * d).mean()
     prec = np.exp(-float(log_var))
     return mean * prec + float(log_var), 2.0 * w * d * prec / d.size, 1.0 - mean * prec
+
+
+def ce_dice_adapt_weight(logits: np.ndarray, labels: np.ndarray, weight: np.ndarray, log_var: float):
+    """CE_DICE_adapt_weight.forward (losses_pytorch/selfloss.py:145-168, Dice :6-17) with its gradients (float64):
+    loss = (mean(weight * CE(logits, labels)) + Dice(p, labels > 0)) * exp(-log_var) + log_var with
+    p = softmax(logits)[:, 1:].sum(1) and Dice(m1, m2) = 1 - (2 sum(m1 m2) + 1) / (sum(m1) + sum(m2) + 1).
+    logits [N,C,H,W], labels [N,H,W] int in [0, C), weight [N,H,W].  Returns loss, d loss/d logits, d loss/d log_var."""
+    z = logits.astype(np.float64)
+    t = labels.astype(np.int64)
+    w = weight.astype(np.float64)
+    c = z.shape[1]
+    e = np.exp(z - z.max(axis=1, keepdims=True))
+    sm = e / e.sum(axis=1, keepdims=True)
+    onehot = np.moveaxis(np.eye(c)[t], -1, 1)
+    ce = -np.log((sm * onehot).sum(axis=1))
+    loss_ce = (ce * w).mean()
+    p = 1.0 - sm[:, 0]
+    m2 = (t > 0).astype(np.float64)
+    inter, den = (p * m2).sum(), p.sum() + m2.sum() + 1.0
+    dice = 1.0 - (2.0 * inter + 1.0) / den
+    prec = np.exp(-float(log_var))
+    loss = (loss_ce + dice) * prec + float(log_var)
+    # d dice / d p_i = (2 inter + 1) / den^2 - 2 m2_i / den;  d p / d z_c = softmax_0 (softmax_c - [c == 0])
+    ddice_dp = (2.0 * inter + 1.0) / den ** 2 - 2.0 * m2 / den
+    first = np.zeros((1, c, 1, 1))
+    first[0, 0] = 1.0
+    grad = prec * ((w / ce.size)[:, None] * (sm - onehot) + (ddice_dp * sm[:, 0])[:, None] * (sm - first))
+    return loss, grad, 1.0 - (loss_ce + dice) * prec
+

@@ -81,6 +81,37 @@ def test_losses_match_their_closed_forms():
     assert abs(val.item() - ref.item()) < 1e-6
 
 
+@pytest.mark.parametrize("c,log_var", [(7, 0.3), (2, -0.5), (16, 0.0)])
+def test_ce_dice_oracle_gradients_match_torch_autograd(c, log_var):
+    """oracle.ce_dice_adapt_weight (the closed-form gradients the fused `bhsr_ce_dice` kernel implements,
+    selfloss.py:145-168) against stock autograd of the reference's formula in fp64, and the host path of
+    dp.CE_DICE_adapt_weight against both."""
+    import bhsr  # noqa: F401
+    from bhsr import dp
+    from oracle import ref_numpy as R
+    rng = np.random.RandomState(c)
+    z = (rng.standard_normal((3, c, 9, 5)) * 3).astype(np.float32)
+    t = (rng.randint(0, c, (3, 9, 5)) * (rng.rand(3, 9, 5) > 0.5)).astype(np.int64)
+    w = (0.1 + 3 * rng.rand(3, 9, 5)).astype(np.float32)
+    zd = torch.from_numpy(z).double().requires_grad_(True)
+    lv = torch.tensor(float(log_var), dtype=torch.float64, requires_grad=True)
+    ce = (torch.nn.functional.cross_entropy(zd, torch.from_numpy(t), reduction="none") * torch.from_numpy(w).double()).mean()
+    p = zd.softmax(dim=1)[:, 1:].sum(dim=1)
+    m2 = (torch.from_numpy(t) > 0).double()
+    ref = (ce + 1 - (2.0 * (p * m2).sum() + 1.0) / (p.sum() + m2.sum() + 1.0)) * torch.exp(-lv) + lv
+    ref.backward()
+    loss, grad, glv = R.ce_dice_adapt_weight(z, t, w, log_var)
+    assert abs(loss - ref.item()) < 1e-12
+    np.testing.assert_allclose(grad, zd.grad.numpy(), rtol=1e-10, atol=1e-15)
+    assert abs(glv - lv.grad.item()) < 1e-12
+    crit = dp.CE_DICE_adapt_weight(log_var, device="cpu")
+    zc = torch.from_numpy(z).requires_grad_(True)
+    val = crit(zc, torch.from_numpy(t), torch.from_numpy(w))
+    val.backward()
+    assert abs(val.item() - loss) < 1e-5 * max(1.0, abs(loss))
+    np.testing.assert_allclose(zc.grad.numpy(), grad, rtol=1e-4, atol=1e-7)
+
+
 def test_bucket_guards_against_detached_grads():
     import bhsr  # noqa: F401
     from bhsr import dp
