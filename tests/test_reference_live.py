@@ -59,6 +59,24 @@ def test_staged_files_are_the_manifest(ref):
 
 
 @needs_ref
+def test_staged_reference_does_not_shadow_the_drop_in_import_paths(ref):
+    """Loading the staged reference leaves `SR.*`, `mymodels` and `aggregate_utils` resolving to this repo's drop-in
+    modules (the reference is imported under private names), so product code can never pick it up by accident."""
+    import importlib
+    import sys
+    ours = importlib.import_module("SR.rrdbnet_arch")
+    assert os.path.realpath(ours.__file__).startswith(os.path.realpath(ROOT) + os.sep + "SR")
+    assert os.path.realpath(ref.arch.__file__).startswith(os.path.realpath(ref.root))
+    assert ours.RRDBNet is not ref.arch.RRDBNet
+    assert importlib.import_module("aggregate_utils").__file__ != ref.aggregate.__file__
+    pkg = importlib.import_module("bhsr")
+    for name, mod in list(sys.modules.items()):
+        f = getattr(mod, "__file__", None) or ""
+        if name.startswith(pkg.__name__ + ".") or name.startswith("bhsr."):
+            assert "baseline" + os.sep + "_ref" not in f and os.sep + "oracle" + os.sep not in f, name
+
+
+@needs_ref
 @pytest.mark.parametrize("scale,num_block,seed", [(4, 2, 11), (2, 1, 12), (1, 1, 13)])
 def test_oracle_rrdbnet_vs_live_reference(ref, scale, num_block, seed):
     """oracle/ref_torch.py == the reference modules, bit for bit (forward_feature and forward, every scale's
